@@ -1,0 +1,175 @@
+/*
+ * zg_b200.h -- C-ABI of the B200-native (sm_100a) GPT-2 forward/decode path that replaces the
+ * CPU arithmetic of EugenHotaj/zig_gpt2 behind its own operator surface.
+ *
+ * The reference has exactly two FFI imports: CBLAS (src/ops.zig:2, used at :30,:268,:289) and
+ * regex.h (src/bpe.zig:2).  This header replaces the CBLAS import: the Zig host keeps the
+ * reference's structs and method signatures (src/ops.zig:4-307, src/main.zig:5-342) and each
+ * `forward` body becomes one call below.  Slices become (pointer, length) pairs whose pointers
+ * are DEVICE pointers obtained from zg_alloc(); the host never dereferences them.  The struct
+ * layouts below are the reference's struct fields in declaration order, so a Zig `extern struct`
+ * with the same fields is ABI-compatible.
+ *
+ * Rules kept from the reference:
+ *   - no allocation after start-up (README.md "No memory allocations at runtime"): only
+ *     zg_init / zg_alloc / zg_engine_create / zg_batch_create allocate; every hot-path entry
+ *     point takes caller-owned buffers and enqueues kernels on one stream;
+ *   - hot-path calls return void (Zig `void`); failures are sticky and read with zg_last_error();
+ *   - the caller is single-threaded per device.
+ *
+ * There is no CPU fallback: every entry point launches hand-written CUDA kernels and fails
+ * (sticky error, non-zero status from init calls) when no sm_100 device is present.
+ */
+#ifndef ZG_B200_H
+#define ZG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------------------------------------
+ * Lifecycle / memory (start-up only).  Status: 0 = ok, otherwise a cudaError_t value.
+ * ------------------------------------------------------------------------------------------- */
+int zg_init(int device);            /* select device, create the stream and scratch; idempotent */
+int zg_shutdown(void);
+int zg_device_count(void);
+int zg_sm_count(void);
+void *zg_alloc(size_t bytes);       /* replaces allocator.alloc() for tensors (ops.zig:314, main.zig:48-60,298-299) */
+int zg_free(void *dev_ptr);
+int zg_memset(void *dev_ptr, int value, size_t bytes);
+int zg_upload(void *dst_dev, const void *src_host, size_t bytes);   /* replaces fd.readAll into the slice (ops.zig:318) */
+int zg_download(void *dst_host, const void *src_dev, size_t bytes); /* synchronises the stream first */
+int zg_sync(void);
+int zg_last_error(void);            /* sticky; 0 when clean */
+const char *zg_last_error_string(void);
+void zg_clear_error(void);
+/* Use an externally owned CUDA stream (e.g. torch's current stream) for subsequent calls; NULL restores the library's. */
+int zg_set_stream(void *cuda_stream);
+/* Number of kernels this library has launched since zg_init (bench.py's gpu_launches). */
+unsigned long long zg_launch_count(void);
+/* CUDA-event stopwatch on the library's stream (bench.py times kernels on the stream they are launched on). */
+int zg_timer_begin(void);
+float zg_timer_end_ms(void); /* records the stop event, synchronises, returns elapsed milliseconds */
+
+/* ---------------------------------------------------------------------------------------------
+ * ops.zig
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { /* ops.zig:4-19 */
+  size_t in_features, out_features;
+  const float *weight; /* device, [out_features, in_features] row-major */
+  const float *bias;   /* device or NULL */
+} zg_linear;
+/* Linear.forward, ops.zig:21-46: outputs[M,N] = bias + inputs[M,K] weight[N,K]^T, M = inputs_len / in_features.
+ * fp32 SIMT path (warp-per-row GEMV, exact fp32 accumulation). */
+void zg_linear_forward(const zg_linear *self, const float *inputs, size_t inputs_len, float *outputs);
+
+typedef struct { size_t emb_dim; const float *weight; } zg_embedding; /* ops.zig:49-57 */
+/* Embedding.forward, ops.zig:59-67.  `idxs` is a HOST array of 64-bit indices (the reference passes
+ * `&[1]usize{token}`, main.zig:179-180); `embeddings` is a device pointer. */
+void zg_embedding_forward(const zg_embedding *self, const size_t *idxs, size_t n_idxs, float *embeddings);
+
+typedef struct { size_t n_features; const float *weight, *bias; float eps; } zg_layer_norm; /* ops.zig:70-80 */
+void zg_layer_norm_forward(const zg_layer_norm *self, float *inputs, size_t inputs_len); /* ops.zig:82-104, in place */
+
+typedef struct { /* ops.zig:107-124 */
+  size_t n_heads, n_embed, head_dim;
+  zg_linear c_attn, c_proj;
+} zg_attention;
+/* CausalSelfAttention.forward, ops.zig:129-173: one new token, cache append at row seq_len-1.
+ * The scratch arguments keep the reference's meaning; _k/_v/_attn are accepted and left untouched
+ * (the fused kernel reads the time-major cache in place instead of transposing it every token). */
+void zg_attention_forward(const zg_attention *self, size_t seq_len, const float *inputs, float *k_cache,
+                          float *v_cache, float *outputs, float *_qkv, float *_q, float *_k, float *_v,
+                          float *_attn);
+void zg_split_qkv(const zg_attention *self, size_t seq_len, const float *inputs, size_t inputs_len,
+                  size_t split_idx, float *outputs);                                      /* ops.zig:177-196 */
+void zg_transpose(const size_t shape[3], const float *inputs, size_t inputs_len, float *outputs); /* ops.zig:199-216 */
+void zg_gelu(float *inputs, size_t n);    /* ops.zig:221-228, in place */
+void zg_softmax(float *inputs, size_t n); /* ops.zig:231-241, in place over the whole slice */
+/* scaled_dot_product_attention, ops.zig:249-307: q[B,n,1,hd], k/v[B,n,T,hd] -> outputs[B,n,1,hd]. */
+void zg_sdpa(const float *q, const float *k, size_t k_len, const float *v, size_t n_heads, size_t seq_len,
+             size_t head_dim, float *outputs, float *_attn);
+
+/* ---------------------------------------------------------------------------------------------
+ * main.zig
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { size_t vocab_size, context_size, n_layer, n_heads, n_embed; } zg_config; /* main.zig:5-23 */
+
+typedef struct { /* main.zig:26-65; every float* is a device pointer, `decoded` is host memory */
+  float *pos_emb, *x, *o, *logits;
+  unsigned char *decoded;
+  float *_h, *_4xh, *_qkv, *_q, *_k, *_v, *_attn;
+} zg_state;
+/* State.init, main.zig:46-64, with zg_alloc as the allocator.  _k/_v (2 x context x n_embed floats of
+ * transposed-cache scratch in the reference) are allocated only if want_transpose_scratch != 0. */
+int zg_state_init(zg_state *s, const zg_config *c, int want_transpose_scratch);
+void zg_state_free(zg_state *s);
+
+typedef struct { zg_linear c_fc, c_proj; } zg_mlp; /* main.zig:67-83 */
+typedef struct { /* main.zig:85-117 */
+  size_t n_embed;
+  zg_layer_norm ln_1;
+  zg_attention attn;
+  zg_layer_norm ln_2;
+  zg_mlp mlp;
+  float *k_cache, *v_cache; /* device, [context_size, n_embed] time-major, heads interleaved (main.zig:298-299) */
+} zg_block;
+typedef struct { /* main.zig:149-176 */
+  zg_config config;
+  zg_embedding wte, wpe;
+  const zg_block *h; /* host array of n_layer blocks */
+  zg_layer_norm ln_f;
+  zg_linear lm_head; /* weight tied to wte.weight, no bias (main.zig:312) */
+} zg_gpt;
+
+void zg_mlp_forward(const zg_mlp *self, const float *inputs, size_t inputs_len, const zg_state *state); /* main.zig:78-82 */
+void zg_block_forward(const zg_block *self, size_t seq_len, const float *inputs, const zg_state *state); /* main.zig:119-146 */
+/* GPT.forward, main.zig:178-195, op by op (one kernel per reference op). */
+void zg_gpt_forward(const zg_gpt *self, size_t seq_len, size_t token, int compute_logits, const zg_state *state);
+/* GPT.sample, main.zig:198-207: temperature softmax + inverse-CDF draw on the device; `u` in [0,1) replaces
+ * the reference's wall-clock-seeded PRNG draw.  Returns the token id (synchronises). */
+size_t zg_gpt_sample(const zg_gpt *self, size_t seq_len, float temp, size_t token, const zg_state *state, double u);
+size_t zg_gpt_sample_greedy(const zg_gpt *self, size_t seq_len, size_t token, const zg_state *state);
+
+/* Model assembly helpers (main.zig:210-314).  `w` = device pointers in canonical order:
+ * wte, wpe, then per block {ln_1-g, ln_1-b, attn-c_attn-w, -b, attn-c_proj-w, -b, ln_2-g, ln_2-b,
+ * mlp-c_fc-w, -b, mlp-c_proj-w, -b}, then ln_f-g, ln_f-b.  Allocates the block array (host) and the KV caches. */
+size_t zg_weight_count(const zg_config *c);
+size_t zg_weight_elems(const zg_config *c, size_t index);
+int zg_gpt_init(zg_gpt *g, const zg_config *c, const float *const *w);
+void zg_gpt_free(zg_gpt *g);
+/* load_gpt, main.zig:304-314: reads `<raw_dir>/model-<name>` files (headerless LE fp32) straight to the device. */
+int zg_load_gpt(zg_gpt *g, const zg_config *c, const char *raw_dir);
+
+/* ---------------------------------------------------------------------------------------------
+ * The fused decode engine: GPT.forward / GPT.sample / generate (main.zig:178-207,322-342) as ONE
+ * persistent cooperative kernel per call -- every SM streams its share of the weights through a
+ * shared-memory ring (cp.async.bulk + mbarrier) while grid-wide barriers separate the layer phases.
+ * Batch 1, fp32 weights, fp32 accumulation.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct zg_engine zg_engine;
+zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state); /* start-up: descriptor tables, barrier words, pinned token ring */
+void zg_engine_destroy(zg_engine *e);
+void zg_engine_forward(zg_engine *e, size_t seq_len, size_t token, int compute_logits); /* == GPT.forward; logits land in state.logits */
+size_t zg_engine_sample_greedy(zg_engine *e, size_t seq_len, size_t token);             /* forward + argmax; synchronises */
+size_t zg_engine_sample(zg_engine *e, size_t seq_len, float temp, size_t token, double u);
+/* generate(), main.zig:322-342, greedy: steps s in [0, n_total); prompt tokens are forwarded one at a time
+ * without logits, the last prompt token is forwarded twice (as the reference does), every step's token is
+ * written to out_tokens (HOST).  One kernel launch covers all steps; tokens are also streamed into a pinned
+ * host ring as they are produced.  Returns 0 or an error code. */
+int zg_engine_generate_greedy(zg_engine *e, const size_t *inputs, size_t n_inputs, size_t n_total, size_t *out_tokens);
+/* Device-only variant for timing: runs steps [first_step, first_step + n_steps) of a generation whose prompt
+ * (device-resident copy made by zg_engine_set_prompt) has n_inputs tokens.  Asynchronous. */
+int zg_engine_set_prompt(zg_engine *e, const size_t *inputs, size_t n_inputs);
+void zg_engine_run_steps(zg_engine *e, size_t first_step, size_t n_steps);
+int zg_engine_read_tokens(zg_engine *e, size_t first_step, size_t n_steps, size_t *out_tokens);
+/* Per-phase device timestamps of the last launch (ns, CTA 0), for profiling; returns entries written. */
+size_t zg_engine_read_profile(zg_engine *e, unsigned long long *out, size_t max_entries);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZG_B200_H */

@@ -1,0 +1,163 @@
+"""-m gpu: main.zig's MLP / Block / GPT.forward / GPT.sample / generate on the GPU (fused persistent
+engine and op-by-op composition) against the CPU oracle on identical synthetic weights and inputs, and
+against the committed golden logits produced by the reference's PyTorch model."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from zig_gpt2_b200.config import SIZES, GPTConfig  # noqa: E402
+
+FP32_RTOL = 1e-4  # north_star: fp32 <= 1e-4 relative (to the logit scale)
+
+
+@pytest.fixture(scope="module")
+def gpu_124m(weights_124m):
+    from zig_gpt2_b200 import gpt, lib
+
+    lib.init(0)
+    cfg = SIZES["124M"]
+    model = gpt.gpt_from_numpy(cfg, weights_124m)
+    state = gpt.State(cfg)
+    yield model, state
+    model.close()
+
+
+@pytest.fixture(scope="module")
+def oracle_124m(weights_124m):
+    import zg_oracle as zo
+
+    zo.use_openblas()
+    m = zo.Model(SIZES["124M"], weights_124m)
+    yield m
+    m.close()
+    zo.use_scalar_blas()
+
+
+def close(a, b, what, rtol=FP32_RTOL):
+    scale = float(np.abs(b).max())
+    err = float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max())
+    assert err <= rtol * scale, f"{what}: max abs err {err:.3e} > {rtol} * scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_prompt_logits_match_reference_torch_golden(gpu_124m, gpt_golden, fused):
+    model, state = gpu_124m
+    p = gpt_golden["prompt"]
+    fwd = model.forward if fused else model.forward_unfused
+    for s, tok in enumerate(p):
+        fwd(s + 1, int(tok), s == len(p) - 1, state)
+    close(state.logits.download(), gpt_golden["prompt_logits"], f"prompt logits fused={fused}")
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_forward_state_matches_oracle(gpu_124m, oracle_124m, gpt_golden, fused):
+    """state.x (ln_f output), state.o (residual stream), logits and the KV cache rows after each step."""
+    model, state = gpu_124m
+    p = gpt_golden["prompt"][:6]
+    fwd = model.forward if fused else model.forward_unfused
+    for s, tok in enumerate(p):
+        fwd(s + 1, int(tok), True, state)
+        ref_logits = oracle_124m.forward(s + 1, int(tok), True)
+        close(state.logits.download(), ref_logits, f"logits step {s}")
+        close(state.x.download(), oracle_124m.x(), f"state.x step {s}")
+    for layer in (0, 5, 11):
+        k_ref, v_ref = oracle_124m.kv(layer, len(p))
+        E = 768
+        close(model.h[layer].k_cache.download(len(p) * E).reshape(len(p), E), k_ref, f"k_cache layer {layer}")
+        close(model.h[layer].v_cache.download(len(p) * E).reshape(len(p), E), v_ref, f"v_cache layer {layer}")
+
+
+def test_generate_greedy_64_tokens_identical_to_oracle(gpu_124m, oracle_124m, gpt_golden):
+    """BASELINE cfg 1 vs cfg 2: 16-token prompt, 64 greedy tokens, following generate()'s loop exactly
+    (prompt one token at a time without logits, duplicate last prompt token)."""
+    model, state = gpu_124m
+    p = gpt_golden["prompt"]
+    n_total = len(p) + 64
+    ref, ref_logits = oracle_124m.generate_greedy(p, n_total, want_logits=True)
+    got = model.generate_greedy(p, n_total, state)
+    srt = np.sort(ref_logits, axis=1)
+    margins = srt[:, -1] - srt[:, -2]
+    assert np.array_equal(got[: len(p)], p)
+    assert np.array_equal(got, ref), f"first mismatch at {int(np.argmax(got != ref))}; min top-2 margin {margins.min():.3e}"
+    assert np.array_equal(got[len(p): len(p) + 12], gpt_golden["greedy_tokens"])  # the reference torch model agrees too
+
+
+def test_step_by_step_sampling_matches_single_launch(gpu_124m, gpt_golden):
+    model, state = gpu_124m
+    p = [int(t) for t in gpt_golden["prompt"]]
+    one = model.generate_greedy(p, len(p) + 8, state)
+    toks, token = [], 0
+    for s in range(len(p) + 8):
+        if s < len(p):
+            token = p[s]
+            model.forward(s + 1, token, False, state)
+        else:
+            token = model.sample_greedy(s + 1, token, state)
+        toks.append(token)
+    assert toks == [int(t) for t in one]
+    toks2, token = [], 0
+    for s in range(len(p) + 8):
+        if s < len(p):
+            token = p[s]
+            model.forward_unfused(s + 1, token, False, state)
+        else:
+            token = model.sample_greedy(s + 1, token, state, fused=False)
+        toks2.append(token)
+    assert toks2 == toks
+
+
+def test_temperature_sampling_matches_oracle_inverse_cdf(gpu_124m, oracle_124m, gpt_golden):
+    model, state = gpu_124m
+    p = [int(t) for t in gpt_golden["prompt"][:5]]
+    for s, tok in enumerate(p[:4]):
+        model.forward(s + 1, tok, False, state)
+        oracle_124m.forward(s + 1, tok, False)
+    for u in (0.0, 0.3, 0.77, 0.999):
+        got = model.sample(5, 0.8, p[4], state, u)
+        want = oracle_124m.sample(5, 0.8, p[4], u)
+        assert abs(got - want) <= 1, (u, got, want)  # parallel vs sequential fp32 running sum
+
+
+def test_long_context_attention_splits(weights_124m):
+    """Flash-decoding split path (T > 128): a 2-layer slice of the 124M model run to T = 300."""
+    import zg_oracle as zo
+    from zig_gpt2_b200 import gpt
+
+    cfg = GPTConfig(50257, 1024, 2, 12, 768)
+    model = gpt.gpt_from_numpy(cfg, weights_124m)
+    state = gpt.State(cfg)
+    zo.use_openblas()
+    orc = zo.Model(cfg, weights_124m)
+    rs = np.random.RandomState(9)
+    prompt = rs.randint(0, cfg.vocab_size, 300)
+    got = model.generate_greedy(prompt, 310, state)
+    ref = orc.generate_greedy(prompt, 310)
+    assert np.array_equal(got, ref)
+    close(model.h[1].k_cache.download(310 * 768), orc.kv(1, 310)[0].reshape(-1), "k_cache at T=310")
+    model.close()
+    orc.close()
+
+
+@pytest.mark.parametrize("size,n_layer", [("355M", 3), ("774M", 2), ("1.5B", 2)])
+def test_other_widths_truncated_depth(size, n_layer):
+    """E = 1024 / 1280 / 1600 (H = 16 / 20 / 25) with the layer count cut down so the oracle stays fast."""
+    import zg_oracle as zo
+    from zig_gpt2_b200 import gpt
+    from zig_gpt2_b200.weights import synth_weights
+
+    full = SIZES[size]
+    cfg = GPTConfig(full.vocab_size, full.context_size, n_layer, full.n_heads, full.n_embed)
+    w = synth_weights(cfg, seed=77)
+    model = gpt.gpt_from_numpy(cfg, w)
+    state = gpt.State(cfg)
+    zo.use_openblas()
+    orc = zo.Model(cfg, w)
+    prompt = np.random.RandomState(1).randint(0, cfg.vocab_size, 9)
+    ref, ref_logits = orc.generate_greedy(prompt, 20, want_logits=True)
+    got = model.generate_greedy(prompt, 20, state)
+    assert np.array_equal(got, ref)
+    model.forward(20 + 1, int(got[-1]), True, state)
+    close(state.logits.download(), orc.forward(21, int(ref[-1]), True), f"{size} logits")
+    model.close()
+    orc.close()

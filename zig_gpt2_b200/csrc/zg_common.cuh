@@ -1,0 +1,93 @@
+// zg_common.cuh -- shared host/device helpers for the sm_100a kernels behind include/zg_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/zg_b200.h"
+
+namespace zg {
+
+// ---- runtime context (one per process; the reference is single-threaded, main.zig:344-371) ----
+struct Context {
+  bool ready = false;
+  int device = -1;
+  int sm_count = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  int last_error = 0;
+  char last_error_msg[256] = {0};
+  unsigned long long launches = 0;
+  // start-up scratch
+  size_t *idx_staging = nullptr;  // device, for Embedding.forward with many indices
+  size_t idx_staging_cap = 0;
+  float *scratch = nullptr;  // device scratch for split-KV partials etc.
+  size_t scratch_floats = 0;
+  unsigned long long *token_slot = nullptr;  // device, 1 x u64 (argmax / sample result)
+  unsigned long long *token_slot_host = nullptr;  // pinned
+};
+Context &ctx();
+void set_error(int code, const char *what, const char *file, int line);
+bool require_ready(const char *fn);
+
+#define ZG_CUDA(expr)                                                   \
+  do {                                                                  \
+    cudaError_t _e = (expr);                                            \
+    if (_e != cudaSuccess) ::zg::set_error((int)_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define ZG_LAUNCH_CHECK()                                               \
+  do {                                                                  \
+    ::zg::ctx().launches++;                                             \
+    cudaError_t _e = cudaGetLastError();                                \
+    if (_e != cudaSuccess) ::zg::set_error((int)_e, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+// ---- device helpers ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// streaming 128-bit read-only load that does not allocate in L1 (weights are read once per token)
+__device__ __forceinline__ float4 ld_stream(const float4 *p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+// The reference's GELU, ops.zig:225: 0.5 x (1 + tanh(x * 0.7978845608 * (1 + 0.044715 x^2)))
+__device__ __forceinline__ float gelu_ref(float x) {
+  return 0.5f * x * (1.0f + tanhf(x * 0.7978845608f * (1.0f + 0.044715f * x * x)));
+}
+// block-wide sum / max over blockDim.x threads (multiple of 32, <= 1024); `red` is 32 floats of smem
+__device__ __forceinline__ float block_sum(float v, float *red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.0f;
+  return warp_sum(t);
+}
+__device__ __forceinline__ float block_max(float v, float *red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : -INFINITY;
+  return warp_max(t);
+}
+#endif
+
+}  // namespace zg

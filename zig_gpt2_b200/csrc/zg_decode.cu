@@ -1,0 +1,944 @@
+// zg_decode.cu -- the fused batch-1 decode engine: GPT.forward / GPT.sample / generate
+// (src/main.zig:178-207, 322-342) as ONE persistent cooperative kernel.
+//
+// Design (B200, 148 SMs, HBM-bound: 495 MB of fp32 weights per token at 124M):
+//   * one CTA per SM, 8 consumer warps + 1 producer warp;
+//   * the producer warp streams this CTA's share of every weight matrix, in execution order, through a
+//     shared-memory ring with cp.async.bulk (UBLKCP) + mbarrier complete_tx, L2 evict-first.  The stream
+//     does not depend on activations, so it runs ahead across layer phases, tokens and grid barriers and
+//     keeps HBM busy while consumers synchronise;
+//   * consumers take weight rows from the ring (conflict-free 128-bit LDS), dot them with the activation
+//     vector held in shared memory, reduce with warp shuffles, and apply the fused epilogue
+//     (bias, GELU, residual add, KV-cache append, running argmax);
+//   * five grid-wide barriers per layer separate the phases
+//        P1 LN1 + c_attn (+ K/V append)   ops.zig:143-158, main.zig:121-123
+//        P2 attention over the time-major cache (flash-decoding splits when T is long)  ops.zig:160-171
+//        P3 attn c_proj + residual         ops.zig:172, main.zig:136-139
+//        P4 LN2 + c_fc + GELU              main.zig:140, :79-80
+//        P5 mlp c_proj + residual          main.zig:81, :142-145
+//     then ln_f + tied lm_head + argmax (main.zig:189-194);
+//   * the token loop of generate() runs inside the kernel; each token is written to device memory and to a
+//     pinned host ring, so the host only waits once per call.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "zg_common.cuh"
+
+namespace zg {
+void launch_softmax_temp(float *x, size_t n, float temp);
+void launch_weighted_index(const float *p, size_t n, float u, unsigned long long *out);
+
+constexpr int NCW = 8;             // consumer warps
+constexpr int NCT = NCW * 32;      // consumer threads
+constexpr int NTHREADS = NCT + 32; // + producer warp
+constexpr int MAXSLOTS = 32;
+constexpr int UB = 8;              // ring units accumulated per reduction round
+constexpr int ATT_CHUNK = 128;     // KV rows per attention work item before splitting
+constexpr int PROF_MAX = 4096;
+
+struct LayerDesc {
+  const float *ln1_g, *ln1_b, *w_attn, *b_attn, *w_proj, *b_proj, *ln2_g, *ln2_b, *w_fc, *b_fc, *w_proj2, *b_proj2;
+  float *k_cache, *v_cache;
+};
+
+struct DecodeParams {
+  int E, H, hd, L, V, C;
+  int nslot, slotf;  // ring geometry: slotf = 4E floats per slot
+  const float *wte, *wpe, *lnf_g, *lnf_b;
+  const LayerDesc *layers;
+  float *xres;    // [E]  residual stream (state.o; the reference leaves the pre-ln_f stream there too)
+  float *xout;    // [E]  ln_f output (state.x)
+  float *q;       // [E]  (state._q)
+  float *att;     // [E]  attention output (state._h)
+  float *f;       // [4E] (state._4xh)
+  float *logits;  // [V]  (state.logits)
+  float *att_part;        // [H][S][hd+2] flash-decoding partials
+  unsigned *head_count;   // [H] arrival counters for the split combine
+  unsigned *bar;          // grid barrier word (monotonic)
+  unsigned bar_base;
+  float *amax_val;        // [G]
+  unsigned *amax_idx;     // [G]
+  const unsigned long long *prompt;  // device, n_prompt entries; null => `single_token` is the forced token
+  unsigned long long single_token;
+  int n_prompt;
+  unsigned long long *tokens;              // device [C]: token forwarded/sampled at every step
+  volatile unsigned long long *tokens_host;  // pinned host ring [C]
+  unsigned long long *last_token;          // device: argmax of the last logits computed
+  int first_step, n_steps;
+  int force_logits;   // compute logits + argmax on every step (GPT.forward(compute_logits=true) on a prompt step)
+  int store_logits;   // also write the logits vector to global memory
+  int write_xout;     // write ln_f(x) to xout (state.x) on the last step
+  unsigned long long *prof;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Watchdog: a protocol bug must not hang the GPU.  After ~2 s of waiting the kernel raises the sticky
+// error word (bar[1]) and every later wait falls through; the host reports the failure after the sync.
+constexpr long long WATCHDOG_CYCLES = 4000000000ll;
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, unsigned *err) {
+  if (*reinterpret_cast<volatile unsigned *>(err)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > WATCHDOG_CYCLES || *reinterpret_cast<volatile unsigned *>(err)) {
+      atomicExch(err, 2u);
+      return;
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned *err) {
+  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity, err);
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// bulk global -> shared copy (SASS: UBLKCP), completion signalled on an mbarrier as transaction bytes
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+struct Pipe {
+  int slot;
+  uint32_t parity;
+  __device__ __forceinline__ void advance(int nslot) {
+    if (++slot == nslot) {
+      slot = 0;
+      parity ^= 1u;
+    }
+  }
+};
+
+// rows [r0, r1) of an N-row matrix owned by this CTA in a phase; `rot` rotates which CTAs get the remainder rows
+__device__ __forceinline__ void row_range(int cta, int G, int rot, int N, int &r0, int &r1) {
+  int c = cta + rot;
+  if (c >= G) c -= G;
+  r0 = (int)(((long long)c * N) / G);
+  r1 = (int)(((long long)(c + 1) * N) / G);
+}
+__device__ __forceinline__ int phase_rot(int layer, int ph, int G) { return ((layer * 5 + ph) * 29) % G; }
+
+struct Smem {
+  float *ring;   // nslot * slotf
+  float *vec;    // 4E: activation vector the GEMV phases read
+  float *xv;     // E: staging for LayerNorm input
+  float *sc;     // C: attention scores
+  float *part;   // UB * NCW (+ attention partials NCW * hd)
+  float *red;    // 64
+  uint32_t full0, empty0;  // shared addresses of mbarrier arrays
+  unsigned *err;           // global sticky watchdog word
+};
+
+// grid-wide barrier among the consumer threads of all CTAs (the producer warp never takes part)
+__device__ __forceinline__ void grid_barrier(const DecodeParams &p, unsigned &target, int G, int &prof_i) {
+  target += (unsigned)G;
+  consumer_sync();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(p.bar, 1u);
+    if ((int)(ld_acquire(p.bar) - target) < 0) {
+      const long long t0 = clock64();
+      unsigned spins = 0;
+      while ((int)(ld_acquire(p.bar) - target) < 0) {
+        if ((++spins & 1023u) == 0 && (clock64() - t0 > WATCHDOG_CYCLES || ld_acquire(p.bar + 1))) {
+          atomicExch(p.bar + 1, 1u);
+          break;
+        }
+      }
+    }
+    if (p.prof && blockIdx.x == 0 && prof_i < PROF_MAX) p.prof[prof_i] = globaltimer();
+  }
+  ++prof_i;
+  consumer_sync();
+}
+
+// n floats (n % 4 == 0) from global memory written by other CTAs (read through L2, never L1) into shared memory
+__device__ __forceinline__ void load_vec4(float *dst_smem, const float *src, int n) {
+  const float4 *s4 = reinterpret_cast<const float4 *>(src);
+  float4 *d4 = reinterpret_cast<float4 *>(dst_smem);
+  for (int i = threadIdx.x; i < (n >> 2); i += NCT) d4[i] = __ldcg(s4 + i);
+}
+
+// LayerNorm of the E-vector `src` (global, read through L2) into smem `dst`; reference formula ops.zig:86-101
+__device__ __forceinline__ void layer_norm_to_smem(const float *src_smem, float *dst, const float *__restrict__ g,
+                                                   const float *__restrict__ b, int E, float eps, float *red) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float s = 0.0f, ss = 0.0f;
+  for (int i = tid; i < E; i += NCT) {
+    const float v = src_smem[i];
+    s += v;
+    ss = fmaf(v, v, ss);
+  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  if (lane == 0) {
+    red[warp] = s;
+    red[NCW + warp] = ss;
+  }
+  consumer_sync();
+  float ts = 0.0f, tss = 0.0f;
+#pragma unroll
+  for (int w = 0; w < NCW; ++w) {
+    ts += red[w];
+    tss += red[NCW + w];
+  }
+  const float n = (float)E;
+  const float mean = ts / n;
+  const float std_ = sqrtf(tss / n - mean * mean + eps);
+  for (int i = tid; i < E; i += NCT) dst[i] = (src_smem[i] - mean) / std_ * __ldg(g + i) + __ldg(b + i);
+  consumer_sync();
+}
+
+// One GEMV phase: this CTA's rows [r0,r1) of W[N,K] (arriving through the ring) dotted with `vec` (smem).
+template <class Epi>
+__device__ __forceinline__ void gemv_phase(const Smem &sm, Pipe &pipe, int nslot, int slotf, int K, int r0, int r1,
+                                           Epi epi) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rps = slotf / K;    // rows per ring unit: 4 (K = E) or 1 (K = 4E)
+  const int seg = slotf / NCW;  // floats of a unit each warp reduces
+  const int seg4 = seg >> 2;
+  const int row_in_unit = (warp * seg) / K;
+  const int spr = NCW / rps;    // warp segments per row
+  const int nrows = r1 - r0;
+  const int n_units = (nrows + rps - 1) / rps;
+  const float4 *vec4 = reinterpret_cast<const float4 *>(sm.vec) + (((warp * seg) % K) >> 2);
+  for (int u0 = 0; u0 < n_units; u0 += UB) {
+    const int nb = min(UB, n_units - u0);
+    float acc[UB];
+#pragma unroll
+    for (int j = 0; j < UB; ++j) {
+      acc[j] = 0.0f;
+      if (j < nb) {
+        const int rows_here = min(rps, nrows - (u0 + j) * rps);
+        mbar_wait(sm.full0 + 8u * pipe.slot, pipe.parity, sm.err);
+        if (row_in_unit < rows_here) {
+          const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)pipe.slot * slotf) + warp * seg4;
+          float a0 = 0.0f, a1 = 0.0f;
+          for (int i = lane; i < seg4; i += 32) {
+            const float4 wv = w4[i];
+            const float4 xv = vec4[i];
+            a0 = fmaf(wv.x, xv.x, a0);
+            a1 = fmaf(wv.y, xv.y, a1);
+            a0 = fmaf(wv.z, xv.z, a0);
+            a1 = fmaf(wv.w, xv.w, a1);
+          }
+          acc[j] = a0 + a1;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sm.empty0 + 8u * pipe.slot);
+        pipe.advance(nslot);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < UB; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < UB; ++j) sm.part[j * NCW + warp] = acc[j];
+    }
+    consumer_sync();
+    if ((int)threadIdx.x < nb * rps) {
+      const int j = threadIdx.x / rps, ri = threadIdx.x % rps;
+      const int r = r0 + (u0 + j) * rps + ri;
+      if (r < r1) {
+        float v = 0.0f;
+        for (int s = 0; s < spr; ++s) v += sm.part[j * NCW + ri * spr + s];
+        epi(r, v);
+      }
+    }
+    consumer_sync();
+  }
+}
+
+// Producer side of one GEMV phase: stream rows [r0,r1) of W[N,K] into the ring.
+__device__ __forceinline__ void produce_phase(const Smem &sm, Pipe &pipe, int nslot, int slotf, const float *W, int K,
+                                              int r0, int r1, uint64_t pol) {
+  const int rps = slotf / K;
+  for (int r = r0; r < r1; r += rps) {
+    const int nr = min(rps, r1 - r);
+    const uint32_t bytes = (uint32_t)nr * (uint32_t)K * 4u;
+    mbar_wait(sm.empty0 + 8u * pipe.slot, pipe.parity ^ 1u, sm.err);
+    const uint32_t fb = sm.full0 + 8u * pipe.slot;
+    mbar_expect_tx(fb, bytes);
+    bulk_g2s(smem_u32(sm.ring + (size_t)pipe.slot * slotf), W + (size_t)r * K, bytes, fb, pol);
+    pipe.advance(nslot);
+  }
+}
+
+// Attention work item (head h, split s of S) over cache rows [t0,t1) -- ops.zig:249-307 without the
+// whole-cache transposes: K/V are read in place from the time-major cache (head stride hd, time stride E).
+__device__ __forceinline__ void attention_item(const DecodeParams &p, const Smem &sm, const LayerDesc &ld, int h,
+                                               int s, int S, int T) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int hd = p.hd, E = p.E;
+  const int chunk = (T + S - 1) / S;
+  const int t0 = s * chunk, t1 = min(T, t0 + chunk), n = t1 - t0;
+  const float scale = 1.0f / sqrtf((float)hd);
+  const float *qh = p.q + h * hd;
+  const float *kh = ld.k_cache + h * hd;
+  const float *vh = ld.v_cache + h * hd;
+  float *po = sm.part + UB * NCW;  // [NCW][hd] per-warp partial outputs
+  float m, l;
+  if (hd == 64) {
+    // fast path (every GPT-2 size): a cache row of one head is 256 B = one float2 per lane
+    const float2 qv = __ldcg(reinterpret_cast<const float2 *>(qh) + lane);
+    for (int t = t0 + warp; t < t1; t += 4 * NCW) {  // 4 rows in flight per warp: overlapped loads + shuffles
+      float a[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int tt = t + u * NCW;
+        a[u] = 0.0f;
+        if (tt < t1) {
+          const float2 kv = __ldcg(reinterpret_cast<const float2 *>(kh + (size_t)tt * E) + lane);
+          a[u] = fmaf(qv.x, kv.x, qv.y * kv.y);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = warp_sum(a[u]);
+      if (lane == 0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (t + u * NCW < t1) sm.sc[t + u * NCW - t0] = a[u] * scale;
+      }
+    }
+    consumer_sync();
+    m = -INFINITY;
+    for (int i = lane; i < n; i += 32) m = fmaxf(m, sm.sc[i]);
+    m = warp_max(m);  // every warp computes the chunk max / sum redundantly (n is at most a few hundred)
+    l = 0.0f;
+    for (int i = lane; i < n; i += 32) l += expf(sm.sc[i] - m);
+    l = warp_sum(l);
+    float2 acc = make_float2(0.0f, 0.0f);
+    for (int t = t0 + warp; t < t1; t += 4 * NCW) {
+      float2 vv[4];
+      float pt[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int tt = t + u * NCW;
+        pt[u] = 0.0f;
+        vv[u] = make_float2(0.0f, 0.0f);
+        if (tt < t1) {
+          vv[u] = __ldcg(reinterpret_cast<const float2 *>(vh + (size_t)tt * E) + lane);
+          pt[u] = expf(sm.sc[tt - t0] - m);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc.x = fmaf(pt[u], vv[u].x, acc.x);
+        acc.y = fmaf(pt[u], vv[u].y, acc.y);
+      }
+    }
+    po[warp * hd + 2 * lane] = acc.x;
+    po[warp * hd + 2 * lane + 1] = acc.y;
+  } else {
+    // generic head_dim: one cache row per warp iteration, hd spread over lanes
+    for (int t = t0 + warp; t < t1; t += NCW) {
+      float a = 0.0f;
+      for (int d = lane; d < hd; d += 32) a = fmaf(__ldcg(qh + d), __ldcg(kh + (size_t)t * E + d), a);
+      a = warp_sum(a);
+      if (lane == 0) sm.sc[t - t0] = a * scale;
+    }
+    consumer_sync();
+    m = -INFINITY;
+    for (int i = lane; i < n; i += 32) m = fmaxf(m, sm.sc[i]);
+    m = warp_max(m);
+    l = 0.0f;
+    for (int i = lane; i < n; i += 32) l += expf(sm.sc[i] - m);
+    l = warp_sum(l);
+    for (int d = lane; d < hd; d += 32) {
+      float a = 0.0f;
+      for (int t = t0 + warp; t < t1; t += NCW) a = fmaf(expf(sm.sc[t - t0] - m), __ldcg(vh + (size_t)t * E + d), a);
+      po[warp * hd + d] = a;
+    }
+  }
+  consumer_sync();
+  if (S == 1) {
+    for (int d = tid; d < hd; d += NCT) {
+      float a = 0.0f;
+#pragma unroll
+      for (int w = 0; w < NCW; ++w) a += po[w * hd + d];
+      p.att[h * hd + d] = a / l;
+    }
+    return;
+  }
+  // flash-decoding partial (m, l, unnormalised o); the last split of this head to arrive combines them
+  float *mine = p.att_part + ((size_t)h * S + s) * (hd + 2);
+  for (int d = tid; d < hd; d += NCT) {
+    float a = 0.0f;
+#pragma unroll
+    for (int w = 0; w < NCW; ++w) a += po[w * hd + d];
+    mine[2 + d] = a;
+  }
+  if (tid == 0) {
+    mine[0] = m;
+    mine[1] = l;
+  }
+  __threadfence();
+  consumer_sync();
+  if (tid == 0) {
+    const unsigned old = atomicAdd(p.head_count + h, 1u);
+    const bool last = (old == (unsigned)(S - 1));
+    if (last) p.head_count[h] = 0u;  // ready for the next layer (ordered by the grid barrier that follows)
+    sm.red[32] = last ? 1.0f : 0.0f;
+    __threadfence();
+  }
+  consumer_sync();
+  if (sm.red[32] != 0.0f) {
+    const float *base = p.att_part + (size_t)h * S * (hd + 2);
+    float M = -INFINITY;
+    for (int i = 0; i < S; ++i) M = fmaxf(M, __ldcg(base + (size_t)i * (hd + 2)));
+    float Lsum = 0.0f;
+    for (int i = 0; i < S; ++i)
+      Lsum += __ldcg(base + (size_t)i * (hd + 2) + 1) * expf(__ldcg(base + (size_t)i * (hd + 2)) - M);
+    for (int d = tid; d < hd; d += NCT) {
+      float a = 0.0f;
+      for (int i = 0; i < S; ++i)
+        a += __ldcg(base + (size_t)i * (hd + 2) + 2 + d) * expf(__ldcg(base + (size_t)i * (hd + 2)) - M);
+      p.att[h * hd + d] = a / Lsum;
+    }
+  }
+}
+
+__device__ __forceinline__ bool step_needs_logits(const DecodeParams &p, int step) {
+  return p.force_logits || step >= p.n_prompt;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const DecodeParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long mbar_store[2 * MAXSLOTS];
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int E = p.E, E4 = 4 * p.E;
+  Smem sm;
+  sm.ring = reinterpret_cast<float *>(smem_raw);
+  sm.vec = sm.ring + (size_t)p.nslot * p.slotf;
+  sm.xv = sm.vec + E4;
+  sm.sc = sm.xv + E;
+  sm.part = sm.sc + p.C;
+  sm.red = sm.part + UB * NCW + NCW * p.hd;
+  sm.full0 = smem_u32(mbar_store);
+  sm.empty0 = smem_u32(mbar_store + MAXSLOTS);
+  sm.err = p.bar + 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.nslot; ++i) {
+      mbar_init(sm.full0 + 8u * i, 1);
+      mbar_init(sm.empty0 + 8u * i, NCW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  Pipe pipe{0, 0u};
+  const int last_step = p.first_step + p.n_steps - 1;
+
+  if (threadIdx.x >= NCT) {
+    // =============================== producer warp ===============================
+    const int lane = threadIdx.x - NCT;
+    const uint64_t pol = policy_evict_first();
+    for (int step = p.first_step; step <= last_step; ++step) {
+      for (int l = 0; l < p.L; ++l) {
+        const LayerDesc &ld = p.layers[l];
+        // pull the layer's small vectors (LayerNorm affine + biases, 13E floats) into L2 ahead of the consumers
+        if (lane < 8) {
+          const float *arr[8] = {ld.ln1_g, ld.ln1_b, ld.b_attn, ld.b_proj, ld.ln2_g, ld.ln2_b, ld.b_fc, ld.b_proj2};
+          const int len[8] = {E, E, 3 * E, E, E, E, E4, E};
+          const int nlines = (len[lane] * 4 + 127) / 128;
+          for (int i = cta; i < nlines; i += G) prefetch_l2(reinterpret_cast<const char *>(arr[lane]) + (size_t)i * 128);
+        }
+        if (lane == 0) {
+          int r0, r1;
+          row_range(cta, G, phase_rot(l, 0, G), 3 * E, r0, r1);
+          produce_phase(sm, pipe, p.nslot, p.slotf, ld.w_attn, E, r0, r1, pol);
+          row_range(cta, G, phase_rot(l, 1, G), E, r0, r1);
+          produce_phase(sm, pipe, p.nslot, p.slotf, ld.w_proj, E, r0, r1, pol);
+          row_range(cta, G, phase_rot(l, 2, G), E4, r0, r1);
+          produce_phase(sm, pipe, p.nslot, p.slotf, ld.w_fc, E, r0, r1, pol);
+          row_range(cta, G, phase_rot(l, 3, G), E, r0, r1);
+          produce_phase(sm, pipe, p.nslot, p.slotf, ld.w_proj2, E4, r0, r1, pol);
+        }
+        __syncwarp();
+      }
+      if (step_needs_logits(p, step) && lane == 0) {
+        int r0, r1;
+        row_range(cta, G, 0, p.V, r0, r1);
+        produce_phase(sm, pipe, p.nslot, p.slotf, p.wte, E, r0, r1, pol);
+      }
+      __syncwarp();
+    }
+    return;
+  }
+
+  // ================================= consumer warps =================================
+  const int tid = threadIdx.x;
+  unsigned target = p.bar_base;
+  int prof_i = 0;
+  if (p.prof && cta == 0 && tid == 0) p.prof[PROF_MAX] = globaltimer();
+  unsigned long long prev_token = 0;
+
+  for (int step = p.first_step; step <= last_step; ++step) {
+    const int pos = step, T = step + 1;  // seq_len = step + 1 (main.zig:333,337)
+    unsigned long long tok;
+    if (step < p.n_prompt) tok = p.prompt ? p.prompt[step] : p.single_token;
+    else if (step == p.first_step) tok = step > 0 ? __ldcg(p.tokens + step - 1) : 0ull;
+    else tok = prev_token;
+    const bool want_logits = step_needs_logits(p, step);
+
+    for (int l = 0; l < p.L; ++l) {
+      const LayerDesc &ld = p.layers[l];
+      int r0, r1;
+      // ---------------- P1: x -> LN1 -> c_attn, K/V straight into the cache ----------------
+      if (l == 0) {  // wte[token] + wpe[pos] (main.zig:179-183), recomputed by every CTA
+        const float *te = p.wte + (size_t)tok * E, *pe = p.wpe + (size_t)pos * E;
+        for (int i = tid; i < E; i += NCT) {
+          const float v = __ldg(te + i) + __ldg(pe + i);
+          sm.xv[i] = v;
+          if (cta == 0) p.xres[i] = v;
+        }
+      } else {
+        load_vec4(sm.xv, p.xres, E);
+      }
+      consumer_sync();
+      layer_norm_to_smem(sm.xv, sm.vec, ld.ln1_g, ld.ln1_b, E, 1e-5f, sm.red);
+      row_range(cta, G, phase_rot(l, 0, G), 3 * E, r0, r1);
+      {
+        float *kc = ld.k_cache + (size_t)pos * E, *vc = ld.v_cache + (size_t)pos * E;
+        const float *bias = ld.b_attn;
+        float *q = p.q;
+        gemv_phase(sm, pipe, p.nslot, p.slotf, E, r0, r1, [=](int r, float v) {
+          v += __ldg(bias + r);
+          if (r < E) q[r] = v;
+          else if (r < 2 * E) kc[r - E] = v;
+          else vc[r - 2 * E] = v;
+        });
+      }
+      grid_barrier(p, target, G, prof_i);
+
+      // ---------------- P2: attention ----------------
+      {
+        int S = (T + ATT_CHUNK - 1) / ATT_CHUNK;
+        const int smax = G / p.H;
+        if (S > smax) S = smax;
+        if (cta < p.H * S) attention_item(p, sm, ld, cta / S, cta % S, S, T);
+      }
+      grid_barrier(p, target, G, prof_i);
+
+      // ---------------- P3: attn c_proj + residual ----------------
+      load_vec4(sm.vec, p.att, E);
+      consumer_sync();
+      row_range(cta, G, phase_rot(l, 1, G), E, r0, r1);
+      {
+        const float *bias = ld.b_proj;
+        float *xres = p.xres;
+        gemv_phase(sm, pipe, p.nslot, p.slotf, E, r0, r1,
+                   [=](int r, float v) { xres[r] = (v + __ldg(bias + r)) + __ldcg(xres + r); });
+      }
+      grid_barrier(p, target, G, prof_i);
+
+      // ---------------- P4: LN2 + c_fc + GELU ----------------
+      load_vec4(sm.xv, p.xres, E);
+      consumer_sync();
+      layer_norm_to_smem(sm.xv, sm.vec, ld.ln2_g, ld.ln2_b, E, 1e-5f, sm.red);
+      row_range(cta, G, phase_rot(l, 2, G), E4, r0, r1);
+      {
+        const float *bias = ld.b_fc;
+        float *f = p.f;
+        gemv_phase(sm, pipe, p.nslot, p.slotf, E, r0, r1,
+                   [=](int r, float v) { f[r] = gelu_ref(v + __ldg(bias + r)); });
+      }
+      grid_barrier(p, target, G, prof_i);
+
+      // ---------------- P5: mlp c_proj + residual ----------------
+      load_vec4(sm.vec, p.f, E4);
+      consumer_sync();
+      row_range(cta, G, phase_rot(l, 3, G), E, r0, r1);
+      {
+        const float *bias = ld.b_proj2;
+        float *xres = p.xres;
+        gemv_phase(sm, pipe, p.nslot, p.slotf, E4, r0, r1,
+                   [=](int r, float v) { xres[r] = (v + __ldg(bias + r)) + __ldcg(xres + r); });
+      }
+      grid_barrier(p, target, G, prof_i);
+    }
+
+    // ---------------- ln_f (+ lm_head + argmax) ----------------
+    const bool need_x = want_logits || (p.write_xout && step == last_step && cta == 0);
+    if (need_x) {
+      load_vec4(sm.xv, p.xres, E);
+      consumer_sync();
+      layer_norm_to_smem(sm.xv, sm.vec, p.lnf_g, p.lnf_b, E, 1e-5f, sm.red);
+      if (p.write_xout && step == last_step && cta == 0)
+        for (int i = tid; i < E; i += NCT) p.xout[i] = sm.vec[i];
+    }
+    unsigned long long out_tok = tok;
+    if (want_logits) {
+      int r0, r1;
+      row_range(cta, G, 0, p.V, r0, r1);
+      float best = -INFINITY;
+      unsigned best_i = 0xffffffffu;
+      {
+        float *logits = (p.store_logits && step == last_step) ? p.logits : nullptr;
+        gemv_phase(sm, pipe, p.nslot, p.slotf, E, r0, r1, [&](int r, float v) {
+          if (logits) logits[r] = v;
+          if (v > best) {  // rows arrive in increasing r per thread, so strict > keeps the first maximum
+            best = v;
+            best_i = (unsigned)r;
+          }
+        });
+      }
+      // epilogue threads all live in warp 0: reduce (value desc, index asc)
+      if (tid < 32) {
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+          const unsigned oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+          if (ov > best || (ov == best && oi < best_i)) {
+            best = ov;
+            best_i = oi;
+          }
+        }
+        if (tid == 0) {
+          p.amax_val[cta] = best;
+          p.amax_idx[cta] = best_i;
+        }
+      }
+      grid_barrier(p, target, G, prof_i);
+      // every CTA reduces the G partials itself: the next step's embedding needs the token everywhere
+      if (tid < 32) {
+        float bv = -INFINITY;
+        unsigned bi = 0xffffffffu;
+        for (int i = tid; i < G; i += 32) {
+          const float ov = __ldcg(p.amax_val + i);
+          const unsigned oi = __ldcg(p.amax_idx + i);
+          if (ov > bv || (ov == bv && oi < bi)) {
+            bv = ov;
+            bi = oi;
+          }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const unsigned oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) {
+            bv = ov;
+            bi = oi;
+          }
+        }
+        if (tid == 0) sm.red[40] = __uint_as_float(bi);
+      }
+      consumer_sync();
+      const unsigned long long amax = (unsigned long long)__float_as_uint(sm.red[40]);
+      if (cta == 0 && tid == 0) *p.last_token = amax;
+      if (step >= p.n_prompt) out_tok = amax;  // generate(): main.zig:335-338
+      consumer_sync();
+    }
+    if (cta == 0 && tid == 0) {
+      p.tokens[step] = out_tok;
+      if (p.tokens_host) p.tokens_host[step] = out_tok;
+    }
+    prev_token = out_tok;
+  }
+  if (p.prof && cta == 0 && tid == 0) {
+    p.prof[PROF_MAX + 1] = globaltimer();
+    p.prof[PROF_MAX + 2] = (unsigned long long)prof_i;
+  }
+}
+
+}  // namespace zg
+
+// =================================================================================================
+// host side
+// =================================================================================================
+using namespace zg;
+
+struct zg_engine {
+  zg_config cfg;
+  zg_state state;
+  DecodeParams base;
+  LayerDesc *layers_dev;
+  unsigned long long *prompt_dev;
+  unsigned long long *tokens_dev;
+  unsigned long long *tokens_host;  // pinned, mapped
+  unsigned long long *tokens_host_devptr;
+  unsigned long long *last_token_dev;
+  unsigned long long *prof_dev;
+  unsigned *bar_dev;
+  unsigned bar_count;  // host mirror of the monotonic barrier word
+  int grid;
+  size_t smem_bytes;
+  int n_prompt;
+  int prof_enabled;
+};
+
+static size_t engine_smem_bytes(const zg_config &c, int nslot) {
+  const size_t E = c.n_embed, hd = E / c.n_heads;
+  const size_t floats = (size_t)nslot * 4 * E + 4 * E + E + c.context_size + UB * NCW + NCW * hd + 64;
+  return floats * sizeof(float);
+}
+
+extern "C" {
+
+zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
+  if (!require_ready("zg_engine_create")) return nullptr;
+  Context &c = ctx();
+  const zg_config &cfg = gpt->config;
+  const size_t E = cfg.n_embed;
+  if (E % 8 != 0 || E / cfg.n_heads * cfg.n_heads != E) {
+    set_error(1, "zg_engine_create: n_embed must be a multiple of 8 and of n_heads", __FILE__, __LINE__);
+    return nullptr;
+  }
+  zg_engine *e = (zg_engine *)calloc(1, sizeof(zg_engine));
+  if (!e) return nullptr;
+  e->cfg = cfg;
+  e->state = *state;
+  e->grid = c.sm_count;
+  if ((size_t)e->grid < cfg.n_heads) {
+    set_error(1, "zg_engine_create: fewer SMs than attention heads", __FILE__, __LINE__);
+    free(e);
+    return nullptr;
+  }
+
+  int max_smem = 0;
+  ZG_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device));
+  int nslot = MAXSLOTS;
+  while (nslot > 2 && engine_smem_bytes(cfg, nslot) + 1024 > (size_t)max_smem) --nslot;
+  if (engine_smem_bytes(cfg, nslot) + 1024 > (size_t)max_smem) {
+    set_error(1, "zg_engine_create: model too wide for the shared-memory ring", __FILE__, __LINE__);
+    free(e);
+    return nullptr;
+  }
+  e->smem_bytes = engine_smem_bytes(cfg, nslot);
+  ZG_CUDA(cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)e->smem_bytes));
+  int per_sm = 0;
+  ZG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persistent_kernel, NTHREADS, e->smem_bytes));
+  if (per_sm < 1) {
+    set_error(1, "zg_engine_create: persistent kernel does not fit on an SM", __FILE__, __LINE__);
+    free(e);
+    return nullptr;
+  }
+
+  // device-side descriptor table (start-up only)
+  LayerDesc *lh = (LayerDesc *)calloc(cfg.n_layer, sizeof(LayerDesc));
+  for (size_t l = 0; l < cfg.n_layer; ++l) {
+    const zg_block &b = gpt->h[l];
+    lh[l] = LayerDesc{b.ln_1.weight, b.ln_1.bias, b.attn.c_attn.weight, b.attn.c_attn.bias, b.attn.c_proj.weight,
+                      b.attn.c_proj.bias, b.ln_2.weight, b.ln_2.bias, b.mlp.c_fc.weight, b.mlp.c_fc.bias,
+                      b.mlp.c_proj.weight, b.mlp.c_proj.bias, b.k_cache, b.v_cache};
+  }
+  e->layers_dev = (LayerDesc *)zg_alloc(cfg.n_layer * sizeof(LayerDesc));
+  zg_upload(e->layers_dev, lh, cfg.n_layer * sizeof(LayerDesc));
+  free(lh);
+
+  const size_t C = cfg.context_size, hd = E / cfg.n_heads;
+  const int smax = e->grid / (int)cfg.n_heads > 0 ? e->grid / (int)cfg.n_heads : 1;
+  e->prompt_dev = (unsigned long long *)zg_alloc(C * 8);
+  e->tokens_dev = (unsigned long long *)zg_alloc(C * 8);
+  e->last_token_dev = (unsigned long long *)zg_alloc(8);
+  e->prof_dev = (unsigned long long *)zg_alloc((PROF_MAX + 4) * 8);
+  e->bar_dev = (unsigned *)zg_alloc(64);
+  float *att_part = (float *)zg_alloc(cfg.n_heads * (size_t)smax * (hd + 2) * sizeof(float));
+  unsigned *head_count = (unsigned *)zg_alloc(cfg.n_heads * sizeof(unsigned));
+  float *amax_val = (float *)zg_alloc(e->grid * sizeof(float));
+  unsigned *amax_idx = (unsigned *)zg_alloc(e->grid * sizeof(unsigned));
+  ZG_CUDA(cudaHostAlloc(&e->tokens_host, C * 8, cudaHostAllocMapped));
+  ZG_CUDA(cudaHostGetDevicePointer((void **)&e->tokens_host_devptr, e->tokens_host, 0));
+  if (zg_last_error()) {
+    free(e);
+    return nullptr;
+  }
+  memset(e->tokens_host, 0xff, C * 8);
+  zg_memset(e->bar_dev, 0, 64);
+  zg_memset(head_count, 0, cfg.n_heads * sizeof(unsigned));
+  zg_memset(e->tokens_dev, 0, C * 8);
+  zg_memset(e->prof_dev, 0, (PROF_MAX + 4) * 8);
+  e->bar_count = 0;
+
+  DecodeParams &p = e->base;
+  memset(&p, 0, sizeof(p));
+  p.E = (int)E; p.H = (int)cfg.n_heads; p.hd = (int)hd; p.L = (int)cfg.n_layer; p.V = (int)cfg.vocab_size; p.C = (int)C;
+  p.nslot = nslot; p.slotf = 4 * (int)E;
+  p.wte = gpt->wte.weight; p.wpe = gpt->wpe.weight; p.lnf_g = gpt->ln_f.weight; p.lnf_b = gpt->ln_f.bias;
+  p.layers = e->layers_dev;
+  p.xres = state->o; p.xout = state->x; p.q = state->_q; p.att = state->_h; p.f = state->_4xh; p.logits = state->logits;
+  p.att_part = att_part; p.head_count = head_count; p.bar = e->bar_dev;
+  p.amax_val = amax_val; p.amax_idx = amax_idx;
+  p.tokens = e->tokens_dev; p.tokens_host = e->tokens_host_devptr; p.last_token = e->last_token_dev;
+  zg_sync();
+  return zg_last_error() ? (free(e), nullptr) : e;
+}
+
+void zg_engine_destroy(zg_engine *e) {
+  if (!e) return;
+  zg_sync();
+  zg_free(e->layers_dev); zg_free(e->prompt_dev); zg_free(e->tokens_dev); zg_free(e->last_token_dev);
+  zg_free(e->prof_dev); zg_free(e->bar_dev); zg_free(e->base.att_part); zg_free(e->base.head_count);
+  zg_free(e->base.amax_val); zg_free(e->base.amax_idx);
+  cudaFreeHost(e->tokens_host);
+  free(e);
+}
+
+}  // extern "C"
+
+// number of grid barriers a launch will execute (the barrier word is monotonic across launches)
+static unsigned barriers_for(const zg_engine *e, const DecodeParams &p) {
+  unsigned n = 0;
+  for (int s = p.first_step; s < p.first_step + p.n_steps; ++s)
+    n += 5u * (unsigned)e->cfg.n_layer + ((p.force_logits || s >= p.n_prompt) ? 1u : 0u);
+  return n;
+}
+
+static void engine_launch(zg_engine *e, DecodeParams &p) {
+  if (p.n_steps <= 0) return;
+  if (p.first_step < 0 || p.first_step + p.n_steps > (int)e->cfg.context_size) {
+    set_error(1, "decode engine: step range exceeds context_size", __FILE__, __LINE__);
+    return;
+  }
+  p.bar_base = e->bar_count;
+  p.prof = e->prof_enabled ? e->prof_dev : nullptr;
+  e->bar_count += barriers_for(e, p) * (unsigned)e->grid;
+  void *args[] = {(void *)&p};
+  ZG_CUDA(cudaLaunchCooperativeKernel((const void *)decode_persistent_kernel, dim3(e->grid), dim3(NTHREADS), args,
+                                      e->smem_bytes, ctx().stream));
+  ctx().launches++;
+}
+
+// after a synchronisation: did the in-kernel watchdog fire (a wait exceeded ~2 s)?
+static int engine_check_watchdog(zg_engine *e) {
+  unsigned w = 0;
+  ZG_CUDA(cudaMemcpyAsync(&w, e->bar_dev + 1, sizeof(w), cudaMemcpyDeviceToHost, ctx().stream));
+  ZG_CUDA(cudaStreamSynchronize(ctx().stream));
+  if (w != 0) {
+    set_error(1, w == 1 ? "decode engine watchdog: grid barrier timed out" : "decode engine watchdog: mbarrier wait timed out",
+              __FILE__, __LINE__);
+    return 1;
+  }
+  return zg_last_error();
+}
+
+extern "C" {
+
+void zg_engine_forward(zg_engine *e, size_t seq_len, size_t token, int compute_logits) {
+  if (!require_ready("zg_engine_forward")) return;
+  const size_t step = seq_len - 1;
+  DecodeParams p = e->base;
+  p.prompt = nullptr;  // the forced token rides in the kernel parameters
+  p.single_token = token;
+  p.n_prompt = (int)step + 1;
+  p.first_step = (int)step;
+  p.n_steps = 1;
+  p.force_logits = compute_logits ? 1 : 0;
+  p.store_logits = compute_logits ? 1 : 0;
+  p.write_xout = 1;
+  engine_launch(e, p);
+}
+
+size_t zg_engine_sample_greedy(zg_engine *e, size_t seq_len, size_t token) {
+  if (!require_ready("zg_engine_sample_greedy")) return (size_t)-1;
+  Context &c = ctx();
+  zg_engine_forward(e, seq_len, token, 1);
+  ZG_CUDA(cudaMemcpyAsync(c.token_slot_host, e->last_token_dev, 8, cudaMemcpyDeviceToHost, c.stream));
+  ZG_CUDA(cudaStreamSynchronize(c.stream));
+  if (engine_check_watchdog(e)) return (size_t)-1;
+  return (size_t)c.token_slot_host[0];
+}
+
+size_t zg_engine_sample(zg_engine *e, size_t seq_len, float temp, size_t token, double u) {
+  if (!require_ready("zg_engine_sample")) return (size_t)-1;
+  Context &c = ctx();
+  zg_engine_forward(e, seq_len, token, 1);
+  launch_softmax_temp(e->state.logits, e->cfg.vocab_size, temp);  // main.zig:200-203
+  launch_weighted_index(e->state.logits, e->cfg.vocab_size, (float)u, c.token_slot);
+  ZG_CUDA(cudaMemcpyAsync(c.token_slot_host, c.token_slot, 8, cudaMemcpyDeviceToHost, c.stream));
+  ZG_CUDA(cudaStreamSynchronize(c.stream));
+  return (size_t)c.token_slot_host[0];
+}
+
+int zg_engine_set_prompt(zg_engine *e, const size_t *inputs, size_t n_inputs) {
+  if (!require_ready("zg_engine_set_prompt")) return 1;
+  if (n_inputs > e->cfg.context_size) return 1;
+  e->n_prompt = (int)n_inputs;
+  if (n_inputs) ZG_CUDA(cudaMemcpyAsync(e->prompt_dev, inputs, n_inputs * 8, cudaMemcpyHostToDevice, ctx().stream));
+  return zg_last_error();
+}
+
+void zg_engine_run_steps(zg_engine *e, size_t first_step, size_t n_steps) {
+  if (!require_ready("zg_engine_run_steps")) return;
+  DecodeParams p = e->base;
+  p.prompt = e->prompt_dev;
+  p.n_prompt = e->n_prompt;
+  p.first_step = (int)first_step;
+  p.n_steps = (int)n_steps;
+  engine_launch(e, p);
+}
+
+int zg_engine_read_tokens(zg_engine *e, size_t first_step, size_t n_steps, size_t *out_tokens) {
+  if (!require_ready("zg_engine_read_tokens")) return 1;
+  if (zg_download(out_tokens, e->tokens_dev + first_step, n_steps * 8)) return zg_last_error();
+  return engine_check_watchdog(e);
+}
+
+int zg_engine_generate_greedy(zg_engine *e, const size_t *inputs, size_t n_inputs, size_t n_total, size_t *out_tokens) {
+  if (!require_ready("zg_engine_generate_greedy")) return 1;
+  if (n_total > e->cfg.context_size || n_inputs > n_total) return 1;
+  if (zg_engine_set_prompt(e, inputs, n_inputs)) return zg_last_error();
+  zg_engine_run_steps(e, 0, n_total);
+  // tokens were streamed into the pinned ring as they were produced; one wait for the whole call
+  ZG_CUDA(cudaStreamSynchronize(ctx().stream));
+  for (size_t i = 0; i < n_total; ++i) out_tokens[i] = (size_t)e->tokens_host[i];
+  return engine_check_watchdog(e);
+}
+
+size_t zg_engine_read_profile(zg_engine *e, unsigned long long *out, size_t max_entries) {
+  if (!require_ready("zg_engine_read_profile")) return 0;
+  if (out == nullptr) {  // toggle: calling with NULL enables profiling for subsequent launches
+    e->prof_enabled = max_entries ? 1 : 0;
+    return 0;
+  }
+  unsigned long long *tmp = (unsigned long long *)malloc((PROF_MAX + 4) * 8);
+  zg_download(tmp, e->prof_dev, (PROF_MAX + 4) * 8);
+  size_t n = (size_t)tmp[PROF_MAX + 2];
+  if (n > PROF_MAX) n = PROF_MAX;
+  size_t w = 0;
+  if (w < max_entries) out[w++] = tmp[PROF_MAX];  // kernel start
+  for (size_t i = 0; i < n && w < max_entries; ++i) out[w++] = tmp[i];
+  if (w < max_entries) out[w++] = tmp[PROF_MAX + 1];  // kernel end
+  free(tmp);
+  return w;
+}
+
+}  // extern "C"
