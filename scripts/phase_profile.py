@@ -1,8 +1,11 @@
-"""Per-phase device timestamps of the persistent decode kernel (CTA 0, %globaltimer at every grid barrier).
-Usage: python scripts/phase_profile.py [size] [n_steps]   -> prints mean us per phase kind."""
+"""Fine-grained timeline of the persistent decode kernel (CTA 0, thread 0: %globaltimer at tagged points).
+Usage: python scripts/phase_profile.py [size] [n_steps]
+Tags: phase*16 + point; phases 1..5 = P1..P5, 6 = lm_head; points: 1 = activation vector ready (load + LayerNorm),
+2 = all ring units of the batch consumed, 3 = reduction + epilogue done, 4 = grid barrier passed."""
 import ctypes as C
 import os
 import sys
+from collections import defaultdict
 
 import numpy as np
 
@@ -26,23 +29,30 @@ L.zg_sync()
 for _ in range(20):
     L.zg_engine_run_steps(eng, 24, n_steps)
 L.zg_sync()
+L.zg_timer_begin()
+L.zg_engine_run_steps(eng, 24, n_steps)
+ms = L.zg_timer_end_ms()
+print(f"{size}: unprofiled launch {ms*1e3/n_steps:.2f} us/token")
 L.zg_engine_read_profile(eng, None, 1)  # enable
 L.zg_engine_run_steps(eng, 24, n_steps)
 L.zg_sync()
-buf = (C.c_ulonglong * 8192)()
-n = L.zg_engine_read_profile(eng, buf, 8192)
+buf = (C.c_ulonglong * (2 * 16384))()
+n = L.zg_engine_read_profile(eng, buf, 2 * 16384)
 lib.check()
-ts = np.array(buf[:n], dtype=np.int64)
-d = np.diff(ts) / 1e3  # us; entries: start, barrier..., end
-per_tok = 5 * cfg.n_layer + 1
-nb = n - 2
-tok = nb // per_tok
-print(f"{size}: {n_steps} steps, {nb} barriers, total {(ts[-1]-ts[0])/1e3:.1f} us, {(ts[-1]-ts[0])/1e3/n_steps:.2f} us/token")
-if tok >= 2:
-    body = d[: tok * per_tok].reshape(tok, per_tok)[1:]  # drop the first token (ring fill)
-    names = ["P1 ln1+qkv", "P2 attn", "P3 proj", "P4 ln2+fc", "P5 proj2"]
-    layers = body[:, : 5 * cfg.n_layer].reshape(-1, cfg.n_layer, 5)
-    for i, nm in enumerate(names):
-        print(f"  {nm:12s} mean {layers[:, :, i].mean():6.2f} us  (layer0 {layers[:, 0, i].mean():6.2f}, last {layers[:, -1, i].mean():6.2f})")
-    print(f"  lm_head+amax mean {body[:, -1].mean():6.2f} us")
-    print(f"  per token: layers {layers.sum(axis=(1, 2)).mean():.1f} us + lm_head {body[:, -1].mean():.1f} us")
+a = np.array(buf[: 2 * n], dtype=np.int64).reshape(n, 2)
+tags, ts = a[:, 0], a[:, 1]
+print(f"{n} marks, total {(ts[-1]-ts[0])/1e3:.1f} us, {(ts[-1]-ts[0])/1e3/n_steps:.2f} us/token (profiled)")
+# skip the first token (ring fill): find the first lm_head barrier (tag 100)
+first = int(np.argmax(tags == 100)) + 1 if (tags == 100).any() else 0
+seg = defaultdict(list)
+for i in range(max(first, 1), n):
+    seg[(int(tags[i - 1]), int(tags[i]))].append((ts[i] - ts[i - 1]) / 1e3)
+names = {1: "P1 qkv", 2: "P2 attn", 3: "P3 proj", 4: "P4 fc", 5: "P5 proj2", 6: "lm_head"}
+pts = {0: "start", 1: "vec ready", 3: "gemv+epilogue", 4: "barrier passed"}
+tot = 0.0
+for (a_, b_), v in sorted(seg.items(), key=lambda kv: (kv[0][1], kv[0][0])):
+    ph, pt = b_ // 16, b_ % 16
+    per_tok = np.sum(v) / max(1, n_steps - 1)
+    tot += per_tok
+    print(f"  {str(names.get(ph, ph)):8s} -> {str(pts.get(pt, pt)):16s} (from tag {a_:3d}): mean {np.mean(v):7.3f} us x {len(v)/max(1,n_steps-1):5.1f}/token = {per_tok:7.2f} us/token")
+print(f"  sum {tot:.1f} us/token")

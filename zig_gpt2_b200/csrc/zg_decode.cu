@@ -24,18 +24,17 @@
 #include <string.h>
 
 #include "zg_common.cuh"
+#include "zg_ptx.cuh"
 
 namespace zg {
 void launch_softmax_temp(float *x, size_t n, float temp);
 void launch_weighted_index(const float *p, size_t n, float u, unsigned long long *out);
 
-constexpr int NCW = 8;             // consumer warps
-constexpr int NCT = NCW * 32;      // consumer threads
 constexpr int NTHREADS = NCT + 32; // + producer warp
 constexpr int MAXSLOTS = 32;
 constexpr int UB = 8;              // ring units accumulated per reduction round
 constexpr int ATT_CHUNK = 128;     // KV rows per attention work item before splitting
-constexpr int PROF_MAX = 4096;
+constexpr int PROF_MAX = 16384;
 
 struct LayerDesc {
   const float *ln1_g, *ln1_b, *w_attn, *b_attn, *w_proj, *b_proj, *ln2_g, *ln2_b, *w_fc, *b_fc, *w_proj2, *b_proj2;
@@ -70,78 +69,21 @@ struct DecodeParams {
   int store_logits;   // also write the logits vector to global memory
   int write_xout;     // write ln_f(x) to xout (state.x) on the last step
   unsigned long long *prof;
+  int dbg;  // debug switches (env ZG_DEBUG): 1 = fence+atomicAdd barrier, 2 = fetch epilogue operands after the wait,
+            // 4 = CTA-wide sync after every GEMV loop
 };
 
-// ---- PTX wrappers -------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Watchdog: a protocol bug must not hang the GPU.  After ~2 s of waiting the kernel raises the sticky
-// error word (bar[1]) and every later wait falls through; the host reports the failure after the sync.
-constexpr long long WATCHDOG_CYCLES = 4000000000ll;
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, unsigned *err) {
-  if (*reinterpret_cast<volatile unsigned *>(err)) return;
-  const long long t0 = clock64();
-  while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > WATCHDOG_CYCLES || *reinterpret_cast<volatile unsigned *>(err)) {
-      atomicExch(err, 2u);
-      return;
-    }
-  }
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned *err) {
-  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity, err);
-}
-__device__ __forceinline__ uint64_t policy_evict_first() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-// bulk global -> shared copy (SASS: UBLKCP), completion signalled on an mbarrier as transaction bytes
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
-__device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long globaltimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-
-struct Pipe {
-  int slot;
-  uint32_t parity;
-  __device__ __forceinline__ void advance(int nslot) {
-    if (++slot == nslot) {
-      slot = 0;
-      parity ^= 1u;
+// optional fine-grained timeline of CTA 0 / thread 0: (tag, %globaltimer) pairs
+struct Prof {
+  unsigned long long *buf;
+  int i;
+  __device__ __forceinline__ void mark(int tag) {
+    if (buf != nullptr) {
+      if (i < PROF_MAX) {
+        buf[2 * i] = (unsigned long long)tag;
+        buf[2 * i + 1] = globaltimer();
+      }
+      ++i;
     }
   }
 };
@@ -150,42 +92,76 @@ struct Pipe {
 __device__ __forceinline__ void row_range(int cta, int G, int rot, int N, int &r0, int &r1) {
   int c = cta + rot;
   if (c >= G) c -= G;
-  r0 = (int)(((long long)c * N) / G);
-  r1 = (int)(((long long)(c + 1) * N) / G);
+  r0 = (int)(((unsigned)c * (unsigned)N) / (unsigned)G);  // c < G <= ~150 SMs, N <= 4E or V: fits 32 bits
+  r1 = (int)(((unsigned)(c + 1) * (unsigned)N) / (unsigned)G);
 }
 __device__ __forceinline__ int phase_rot(int layer, int ph, int G) { return ((layer * 5 + ph) * 29) % G; }
+
+// GEMV phases.  ph numbering inside a layer: 0 = c_attn, 1 = attention (no weights), 2 = attn c_proj,
+// 3 = c_fc, 4 = mlp c_proj; the tied lm_head is phase index 5L of a step.
+enum { M_QKV = 0, M_RESID = 1, M_GELU = 2, M_LMHEAD = 3 };
+struct PhaseDesc {
+  const float *W, *bias, *ln_g, *ln_b, *src;
+  int N, K, mode, rot;
+};
+__device__ __forceinline__ PhaseDesc phase_desc(const DecodeParams &p, int l, int ph, bool is_head, int G) {
+  PhaseDesc d;
+  const int E = p.E;
+  if (is_head) {
+    d = PhaseDesc{p.wte, nullptr, p.lnf_g, p.lnf_b, p.xres, p.V, E, M_LMHEAD, 0};
+    return d;
+  }
+  const LayerDesc &ld = p.layers[l];
+  d.rot = phase_rot(l, ph, G);
+  d.K = E;
+  d.ln_g = d.ln_b = nullptr;
+  if (ph == 0) {
+    d.W = ld.w_attn; d.bias = ld.b_attn; d.ln_g = ld.ln1_g; d.ln_b = ld.ln1_b; d.src = p.xres; d.N = 3 * E; d.mode = M_QKV;
+  } else if (ph == 2) {
+    d.W = ld.w_proj; d.bias = ld.b_proj; d.src = p.att; d.N = E; d.mode = M_RESID;
+  } else if (ph == 3) {
+    d.W = ld.w_fc; d.bias = ld.b_fc; d.ln_g = ld.ln2_g; d.ln_b = ld.ln2_b; d.src = p.xres; d.N = 4 * E; d.mode = M_GELU;
+  } else {
+    d.W = ld.w_proj2; d.bias = ld.b_proj2; d.src = p.f; d.N = E; d.K = 4 * E; d.mode = M_RESID;
+  }
+  return d;
+}
 
 struct Smem {
   float *ring;   // nslot * slotf
   float *vec;    // 4E: activation vector the GEMV phases read
   float *xv;     // E: staging for LayerNorm input
   float *sc;     // C: attention scores
-  float *part;   // UB * NCW (+ attention partials NCW * hd)
+  float *part;   // NCW * hd attention partial outputs
   float *red;    // 64
   uint32_t full0, empty0;  // shared addresses of mbarrier arrays
-  unsigned *err;           // global sticky watchdog word
+  Watchdog wd;             // sticky global error word + CTA-local tripped flag
 };
 
 // grid-wide barrier among the consumer threads of all CTAs (the producer warp never takes part)
-__device__ __forceinline__ void grid_barrier(const DecodeParams &p, unsigned &target, int G, int &prof_i) {
+__device__ __forceinline__ void grid_barrier(const DecodeParams &p, unsigned &target, int G, Prof &pf, int tag) {
   target += (unsigned)G;
   consumer_sync();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(p.bar, 1u);
-    if ((int)(ld_acquire(p.bar) - target) < 0) {
+    if (p.dbg & 1) {
+      __threadfence();
+      atomicAdd(p.bar, 1u);
+    } else {
+      red_release_gpu(p.bar, 1u);
+    }
+    if ((int)(ld_relaxed(p.bar) - target) < 0) {
       const long long t0 = clock64();
       unsigned spins = 0;
-      while ((int)(ld_acquire(p.bar) - target) < 0) {
-        if ((++spins & 1023u) == 0 && (clock64() - t0 > WATCHDOG_CYCLES || ld_acquire(p.bar + 1))) {
-          atomicExch(p.bar + 1, 1u);
+      while ((int)(ld_relaxed(p.bar) - target) < 0) {
+        if ((++spins & 1023u) == 0 && (clock64() - t0 > WATCHDOG_CYCLES || ld_relaxed(p.bar + 32))) {
+          atomicExch(p.bar + 32, 1u);
           break;
         }
       }
     }
-    if (p.prof && blockIdx.x == 0 && prof_i < PROF_MAX) p.prof[prof_i] = globaltimer();
+    fence_acquire_gpu();
+    pf.mark(tag);
   }
-  ++prof_i;
   consumer_sync();
 }
 
@@ -193,18 +169,25 @@ __device__ __forceinline__ void grid_barrier(const DecodeParams &p, unsigned &ta
 __device__ __forceinline__ void load_vec4(float *dst_smem, const float *src, int n) {
   const float4 *s4 = reinterpret_cast<const float4 *>(src);
   float4 *d4 = reinterpret_cast<float4 *>(dst_smem);
+#pragma unroll 1
   for (int i = threadIdx.x; i < (n >> 2); i += NCT) d4[i] = __ldcg(s4 + i);
 }
 
-// LayerNorm of the E-vector `src` (global, read through L2) into smem `dst`; reference formula ops.zig:86-101
-__device__ __forceinline__ void layer_norm_to_smem(const float *src_smem, float *dst, const float *__restrict__ g,
-                                                   const float *__restrict__ b, int E, float eps, float *red) {
+// LayerNorm of the E-vector in smem `src` into smem `dst`; reference formula ops.zig:86-101.  The affine
+// parameters arrive in registers (element i = tid + j*NCT), fetched at the top of the phase so that their
+// global-memory latency overlaps the activation gather.
+constexpr int LNR = 7;  // E <= 7 * 256
+__device__ __forceinline__ void layer_norm_to_smem(const float *src_smem, float *dst, const float (&lg)[LNR],
+                                                   const float (&lb)[LNR], int E, float eps, float *red) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float xr[LNR];
   float s = 0.0f, ss = 0.0f;
-  for (int i = tid; i < E; i += NCT) {
-    const float v = src_smem[i];
-    s += v;
-    ss = fmaf(v, v, ss);
+#pragma unroll
+  for (int j = 0; j < LNR; ++j) {
+    const int i = tid + j * NCT;
+    xr[j] = (i < E) ? src_smem[i] : 0.0f;
+    s += xr[j];
+    ss = fmaf(xr[j], xr[j], ss);
   }
   s = warp_sum(s);
   ss = warp_sum(ss);
@@ -222,89 +205,26 @@ __device__ __forceinline__ void layer_norm_to_smem(const float *src_smem, float 
   const float n = (float)E;
   const float mean = ts / n;
   const float std_ = sqrtf(tss / n - mean * mean + eps);
-  for (int i = tid; i < E; i += NCT) dst[i] = (src_smem[i] - mean) / std_ * __ldg(g + i) + __ldg(b + i);
+#pragma unroll
+  for (int j = 0; j < LNR; ++j) {
+    const int i = tid + j * NCT;
+    if (i < E) dst[i] = (xr[j] - mean) / std_ * lg[j] + lb[j];
+  }
   consumer_sync();
 }
-
-// One GEMV phase: this CTA's rows [r0,r1) of W[N,K] (arriving through the ring) dotted with `vec` (smem).
-template <class Epi>
-__device__ __forceinline__ void gemv_phase(const Smem &sm, Pipe &pipe, int nslot, int slotf, int K, int r0, int r1,
-                                           Epi epi) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rps = slotf / K;    // rows per ring unit: 4 (K = E) or 1 (K = 4E)
-  const int seg = slotf / NCW;  // floats of a unit each warp reduces
-  const int seg4 = seg >> 2;
-  const int row_in_unit = (warp * seg) / K;
-  const int spr = NCW / rps;    // warp segments per row
-  const int nrows = r1 - r0;
-  const int n_units = (nrows + rps - 1) / rps;
-  const float4 *vec4 = reinterpret_cast<const float4 *>(sm.vec) + (((warp * seg) % K) >> 2);
-  for (int u0 = 0; u0 < n_units; u0 += UB) {
-    const int nb = min(UB, n_units - u0);
-    float acc[UB];
+__device__ __forceinline__ void load_ln_params(const float *g, const float *b, int E, float (&lg)[LNR], float (&lb)[LNR]) {
 #pragma unroll
-    for (int j = 0; j < UB; ++j) {
-      acc[j] = 0.0f;
-      if (j < nb) {
-        const int rows_here = min(rps, nrows - (u0 + j) * rps);
-        mbar_wait(sm.full0 + 8u * pipe.slot, pipe.parity, sm.err);
-        if (row_in_unit < rows_here) {
-          const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)pipe.slot * slotf) + warp * seg4;
-          float a0 = 0.0f, a1 = 0.0f;
-          for (int i = lane; i < seg4; i += 32) {
-            const float4 wv = w4[i];
-            const float4 xv = vec4[i];
-            a0 = fmaf(wv.x, xv.x, a0);
-            a1 = fmaf(wv.y, xv.y, a1);
-            a0 = fmaf(wv.z, xv.z, a0);
-            a1 = fmaf(wv.w, xv.w, a1);
-          }
-          acc[j] = a0 + a1;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sm.empty0 + 8u * pipe.slot);
-        pipe.advance(nslot);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < UB; ++j) acc[j] = warp_sum(acc[j]);
-    if (lane == 0) {
-#pragma unroll
-      for (int j = 0; j < UB; ++j) sm.part[j * NCW + warp] = acc[j];
-    }
-    consumer_sync();
-    if ((int)threadIdx.x < nb * rps) {
-      const int j = threadIdx.x / rps, ri = threadIdx.x % rps;
-      const int r = r0 + (u0 + j) * rps + ri;
-      if (r < r1) {
-        float v = 0.0f;
-        for (int s = 0; s < spr; ++s) v += sm.part[j * NCW + ri * spr + s];
-        epi(r, v);
-      }
-    }
-    consumer_sync();
-  }
-}
-
-// Producer side of one GEMV phase: stream rows [r0,r1) of W[N,K] into the ring.
-__device__ __forceinline__ void produce_phase(const Smem &sm, Pipe &pipe, int nslot, int slotf, const float *W, int K,
-                                              int r0, int r1, uint64_t pol) {
-  const int rps = slotf / K;
-  for (int r = r0; r < r1; r += rps) {
-    const int nr = min(rps, r1 - r);
-    const uint32_t bytes = (uint32_t)nr * (uint32_t)K * 4u;
-    mbar_wait(sm.empty0 + 8u * pipe.slot, pipe.parity ^ 1u, sm.err);
-    const uint32_t fb = sm.full0 + 8u * pipe.slot;
-    mbar_expect_tx(fb, bytes);
-    bulk_g2s(smem_u32(sm.ring + (size_t)pipe.slot * slotf), W + (size_t)r * K, bytes, fb, pol);
-    pipe.advance(nslot);
+  for (int j = 0; j < LNR; ++j) {
+    const int i = threadIdx.x + j * NCT;
+    lg[j] = (i < E) ? __ldg(g + i) : 0.0f;
+    lb[j] = (i < E) ? __ldg(b + i) : 0.0f;
   }
 }
 
 // Attention work item (head h, split s of S) over cache rows [t0,t1) -- ops.zig:249-307 without the
 // whole-cache transposes: K/V are read in place from the time-major cache (head stride hd, time stride E).
-__device__ __forceinline__ void attention_item(const DecodeParams &p, const Smem &sm, const LayerDesc &ld, int h,
-                                               int s, int S, int T) {
+__device__ __noinline__ void attention_item(const DecodeParams &p, const Smem &sm, const LayerDesc &ld, int h, int s,
+                                            int S, int T) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hd = p.hd, E = p.E;
   const int chunk = (T + S - 1) / S;
@@ -313,61 +233,77 @@ __device__ __forceinline__ void attention_item(const DecodeParams &p, const Smem
   const float *qh = p.q + h * hd;
   const float *kh = ld.k_cache + h * hd;
   const float *vh = ld.v_cache + h * hd;
-  float *po = sm.part + UB * NCW;  // [NCW][hd] per-warp partial outputs
+  float *po = sm.part;  // [NCW][hd] per-warp partial outputs
   float m, l;
   if (hd == 64) {
-    // fast path (every GPT-2 size): a cache row of one head is 256 B = one float2 per lane
+    // fast path (every GPT-2 size): a cache row of one head is 256 B = one float2 per lane.  One pass with
+    // an online softmax per warp (K and V rows of 4 cache rows in flight together), merged across warps below.
     const float2 qv = __ldcg(reinterpret_cast<const float2 *>(qh) + lane);
-    for (int t = t0 + warp; t < t1; t += 4 * NCW) {  // 4 rows in flight per warp: overlapped loads + shuffles
-      float a[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int tt = t + u * NCW;
-        a[u] = 0.0f;
-        if (tt < t1) {
-          const float2 kv = __ldcg(reinterpret_cast<const float2 *>(kh + (size_t)tt * E) + lane);
-          a[u] = fmaf(qv.x, kv.x, qv.y * kv.y);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) a[u] = warp_sum(a[u]);
-      if (lane == 0) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (t + u * NCW < t1) sm.sc[t + u * NCW - t0] = a[u] * scale;
-      }
-    }
-    consumer_sync();
-    m = -INFINITY;
-    for (int i = lane; i < n; i += 32) m = fmaxf(m, sm.sc[i]);
-    m = warp_max(m);  // every warp computes the chunk max / sum redundantly (n is at most a few hundred)
-    l = 0.0f;
-    for (int i = lane; i < n; i += 32) l += expf(sm.sc[i] - m);
-    l = warp_sum(l);
+    float mw = -INFINITY, lw = 0.0f;
     float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll 1
     for (int t = t0 + warp; t < t1; t += 4 * NCW) {
-      float2 vv[4];
-      float pt[4];
+      float2 kv[4], vv[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int tt = t + u * NCW;
-        pt[u] = 0.0f;
+        kv[u] = make_float2(0.0f, 0.0f);
         vv[u] = make_float2(0.0f, 0.0f);
         if (tt < t1) {
+          kv[u] = __ldcg(reinterpret_cast<const float2 *>(kh + (size_t)tt * E) + lane);
           vv[u] = __ldcg(reinterpret_cast<const float2 *>(vh + (size_t)tt * E) + lane);
-          pt[u] = expf(sm.sc[tt - t0] - m);
         }
       }
+      float a[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = fmaf(qv.x, kv[u].x, qv.y * kv[u].y);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = warp_sum(a[u]) * scale;
+      float mnew = mw;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (t + u * NCW < t1) mnew = fmaxf(mnew, a[u]);
+      const float corr = (mw == -INFINITY) ? 0.0f : expf(mw - mnew);
+      lw *= corr;
+      acc.x *= corr;
+      acc.y *= corr;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        acc.x = fmaf(pt[u], vv[u].x, acc.x);
-        acc.y = fmaf(pt[u], vv[u].y, acc.y);
+        if (t + u * NCW < t1) {
+          const float pt = expf(a[u] - mnew);
+          lw += pt;
+          acc.x = fmaf(pt, vv[u].x, acc.x);
+          acc.y = fmaf(pt, vv[u].y, acc.y);
+        }
       }
+      mw = mnew;
     }
     po[warp * hd + 2 * lane] = acc.x;
     po[warp * hd + 2 * lane + 1] = acc.y;
+    if (lane == 0) {
+      sm.red[16 + warp] = mw;
+      sm.red[24 + warp] = lw;
+    }
+    consumer_sync();
+    m = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < NCW; ++w) m = fmaxf(m, sm.red[16 + w]);
+    l = 0.0f;
+    float wsc[NCW];
+#pragma unroll
+    for (int w = 0; w < NCW; ++w) {
+      const float mwv = sm.red[16 + w];
+      wsc[w] = (mwv == -INFINITY) ? 0.0f : expf(mwv - m);
+      l = fmaf(sm.red[24 + w], wsc[w], l);
+    }
+    // rescale the per-warp partial outputs in place so the common tail below can just add them up
+    if (tid < hd) {
+#pragma unroll
+      for (int w = 0; w < NCW; ++w) po[w * hd + tid] *= wsc[w];
+    }
   } else {
     // generic head_dim: one cache row per warp iteration, hd spread over lanes
+#pragma unroll 1
     for (int t = t0 + warp; t < t1; t += NCW) {
       float a = 0.0f;
       for (int d = lane; d < hd; d += 32) a = fmaf(__ldcg(qh + d), __ldcg(kh + (size_t)t * E + d), a);
@@ -381,6 +317,7 @@ __device__ __forceinline__ void attention_item(const DecodeParams &p, const Smem
     l = 0.0f;
     for (int i = lane; i < n; i += 32) l += expf(sm.sc[i] - m);
     l = warp_sum(l);
+#pragma unroll 1
     for (int d = lane; d < hd; d += 32) {
       float a = 0.0f;
       for (int t = t0 + warp; t < t1; t += NCW) a = fmaf(expf(sm.sc[t - t0] - m), __ldcg(vh + (size_t)t * E + d), a);
@@ -389,6 +326,7 @@ __device__ __forceinline__ void attention_item(const DecodeParams &p, const Smem
   }
   consumer_sync();
   if (S == 1) {
+#pragma unroll 1
     for (int d = tid; d < hd; d += NCT) {
       float a = 0.0f;
 #pragma unroll
@@ -399,6 +337,7 @@ __device__ __forceinline__ void attention_item(const DecodeParams &p, const Smem
   }
   // flash-decoding partial (m, l, unnormalised o); the last split of this head to arrive combines them
   float *mine = p.att_part + ((size_t)h * S + s) * (hd + 2);
+#pragma unroll 1
   for (int d = tid; d < hd; d += NCT) {
     float a = 0.0f;
 #pragma unroll
@@ -426,6 +365,7 @@ __device__ __forceinline__ void attention_item(const DecodeParams &p, const Smem
     float Lsum = 0.0f;
     for (int i = 0; i < S; ++i)
       Lsum += __ldcg(base + (size_t)i * (hd + 2) + 1) * expf(__ldcg(base + (size_t)i * (hd + 2)) - M);
+#pragma unroll 1
     for (int d = tid; d < hd; d += NCT) {
       float a = 0.0f;
       for (int i = 0; i < S; ++i)
@@ -442,229 +382,307 @@ __device__ __forceinline__ bool step_needs_logits(const DecodeParams &p, int ste
 __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const DecodeParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar_store[2 * MAXSLOTS];
+  __shared__ unsigned wd_tripped;
   const int G = gridDim.x, cta = blockIdx.x;
   const int E = p.E, E4 = 4 * p.E;
+  const int nslot = p.nslot, slotf = p.slotf;
   Smem sm;
   sm.ring = reinterpret_cast<float *>(smem_raw);
-  sm.vec = sm.ring + (size_t)p.nslot * p.slotf;
+  sm.vec = sm.ring + (size_t)nslot * slotf;
   sm.xv = sm.vec + E4;
   sm.sc = sm.xv + E;
   sm.part = sm.sc + p.C;
-  sm.red = sm.part + UB * NCW + NCW * p.hd;
+  sm.red = sm.part + NCW * p.hd;
   sm.full0 = smem_u32(mbar_store);
   sm.empty0 = smem_u32(mbar_store + MAXSLOTS);
-  sm.err = p.bar + 1;
+  sm.wd.err_global = p.bar + 32;  // its own 128-byte line, away from the barrier word
+  sm.wd.tripped_smem = smem_u32(&wd_tripped);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.nslot; ++i) {
+    wd_tripped = 0u;
+    for (int i = 0; i < nslot; ++i) {
       mbar_init(sm.full0 + 8u * i, 1);
-      mbar_init(sm.empty0 + 8u * i, NCW);
+      mbar_init(sm.empty0 + 8u * i, 1);  // one warp owns a ring unit and releases it
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
 
-  Pipe pipe{0, 0u};
   const int last_step = p.first_step + p.n_steps - 1;
+  const int L5 = 5 * p.L;
 
   if (threadIdx.x >= NCT) {
     // =============================== producer warp ===============================
+    // Streams, in consumption order, the rows this CTA owns in every GEMV phase.  Unit = up to slotf floats
+    // (4 rows of K = E, or 1 row of K = 4E) = one cp.async.bulk into one ring slot.
     const int lane = threadIdx.x - NCT;
     const uint64_t pol = policy_evict_first();
+    int slot = 0;
+    uint32_t parity = 0;
+#pragma unroll 1
     for (int step = p.first_step; step <= last_step; ++step) {
-      for (int l = 0; l < p.L; ++l) {
-        const LayerDesc &ld = p.layers[l];
-        // pull the layer's small vectors (LayerNorm affine + biases, 13E floats) into L2 ahead of the consumers
-        if (lane < 8) {
-          const float *arr[8] = {ld.ln1_g, ld.ln1_b, ld.b_attn, ld.b_proj, ld.ln2_g, ld.ln2_b, ld.b_fc, ld.b_proj2};
-          const int len[8] = {E, E, 3 * E, E, E, E, E4, E};
-          const int nlines = (len[lane] * 4 + 127) / 128;
-          for (int i = cta; i < nlines; i += G) prefetch_l2(reinterpret_cast<const char *>(arr[lane]) + (size_t)i * 128);
+      const int nph = L5 + (step_needs_logits(p, step) ? 1 : 0);
+#pragma unroll 1
+      for (int g = 0; g < nph; ++g) {
+        const int l = g / 5, ph = g - 5 * l;
+        const bool is_head = (g == L5);
+        if (!is_head && ph == 1) continue;
+        const PhaseDesc d = phase_desc(p, l, ph, is_head, G);
+        if (!is_head && ph == 0 && lane < 8) {
+          // pull the layer's small vectors (LayerNorm affine + biases, 13E floats) into L2 ahead of the consumers
+          const LayerDesc &ld = p.layers[l];
+          const float *arr = lane == 0 ? ld.ln1_g : lane == 1 ? ld.ln1_b : lane == 2 ? ld.b_attn : lane == 3 ? ld.b_proj
+                           : lane == 4 ? ld.ln2_g : lane == 5 ? ld.ln2_b : lane == 6 ? ld.b_fc : ld.b_proj2;
+          const int len = lane == 2 ? 3 * E : lane == 6 ? E4 : E;
+          const int nlines = (len * 4 + 127) / 128;
+          for (int i = cta; i < nlines; i += G) prefetch_l2(reinterpret_cast<const char *>(arr) + (size_t)i * 128);
         }
         if (lane == 0) {
           int r0, r1;
-          row_range(cta, G, phase_rot(l, 0, G), 3 * E, r0, r1);
-          produce_phase(sm, pipe, p.nslot, p.slotf, ld.w_attn, E, r0, r1, pol);
-          row_range(cta, G, phase_rot(l, 1, G), E, r0, r1);
-          produce_phase(sm, pipe, p.nslot, p.slotf, ld.w_proj, E, r0, r1, pol);
-          row_range(cta, G, phase_rot(l, 2, G), E4, r0, r1);
-          produce_phase(sm, pipe, p.nslot, p.slotf, ld.w_fc, E, r0, r1, pol);
-          row_range(cta, G, phase_rot(l, 3, G), E, r0, r1);
-          produce_phase(sm, pipe, p.nslot, p.slotf, ld.w_proj2, E4, r0, r1, pol);
+          row_range(cta, G, d.rot, d.N, r0, r1);
+          const int rps = slotf / d.K;
+#pragma unroll 1
+          for (int r = r0; r < r1; r += rps) {
+            const int nr = min(rps, r1 - r);
+            const uint32_t bytes = (uint32_t)nr * (uint32_t)d.K * 4u;
+            mbar_wait(sm.empty0 + 8u * slot, parity ^ 1u, sm.wd);
+            const uint32_t fb = sm.full0 + 8u * slot;
+            mbar_expect_tx(fb, bytes);
+            bulk_g2s(smem_u32(sm.ring + (size_t)slot * slotf), d.W + (size_t)r * d.K, bytes, fb, pol);
+            if (++slot == nslot) { slot = 0; parity ^= 1u; }
+          }
         }
         __syncwarp();
       }
-      if (step_needs_logits(p, step) && lane == 0) {
-        int r0, r1;
-        row_range(cta, G, 0, p.V, r0, r1);
-        produce_phase(sm, pipe, p.nslot, p.slotf, p.wte, E, r0, r1, pol);
-      }
-      __syncwarp();
     }
     return;
   }
 
   // ================================= consumer warps =================================
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned target = p.bar_base;
-  int prof_i = 0;
-  if (p.prof && cta == 0 && tid == 0) p.prof[PROF_MAX] = globaltimer();
+  Prof pf{(p.prof && cta == 0 && tid == 0) ? p.prof : nullptr, 0};
+  pf.mark(0);
   unsigned long long prev_token = 0;
+  unsigned useq = 0;  // ring units consumed by this CTA so far (slot = useq % nslot, parity = (useq / nslot) & 1)
 
+#pragma unroll 1
   for (int step = p.first_step; step <= last_step; ++step) {
     const int pos = step, T = step + 1;  // seq_len = step + 1 (main.zig:333,337)
     unsigned long long tok;
     if (step < p.n_prompt) tok = p.prompt ? p.prompt[step] : p.single_token;
     else if (step == p.first_step) tok = step > 0 ? __ldcg(p.tokens + step - 1) : 0ull;
     else tok = prev_token;
+    if (tok >= (unsigned long long)p.V) tok = 0;  // never index the embedding out of bounds, whatever came in
     const bool want_logits = step_needs_logits(p, step);
+    const int nph = L5 + (want_logits ? 1 : 0);
+    unsigned long long out_tok = tok;
 
-    for (int l = 0; l < p.L; ++l) {
-      const LayerDesc &ld = p.layers[l];
-      int r0, r1;
-      // ---------------- P1: x -> LN1 -> c_attn, K/V straight into the cache ----------------
-      if (l == 0) {  // wte[token] + wpe[pos] (main.zig:179-183), recomputed by every CTA
-        const float *te = p.wte + (size_t)tok * E, *pe = p.wpe + (size_t)pos * E;
-        for (int i = tid; i < E; i += NCT) {
-          const float v = __ldg(te + i) + __ldg(pe + i);
-          sm.xv[i] = v;
-          if (cta == 0) p.xres[i] = v;
-        }
-      } else {
-        load_vec4(sm.xv, p.xres, E);
-      }
-      consumer_sync();
-      layer_norm_to_smem(sm.xv, sm.vec, ld.ln1_g, ld.ln1_b, E, 1e-5f, sm.red);
-      row_range(cta, G, phase_rot(l, 0, G), 3 * E, r0, r1);
-      {
-        float *kc = ld.k_cache + (size_t)pos * E, *vc = ld.v_cache + (size_t)pos * E;
-        const float *bias = ld.b_attn;
-        float *q = p.q;
-        gemv_phase(sm, pipe, p.nslot, p.slotf, E, r0, r1, [=](int r, float v) {
-          v += __ldg(bias + r);
-          if (r < E) q[r] = v;
-          else if (r < 2 * E) kc[r - E] = v;
-          else vc[r - 2 * E] = v;
-        });
-      }
-      grid_barrier(p, target, G, prof_i);
+#pragma unroll 1
+    for (int g = 0; g < nph; ++g) {
+      const int l = g / 5, ph = g - 5 * l;
+      const bool is_head = (g == L5);
+      const int tag = is_head ? 96 : 16 * (ph + 1);
+      float best = -INFINITY;  // running argmax of the rows this lane finishes (lm_head only)
+      unsigned best_i = 0xffffffffu;
 
-      // ---------------- P2: attention ----------------
-      {
+      if (!is_head && ph == 1) {
+        // ---------------- attention over the cache (ops.zig:160-171) ----------------
         int S = (T + ATT_CHUNK - 1) / ATT_CHUNK;
         const int smax = G / p.H;
         if (S > smax) S = smax;
-        if (cta < p.H * S) attention_item(p, sm, ld, cta / S, cta % S, S, T);
-      }
-      grid_barrier(p, target, G, prof_i);
+        if (cta < p.H * S) attention_item(p, sm, p.layers[l], cta / S, cta % S, S, T);
+      } else {
+        const PhaseDesc d = phase_desc(p, l, ph, is_head, G);
+        // ---------------- phase-top prefetch: everything whose address is known before the activation arrives
+        int r0, r1;
+        row_range(cta, G, d.rot, d.N, r0, r1);
+        const int rps = slotf / d.K;  // rows per unit: 4 (K = E) or 1 (K = 4E)
+        const int nrows = r1 - r0;
+        const int n_units = (nrows + rps - 1) / rps;
+        const int rw = nslot < NCW ? nslot : NCW;
+        float bias0 = 0.0f, resid0 = 0.0f;
+        if (warp < rw && warp < n_units && lane < min(rps, nrows - warp * rps)) {
+          if (d.bias) bias0 = __ldg(d.bias + r0 + warp * rps + lane);
+          if (d.mode == M_RESID) resid0 = __ldcg(p.xres + r0 + warp * rps + lane);
+        }
+        float lg[LNR], lb[LNR];
+        if (d.ln_g != nullptr) load_ln_params(d.ln_g, d.ln_b, E, lg, lb);
+        // ---------------- activation vector -> shared memory ----------------
+        if (d.ln_g != nullptr) {
+          if (g == 0) {  // wte[token] + wpe[pos] (main.zig:179-183), recomputed by every CTA
+            const float *te = p.wte + (size_t)tok * E, *pe = p.wpe + (size_t)pos * E;
+#pragma unroll 1
+            for (int i = tid; i < E; i += NCT) {
+              const float v = __ldg(te + i) + __ldg(pe + i);
+              sm.xv[i] = v;
+              if (cta == 0) p.xres[i] = v;
+            }
+          } else {
+            load_vec4(sm.xv, d.src, E);
+          }
+          consumer_sync();
+          layer_norm_to_smem(sm.xv, sm.vec, lg, lb, E, 1e-5f, sm.red);  // main.zig:123,140,189
+          if (is_head && p.write_xout && step == last_step && cta == 0) {
+#pragma unroll 1
+            for (int i = tid; i < E; i += NCT) p.xout[i] = sm.vec[i];
+          }
+        } else {
+          load_vec4(sm.vec, d.src, d.K);
+          consumer_sync();
+        }
+        pf.mark(tag + 1);
 
-      // ---------------- P3: attn c_proj + residual ----------------
-      load_vec4(sm.vec, p.att, E);
-      consumer_sync();
-      row_range(cta, G, phase_rot(l, 1, G), E, r0, r1);
-      {
-        const float *bias = ld.b_proj;
-        float *xres = p.xres;
-        gemv_phase(sm, pipe, p.nslot, p.slotf, E, r0, r1,
-                   [=](int r, float v) { xres[r] = (v + __ldg(bias + r)) + __ldcg(xres + r); });
-      }
-      grid_barrier(p, target, G, prof_i);
+        // ---------------- GEMV: one warp per ring unit ----------------
+        float *kc = nullptr, *vc = nullptr;
+        if (d.mode == M_QKV) {
+          kc = p.layers[l].k_cache + (size_t)pos * E;
+          vc = p.layers[l].v_cache + (size_t)pos * E;
+        }
+        float *logits = (is_head && p.store_logits && step == last_step) ? p.logits : nullptr;
+        const float4 *vec4 = reinterpret_cast<const float4 *>(sm.vec);
+        const int k4 = d.K >> 2;
+        // Warps advance through the ring in lockstep rounds of `rw` consecutive units with a CTA sync between
+        // rounds.  An mbarrier only tracks phase PARITY: a warp that waited on a slot's next fill while the
+        // current fill was still in flight would see the matching parity and read stale data.  Keeping every
+        // round's units on distinct slots (rw <= nslot) and finishing a round before the next starts rules
+        // that out.
+#pragma unroll 1
+        for (int ub = 0; ub < n_units; ub += rw) {
+          const int u = ub + warp;
+          if (warp < rw && u < n_units) {
+          const unsigned n = useq + (unsigned)u;
+          const int slot = (int)(n % (unsigned)nslot);
+          const uint32_t parity = (n / (unsigned)nslot) & 1u;
+          const int rbase = r0 + u * rps;
+          const int rows_here = min(rps, r1 - rbase);
+          // epilogue operands are fetched before the wait so their L2 latency hides behind it
+          float bias_v = bias0, resid_v = resid0;
+          if (ub > 0 && lane < rows_here) {
+            if (d.bias) bias_v = __ldg(d.bias + rbase + lane);
+            if (d.mode == M_RESID) resid_v = __ldcg(p.xres + rbase + lane);
+          }
+          mbar_wait(sm.full0 + 8u * slot, parity, sm.wd);
+          const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)slot * slotf);
+          float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+          if (rps == 4) {
+            // 4 rows share the activation vector: one x load feeds four row accumulators
+#pragma unroll 2
+            for (int i = lane; i < k4; i += 32) {
+              const float4 xv = vec4[i];
+              const float4 w0 = w4[i];
+              const float4 w1 = (rows_here > 1) ? w4[k4 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 w2 = (rows_here > 2) ? w4[2 * k4 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 w3 = (rows_here > 3) ? w4[3 * k4 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+              a0 = fmaf(w0.x, xv.x, a0); a0 = fmaf(w0.y, xv.y, a0); a0 = fmaf(w0.z, xv.z, a0); a0 = fmaf(w0.w, xv.w, a0);
+              a1 = fmaf(w1.x, xv.x, a1); a1 = fmaf(w1.y, xv.y, a1); a1 = fmaf(w1.z, xv.z, a1); a1 = fmaf(w1.w, xv.w, a1);
+              a2 = fmaf(w2.x, xv.x, a2); a2 = fmaf(w2.y, xv.y, a2); a2 = fmaf(w2.z, xv.z, a2); a2 = fmaf(w2.w, xv.w, a2);
+              a3 = fmaf(w3.x, xv.x, a3); a3 = fmaf(w3.y, xv.y, a3); a3 = fmaf(w3.z, xv.z, a3); a3 = fmaf(w3.w, xv.w, a3);
+            }
+          } else {
+            // one long row (K = 4E): four independent accumulators for ILP, summed below
+#pragma unroll 4
+            for (int i = lane; i < k4; i += 32) {
+              const float4 xv = vec4[i];
+              const float4 w0 = w4[i];
+              a0 = fmaf(w0.x, xv.x, a0); a1 = fmaf(w0.y, xv.y, a1); a2 = fmaf(w0.z, xv.z, a2); a3 = fmaf(w0.w, xv.w, a3);
+            }
+            a0 = (a0 + a1) + (a2 + a3);
+            a1 = a2 = a3 = 0.0f;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sm.empty0 + 8u * slot);  // ring slot free again
+          a0 = warp_sum(a0);
+          a1 = warp_sum(a1);
+          a2 = warp_sum(a2);
+          a3 = warp_sum(a3);
+          if (lane < rows_here) {
+            const int r = rbase + lane;
+            float v = lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : a3;
+            v += bias_v;
+            if (d.mode == M_QKV) {  // q to scratch, k/v straight into cache row `pos` (ops.zig:146-158)
+              if (r < E) p.q[r] = v;
+              else if (r < 2 * E) kc[r - E] = v;
+              else vc[r - 2 * E] = v;
+            } else if (d.mode == M_RESID) {  // main.zig:136-139,142-145
+              p.xres[r] = v + resid_v;
+            } else if (d.mode == M_GELU) {  // main.zig:80
+              p.f[r] = gelu_ref(v);
+            } else {  // tied lm_head (main.zig:193) + running argmax; this lane sees increasing r, so strict >
+              if (logits) logits[r] = v;
+              if (v > best) { best = v; best_i = (unsigned)r; }
+            }
+          }
+          }
+          if (ub + rw < n_units) consumer_sync();
+        }
+        useq += (unsigned)n_units;
+        if (p.dbg & 4) consumer_sync();
+        pf.mark(tag + 3);
 
-      // ---------------- P4: LN2 + c_fc + GELU ----------------
-      load_vec4(sm.xv, p.xres, E);
-      consumer_sync();
-      layer_norm_to_smem(sm.xv, sm.vec, ld.ln2_g, ld.ln2_b, E, 1e-5f, sm.red);
-      row_range(cta, G, phase_rot(l, 2, G), E4, r0, r1);
-      {
-        const float *bias = ld.b_fc;
-        float *f = p.f;
-        gemv_phase(sm, pipe, p.nslot, p.slotf, E, r0, r1,
-                   [=](int r, float v) { f[r] = gelu_ref(v + __ldg(bias + r)); });
+        if (is_head) {
+          // CTA-level argmax (value desc, index asc), then one partial per CTA
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const unsigned oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+            if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+          }
+          if (lane == 0) {
+            sm.red[16 + warp] = best;
+            sm.red[24 + warp] = __uint_as_float(best_i);
+          }
+          consumer_sync();
+          if (tid == 0) {
+            for (int w = 1; w < NCW; ++w) {
+              const float ov = sm.red[16 + w];
+              const unsigned oi = __float_as_uint(sm.red[24 + w]);
+              if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+            }
+            p.amax_val[cta] = best;
+            p.amax_idx[cta] = best_i;
+          }
+        }
       }
-      grid_barrier(p, target, G, prof_i);
 
-      // ---------------- P5: mlp c_proj + residual ----------------
-      load_vec4(sm.vec, p.f, E4);
-      consumer_sync();
-      row_range(cta, G, phase_rot(l, 3, G), E, r0, r1);
-      {
-        const float *bias = ld.b_proj2;
-        float *xres = p.xres;
-        gemv_phase(sm, pipe, p.nslot, p.slotf, E4, r0, r1,
-                   [=](int r, float v) { xres[r] = (v + __ldg(bias + r)) + __ldcg(xres + r); });
+      grid_barrier(p, target, G, pf, tag + 4);
+
+      if (is_head) {
+        // every CTA reduces the G partials itself: the next step's embedding needs the token everywhere
+        if (tid < 32) {
+          float bv = -INFINITY;
+          unsigned bi = 0xffffffffu;
+          for (int i = tid; i < G; i += 32) {
+            const float ov = __ldcg(p.amax_val + i);
+            const unsigned oi = __ldcg(p.amax_idx + i);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const unsigned oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+          }
+          if (tid == 0) sm.red[40] = __uint_as_float(bi);
+        }
+        consumer_sync();
+        const unsigned long long amax = (unsigned long long)__float_as_uint(sm.red[40]);
+        if (cta == 0 && tid == 0) *p.last_token = amax;
+        if (step >= p.n_prompt) out_tok = amax;  // generate(): main.zig:335-338
+        consumer_sync();
       }
-      grid_barrier(p, target, G, prof_i);
     }
 
-    // ---------------- ln_f (+ lm_head + argmax) ----------------
-    const bool need_x = want_logits || (p.write_xout && step == last_step && cta == 0);
-    if (need_x) {
+    if (!want_logits && p.write_xout && step == last_step && cta == 0) {
+      // GPT.forward(compute_logits = false) still leaves ln_f(x) in state.x (main.zig:189)
+      float lg[LNR], lb[LNR];
+      load_ln_params(p.lnf_g, p.lnf_b, E, lg, lb);
       load_vec4(sm.xv, p.xres, E);
       consumer_sync();
-      layer_norm_to_smem(sm.xv, sm.vec, p.lnf_g, p.lnf_b, E, 1e-5f, sm.red);
-      if (p.write_xout && step == last_step && cta == 0)
-        for (int i = tid; i < E; i += NCT) p.xout[i] = sm.vec[i];
-    }
-    unsigned long long out_tok = tok;
-    if (want_logits) {
-      int r0, r1;
-      row_range(cta, G, 0, p.V, r0, r1);
-      float best = -INFINITY;
-      unsigned best_i = 0xffffffffu;
-      {
-        float *logits = (p.store_logits && step == last_step) ? p.logits : nullptr;
-        gemv_phase(sm, pipe, p.nslot, p.slotf, E, r0, r1, [&](int r, float v) {
-          if (logits) logits[r] = v;
-          if (v > best) {  // rows arrive in increasing r per thread, so strict > keeps the first maximum
-            best = v;
-            best_i = (unsigned)r;
-          }
-        });
-      }
-      // epilogue threads all live in warp 0: reduce (value desc, index asc)
-      if (tid < 32) {
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-          const unsigned oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-          if (ov > best || (ov == best && oi < best_i)) {
-            best = ov;
-            best_i = oi;
-          }
-        }
-        if (tid == 0) {
-          p.amax_val[cta] = best;
-          p.amax_idx[cta] = best_i;
-        }
-      }
-      grid_barrier(p, target, G, prof_i);
-      // every CTA reduces the G partials itself: the next step's embedding needs the token everywhere
-      if (tid < 32) {
-        float bv = -INFINITY;
-        unsigned bi = 0xffffffffu;
-        for (int i = tid; i < G; i += 32) {
-          const float ov = __ldcg(p.amax_val + i);
-          const unsigned oi = __ldcg(p.amax_idx + i);
-          if (ov > bv || (ov == bv && oi < bi)) {
-            bv = ov;
-            bi = oi;
-          }
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-          const unsigned oi = __shfl_xor_sync(0xffffffffu, bi, o);
-          if (ov > bv || (ov == bv && oi < bi)) {
-            bv = ov;
-            bi = oi;
-          }
-        }
-        if (tid == 0) sm.red[40] = __uint_as_float(bi);
-      }
-      consumer_sync();
-      const unsigned long long amax = (unsigned long long)__float_as_uint(sm.red[40]);
-      if (cta == 0 && tid == 0) *p.last_token = amax;
-      if (step >= p.n_prompt) out_tok = amax;  // generate(): main.zig:335-338
-      consumer_sync();
+      layer_norm_to_smem(sm.xv, sm.vec, lg, lb, E, 1e-5f, sm.red);
+#pragma unroll 1
+      for (int i = tid; i < E; i += NCT) p.xout[i] = sm.vec[i];
     }
     if (cta == 0 && tid == 0) {
       p.tokens[step] = out_tok;
@@ -672,10 +690,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
     }
     prev_token = out_tok;
   }
-  if (p.prof && cta == 0 && tid == 0) {
-    p.prof[PROF_MAX + 1] = globaltimer();
-    p.prof[PROF_MAX + 2] = (unsigned long long)prof_i;
-  }
+  pf.mark(1);
+  if (pf.buf) pf.buf[2 * PROF_MAX] = (unsigned long long)pf.i;
 }
 
 }  // namespace zg
@@ -706,7 +722,7 @@ struct zg_engine {
 
 static size_t engine_smem_bytes(const zg_config &c, int nslot) {
   const size_t E = c.n_embed, hd = E / c.n_heads;
-  const size_t floats = (size_t)nslot * 4 * E + 4 * E + E + c.context_size + UB * NCW + NCW * hd + 64;
+  const size_t floats = (size_t)nslot * 4 * E + 4 * E + E + c.context_size + NCW * hd + 64;
   return floats * sizeof(float);
 }
 
@@ -717,8 +733,8 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
   Context &c = ctx();
   const zg_config &cfg = gpt->config;
   const size_t E = cfg.n_embed;
-  if (E % 8 != 0 || E / cfg.n_heads * cfg.n_heads != E) {
-    set_error(1, "zg_engine_create: n_embed must be a multiple of 8 and of n_heads", __FILE__, __LINE__);
+  if (E % 8 != 0 || E / cfg.n_heads * cfg.n_heads != E || E > (size_t)LNR * NCT) {
+    set_error(1, "zg_engine_create: n_embed must be a multiple of 8 and of n_heads, and at most 1792", __FILE__, __LINE__);
     return nullptr;
   }
   zg_engine *e = (zg_engine *)calloc(1, sizeof(zg_engine));
@@ -769,8 +785,8 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
   e->prompt_dev = (unsigned long long *)zg_alloc(C * 8);
   e->tokens_dev = (unsigned long long *)zg_alloc(C * 8);
   e->last_token_dev = (unsigned long long *)zg_alloc(8);
-  e->prof_dev = (unsigned long long *)zg_alloc((PROF_MAX + 4) * 8);
-  e->bar_dev = (unsigned *)zg_alloc(64);
+  e->prof_dev = (unsigned long long *)zg_alloc((2 * PROF_MAX + 4) * 8);
+  e->bar_dev = (unsigned *)zg_alloc(1024);
   float *att_part = (float *)zg_alloc(cfg.n_heads * (size_t)smax * (hd + 2) * sizeof(float));
   unsigned *head_count = (unsigned *)zg_alloc(cfg.n_heads * sizeof(unsigned));
   float *amax_val = (float *)zg_alloc(e->grid * sizeof(float));
@@ -782,10 +798,10 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
     return nullptr;
   }
   memset(e->tokens_host, 0xff, C * 8);
-  zg_memset(e->bar_dev, 0, 64);
+  zg_memset(e->bar_dev, 0, 1024);
   zg_memset(head_count, 0, cfg.n_heads * sizeof(unsigned));
   zg_memset(e->tokens_dev, 0, C * 8);
-  zg_memset(e->prof_dev, 0, (PROF_MAX + 4) * 8);
+  zg_memset(e->prof_dev, 0, (2 * PROF_MAX + 4) * 8);
   e->bar_count = 0;
 
   DecodeParams &p = e->base;
@@ -798,6 +814,7 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
   p.att_part = att_part; p.head_count = head_count; p.bar = e->bar_dev;
   p.amax_val = amax_val; p.amax_idx = amax_idx;
   p.tokens = e->tokens_dev; p.tokens_host = e->tokens_host_devptr; p.last_token = e->last_token_dev;
+  p.dbg = getenv("ZG_DEBUG") ? atoi(getenv("ZG_DEBUG")) : 0;
   zg_sync();
   return zg_last_error() ? (free(e), nullptr) : e;
 }
@@ -840,7 +857,7 @@ static void engine_launch(zg_engine *e, DecodeParams &p) {
 // after a synchronisation: did the in-kernel watchdog fire (a wait exceeded ~2 s)?
 static int engine_check_watchdog(zg_engine *e) {
   unsigned w = 0;
-  ZG_CUDA(cudaMemcpyAsync(&w, e->bar_dev + 1, sizeof(w), cudaMemcpyDeviceToHost, ctx().stream));
+  ZG_CUDA(cudaMemcpyAsync(&w, e->bar_dev + 32, sizeof(w), cudaMemcpyDeviceToHost, ctx().stream));
   ZG_CUDA(cudaStreamSynchronize(ctx().stream));
   if (w != 0) {
     set_error(1, w == 1 ? "decode engine watchdog: grid barrier timed out" : "decode engine watchdog: mbarrier wait timed out",
@@ -929,16 +946,15 @@ size_t zg_engine_read_profile(zg_engine *e, unsigned long long *out, size_t max_
     e->prof_enabled = max_entries ? 1 : 0;
     return 0;
   }
-  unsigned long long *tmp = (unsigned long long *)malloc((PROF_MAX + 4) * 8);
-  zg_download(tmp, e->prof_dev, (PROF_MAX + 4) * 8);
-  size_t n = (size_t)tmp[PROF_MAX + 2];
+  // out receives (tag, ns) pairs; returns the number of pairs
+  unsigned long long *tmp = (unsigned long long *)malloc((2 * PROF_MAX + 4) * 8);
+  zg_download(tmp, e->prof_dev, (2 * PROF_MAX + 4) * 8);
+  size_t n = (size_t)tmp[2 * PROF_MAX];
   if (n > PROF_MAX) n = PROF_MAX;
-  size_t w = 0;
-  if (w < max_entries) out[w++] = tmp[PROF_MAX];  // kernel start
-  for (size_t i = 0; i < n && w < max_entries; ++i) out[w++] = tmp[i];
-  if (w < max_entries) out[w++] = tmp[PROF_MAX + 1];  // kernel end
+  if (2 * n > max_entries) n = max_entries / 2;
+  memcpy(out, tmp, 2 * n * 8);
   free(tmp);
-  return w;
+  return n;
 }
 
 }  // extern "C"
