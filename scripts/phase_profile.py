@@ -19,7 +19,13 @@ size = sys.argv[1] if len(sys.argv) > 1 else "124M"
 n_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 L = lib.init(0)
 cfg = SIZES[size]
-model = G.gpt_from_numpy(cfg, synth_for_size(size))
+if len(sys.argv) > 4:  # optional overrides: n_layer vocab  (e.g. a model small enough to live in L2)
+    from zig_gpt2_b200.config import GPTConfig
+    from zig_gpt2_b200.weights import synth_weights
+    cfg = GPTConfig(int(sys.argv[4]), cfg.context_size, int(sys.argv[3]), cfg.n_heads, cfg.n_embed)
+    model = G.gpt_from_numpy(cfg, synth_weights(cfg, seed=5))
+else:
+    model = G.gpt_from_numpy(cfg, synth_for_size(size))
 state = G.State(cfg)
 eng = model.engine(state)
 prompt = np.random.Generator(np.random.PCG64(1235)).integers(0, cfg.vocab_size, 16).astype(np.uint64)
@@ -48,7 +54,20 @@ seg = defaultdict(list)
 for i in range(max(first, 1), n):
     seg[(int(tags[i - 1]), int(tags[i]))].append((ts[i] - ts[i - 1]) / 1e3)
 names = {1: "P1 qkv", 2: "P2 attn", 3: "P3 proj", 4: "P4 fc", 5: "P5 proj2", 6: "lm_head"}
-pts = {0: "start", 1: "vec ready", 3: "gemv+epilogue", 4: "barrier passed"}
+pts = {0: "start", 1: "vec gathered", 3: "phase done", 4: "token reduced"}
+fine = {257: "B:after sync1", 258: "B:after red", 259: "B:poll done", 260: "V:prefetch issued", 261: "V:gather issued",
+        262: "V:gather sync", 263: "G:wait done", 264: "G:dot done", 265: "G:arrive done", 266: "G:shuffles done"}
+def nm(t):
+    if t in fine: return fine[t]
+    ph, pt = t // 16, t % 16
+    return f"{names.get(ph, ph)}:{pts.get(pt, pt)}"
+if any(t >= 256 for t in tags):
+    agg = defaultdict(list)
+    for (a_, b_), v in seg.items():
+        agg[(nm(a_) if a_ >= 256 else "phase-mark", nm(b_) if b_ >= 256 else "phase-mark:" + str(pts.get(b_ % 16, b_ % 16)))].extend(v)
+    print("fine-grained segments (mean us, count):")
+    for k, v in sorted(agg.items(), key=lambda kv: -np.sum(kv[1])):
+        print(f"  {k[0]:22s} -> {k[1]:28s} mean {np.mean(v):6.3f}  n={len(v):5d}  total/token {np.sum(v)/max(1,n_steps-1):7.2f}")
 tot = 0.0
 for (a_, b_), v in sorted(seg.items(), key=lambda kv: (kv[0][1], kv[0][0])):
     ph, pt = b_ // 16, b_ % 16

@@ -4,19 +4,25 @@
 // Design (B200, 148 SMs, HBM-bound: 495 MB of fp32 weights per token at 124M):
 //   * one CTA per SM, 8 consumer warps + 1 producer warp;
 //   * the producer warp streams this CTA's share of every weight matrix, in execution order, through a
-//     shared-memory ring with cp.async.bulk (UBLKCP) + mbarrier complete_tx, L2 evict-first.  The stream
-//     does not depend on activations, so it runs ahead across layer phases, tokens and grid barriers and
-//     keeps HBM busy while consumers synchronise;
-//   * consumers take weight rows from the ring (conflict-free 128-bit LDS), dot them with the activation
-//     vector held in shared memory, reduce with warp shuffles, and apply the fused epilogue
-//     (bias, GELU, residual add, KV-cache append, running argmax);
-//   * five grid-wide barriers per layer separate the phases
+//     shared-memory ring with cp.async.bulk (UBLKCP) + mbarrier complete_tx, L2 evict-first.  The stream does
+//     not depend on activations, so it runs ahead across layer phases and tokens;
+//   * consumers take weight rows from the ring (one warp per ring unit, conflict-free 128-bit LDS), dot them
+//     with the activation vector held in shared memory, reduce with warp shuffles, and apply the fused
+//     epilogue (bias, GELU, residual add, KV-cache append, running argmax);
+//   * five phases per layer
 //        P1 LN1 + c_attn (+ K/V append)   ops.zig:143-158, main.zig:121-123
 //        P2 attention over the time-major cache (flash-decoding splits when T is long)  ops.zig:160-171
 //        P3 attn c_proj + residual         ops.zig:172, main.zig:136-139
 //        P4 LN2 + c_fc + GELU              main.zig:140, :79-80
 //        P5 mlp c_proj + residual          main.zig:81, :142-145
 //     then ln_f + tied lm_head + argmax (main.zig:189-194);
+//   * NO grid barrier and NO memory fence between phases.  Every activation word crosses SMs as one 64-bit
+//     store {epoch : 32 | fp32 bits : 32}; a consumer gathers the vector it needs with 128-bit relaxed loads
+//     and spins until every word carries the epoch of the phase that produces it (the NCCL "LL" idea: the
+//     flag travels inside the datum, so there is nothing to fence).  A measured grid barrier costs ~2.6 us per
+//     phase inside this kernel (0.9 us release fence + 0.7 us poll + 0.5 us acquire fence + skew); the
+//     flagged gather costs one L2 round trip;
+//   * the layer table lives in __constant__ memory, so no phase starts with a dependent global load;
 //   * the token loop of generate() runs inside the kernel; each token is written to device memory and to a
 //     pinned host ring, so the host only waits once per call.
 #include <cooperative_groups.h>
@@ -30,63 +36,149 @@ namespace zg {
 void launch_softmax_temp(float *x, size_t n, float temp);
 void launch_weighted_index(const float *p, size_t n, float u, unsigned long long *out);
 
-constexpr int NTHREADS = NCT + 32; // + producer warp
+typedef unsigned long long u64;
+
+constexpr int NTHREADS = NCT + 32;  // + producer warp
 constexpr int MAXSLOTS = 32;
-constexpr int UB = 8;              // ring units accumulated per reduction round
-constexpr int ATT_CHUNK = 128;     // KV rows per attention work item before splitting
+constexpr int MAX_LAYERS = 64;
+constexpr int ATT_CHUNK = 128;  // KV rows per attention work item before splitting
 constexpr int PROF_MAX = 16384;
+constexpr int LNR = 7;          // LayerNorm elements per thread: E <= 7 * 256
+constexpr int GB = 6;           // flagged pairs a thread keeps in flight while gathering
 
 struct LayerDesc {
   const float *ln1_g, *ln1_b, *w_attn, *b_attn, *w_proj, *b_proj, *ln2_g, *ln2_b, *w_fc, *b_fc, *w_proj2, *b_proj2;
   float *k_cache, *v_cache;
 };
+__constant__ LayerDesc c_layers[MAX_LAYERS];
 
 struct DecodeParams {
   int E, H, hd, L, V, C;
   int nslot, slotf;  // ring geometry: slotf = 4E floats per slot
   const float *wte, *wpe, *lnf_g, *lnf_b;
-  const LayerDesc *layers;
-  float *xres;    // [E]  residual stream (state.o; the reference leaves the pre-ln_f stream there too)
-  float *xout;    // [E]  ln_f output (state.x)
-  float *q;       // [E]  (state._q)
-  float *att;     // [E]  attention output (state._h)
-  float *f;       // [4E] (state._4xh)
-  float *logits;  // [V]  (state.logits)
-  float *att_part;        // [H][S][hd+2] flash-decoding partials
-  unsigned *head_count;   // [H] arrival counters for the split combine
-  unsigned *bar;          // grid barrier word (monotonic)
-  unsigned bar_base;
-  float *amax_val;        // [G]
-  unsigned *amax_idx;     // [G]
-  const unsigned long long *prompt;  // device, n_prompt entries; null => `single_token` is the forced token
-  unsigned long long single_token;
+  // flagged exchange buffers: word = {epoch << 32 | fp32 bits}
+  u64 *xres_f;  // [E]   residual stream
+  u64 *q_f;     // [E]   query of the current token
+  u64 *kvn_f;   // [2E]  K row then V row of the current token (the cache gets the same values, unflagged)
+  u64 *att_f;   // [E]   attention output
+  u64 *f_f;     // [4E]  GELU(c_fc)
+  u64 *amax_f;  // [2G]  per-CTA argmax partial: value word, index word
+  unsigned epoch_base;
+  float *xres_out;  // [E] state.o: the reference leaves the pre-ln_f stream there (main.zig:116-118)
+  float *xout;      // [E] state.x: ln_f output
+  float *logits;    // [V] state.logits
+  float *att_part;       // [H][S][hd+2] flash-decoding partials
+  unsigned *head_count;  // [H] arrival counters for the split combine
+  unsigned *err;         // sticky watchdog word
+  const u64 *prompt;     // device, n_prompt entries; null => `single_token` is the forced token
+  u64 single_token;
   int n_prompt;
-  unsigned long long *tokens;              // device [C]: token forwarded/sampled at every step
-  volatile unsigned long long *tokens_host;  // pinned host ring [C]
-  unsigned long long *last_token;          // device: argmax of the last logits computed
+  u64 *tokens;                 // device [C]: token forwarded/sampled at every step
+  volatile u64 *tokens_host;   // pinned host ring [C]
+  u64 *last_token;             // device: argmax of the last logits computed
   int first_step, n_steps;
-  int force_logits;   // compute logits + argmax on every step (GPT.forward(compute_logits=true) on a prompt step)
-  int store_logits;   // also write the logits vector to global memory
-  int write_xout;     // write ln_f(x) to xout (state.x) on the last step
-  unsigned long long *prof;
-  int dbg;  // debug switches (env ZG_DEBUG): 1 = fence+atomicAdd barrier, 2 = fetch epilogue operands after the wait,
-            // 4 = CTA-wide sync after every GEMV loop
+  int force_logits;  // compute logits + argmax on every step (GPT.forward(compute_logits=true) on a prompt step)
+  int store_logits;  // also write the logits vector to global memory
+  int write_xout;    // write ln_f(x) to xout (state.x) and the stream to xres_out on the last step
+  u64 *prof;
+  int dbg;
 };
 
-// optional fine-grained timeline of CTA 0 / thread 0: (tag, %globaltimer) pairs
+// optional timeline of CTA 0 / thread 0: (tag, %globaltimer) pairs
 struct Prof {
-  unsigned long long *buf;
+  u64 *buf;
   int i;
   __device__ __forceinline__ void mark(int tag) {
     if (buf != nullptr) {
       if (i < PROF_MAX) {
-        buf[2 * i] = (unsigned long long)tag;
+        buf[2 * i] = (u64)tag;
         buf[2 * i + 1] = globaltimer();
       }
       ++i;
     }
   }
 };
+
+// ---- flag-in-data exchange ------------------------------------------------------------------------
+__device__ __forceinline__ void st_flag(u64 *p, float v, unsigned ep) {
+  const u64 w = ((u64)ep << 32) | (u64)__float_as_uint(v);
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ ulonglong2 ld_pair(const u64 *p) {
+  ulonglong2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ u64 ld_word(const u64 *p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool pair_ok(const ulonglong2 &v, unsigned ep) {
+  return (unsigned)(v.x >> 32) == ep && (unsigned)(v.y >> 32) == ep;
+}
+__device__ __forceinline__ float lo_f(u64 w) { return __uint_as_float((unsigned)w); }
+
+__device__ __forceinline__ bool wd_tripped(const Watchdog &wd) {
+  uint32_t t;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(t) : "r"(wd.tripped_smem));
+  return t != 0;
+}
+__device__ __forceinline__ void wd_trip(const Watchdog &wd, unsigned code) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(wd.tripped_smem), "r"(1u));
+  atomicExch(wd.err_global, code);
+}
+// spin until both words of a pair carry `ep` (watchdogged: a protocol bug must not hang the GPU)
+__device__ __noinline__ ulonglong2 spin_pair(const u64 *p, unsigned ep, Watchdog wd) {
+  ulonglong2 v = ld_pair(p);
+  if (wd_tripped(wd)) return v;
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  while (!pair_ok(v, ep)) {
+    v = ld_pair(p);
+    if ((++spins & 255u) == 0 && clock64() - t0 > WATCHDOG_CYCLES) {
+      wd_trip(wd, 3u);
+      break;
+    }
+  }
+  return v;
+}
+__device__ __noinline__ u64 spin_word(const u64 *p, unsigned ep, Watchdog wd) {
+  u64 v = ld_word(p);
+  if (wd_tripped(wd)) return v;
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  while ((unsigned)(v >> 32) != ep) {
+    v = ld_word(p);
+    if ((++spins & 255u) == 0 && clock64() - t0 > WATCHDOG_CYCLES) {
+      wd_trip(wd, 4u);
+      break;
+    }
+  }
+  return v;
+}
+// gather n floats (n even) whose words must carry epoch `ep` into shared memory; all loads of a thread are
+// issued before the first check, so the common case costs one L2 round trip
+__device__ __forceinline__ void gather_flagged(float *dst_smem, const u64 *src, int n, unsigned ep, const Watchdog &wd) {
+  const int npairs = n >> 1;
+#pragma unroll 1
+  for (int base = 0; base < npairs; base += GB * NCT) {
+    ulonglong2 v[GB];
+#pragma unroll
+    for (int j = 0; j < GB; ++j) {
+      const int idx = base + j * NCT + (int)threadIdx.x;
+      if (idx < npairs) v[j] = ld_pair(src + 2 * idx);
+    }
+#pragma unroll
+    for (int j = 0; j < GB; ++j) {
+      const int idx = base + j * NCT + (int)threadIdx.x;
+      if (idx < npairs) {
+        if (!pair_ok(v[j], ep)) v[j] = spin_pair(src + 2 * idx, ep, wd);
+        reinterpret_cast<float2 *>(dst_smem)[idx] = make_float2(lo_f(v[j].x), lo_f(v[j].y));
+      }
+    }
+  }
+}
 
 // rows [r0, r1) of an N-row matrix owned by this CTA in a phase; `rot` rotates which CTAs get the remainder rows
 __device__ __forceinline__ void row_range(int cta, int G, int rot, int N, int &r0, int &r1) {
@@ -101,82 +193,48 @@ __device__ __forceinline__ int phase_rot(int layer, int ph, int G) { return ((la
 // 3 = c_fc, 4 = mlp c_proj; the tied lm_head is phase index 5L of a step.
 enum { M_QKV = 0, M_RESID = 1, M_GELU = 2, M_LMHEAD = 3 };
 struct PhaseDesc {
-  const float *W, *bias, *ln_g, *ln_b, *src;
+  const float *W, *bias, *ln_g, *ln_b;
+  const u64 *src;
   int N, K, mode, rot;
 };
 __device__ __forceinline__ PhaseDesc phase_desc(const DecodeParams &p, int l, int ph, bool is_head, int G) {
   PhaseDesc d;
   const int E = p.E;
   if (is_head) {
-    d = PhaseDesc{p.wte, nullptr, p.lnf_g, p.lnf_b, p.xres, p.V, E, M_LMHEAD, 0};
+    d = PhaseDesc{p.wte, nullptr, p.lnf_g, p.lnf_b, p.xres_f, p.V, E, M_LMHEAD, 0};
     return d;
   }
-  const LayerDesc &ld = p.layers[l];
+  const LayerDesc &ld = c_layers[l];
   d.rot = phase_rot(l, ph, G);
   d.K = E;
   d.ln_g = d.ln_b = nullptr;
   if (ph == 0) {
-    d.W = ld.w_attn; d.bias = ld.b_attn; d.ln_g = ld.ln1_g; d.ln_b = ld.ln1_b; d.src = p.xres; d.N = 3 * E; d.mode = M_QKV;
+    d.W = ld.w_attn; d.bias = ld.b_attn; d.ln_g = ld.ln1_g; d.ln_b = ld.ln1_b; d.src = p.xres_f; d.N = 3 * E; d.mode = M_QKV;
   } else if (ph == 2) {
-    d.W = ld.w_proj; d.bias = ld.b_proj; d.src = p.att; d.N = E; d.mode = M_RESID;
+    d.W = ld.w_proj; d.bias = ld.b_proj; d.src = p.att_f; d.N = E; d.mode = M_RESID;
   } else if (ph == 3) {
-    d.W = ld.w_fc; d.bias = ld.b_fc; d.ln_g = ld.ln2_g; d.ln_b = ld.ln2_b; d.src = p.xres; d.N = 4 * E; d.mode = M_GELU;
+    d.W = ld.w_fc; d.bias = ld.b_fc; d.ln_g = ld.ln2_g; d.ln_b = ld.ln2_b; d.src = p.xres_f; d.N = 4 * E; d.mode = M_GELU;
   } else {
-    d.W = ld.w_proj2; d.bias = ld.b_proj2; d.src = p.f; d.N = E; d.K = 4 * E; d.mode = M_RESID;
+    d.W = ld.w_proj2; d.bias = ld.b_proj2; d.src = p.f_f; d.N = E; d.K = 4 * E; d.mode = M_RESID;
   }
   return d;
 }
 
 struct Smem {
   float *ring;   // nslot * slotf
-  float *vec;    // 4E: activation vector the GEMV phases read
+  float *vec;    // 2 x 4E: activation vector the GEMV phases read, double-buffered: with no CTA-wide sync at the
+                 // end of a phase, a fast warp may already be gathering the next vector while a slow one still reads
+                 // the current one (a gather into buffer b is two CTA syncs after the last read of buffer b)
   float *xv;     // E: staging for LayerNorm input
-  float *sc;     // C: attention scores
   float *part;   // NCW * hd attention partial outputs
   float *red;    // 64
   uint32_t full0, empty0;  // shared addresses of mbarrier arrays
   Watchdog wd;             // sticky global error word + CTA-local tripped flag
 };
 
-// grid-wide barrier among the consumer threads of all CTAs (the producer warp never takes part)
-__device__ __forceinline__ void grid_barrier(const DecodeParams &p, unsigned &target, int G, Prof &pf, int tag) {
-  target += (unsigned)G;
-  consumer_sync();
-  if (threadIdx.x == 0) {
-    if (p.dbg & 1) {
-      __threadfence();
-      atomicAdd(p.bar, 1u);
-    } else {
-      red_release_gpu(p.bar, 1u);
-    }
-    if ((int)(ld_relaxed(p.bar) - target) < 0) {
-      const long long t0 = clock64();
-      unsigned spins = 0;
-      while ((int)(ld_relaxed(p.bar) - target) < 0) {
-        if ((++spins & 1023u) == 0 && (clock64() - t0 > WATCHDOG_CYCLES || ld_relaxed(p.bar + 32))) {
-          atomicExch(p.bar + 32, 1u);
-          break;
-        }
-      }
-    }
-    fence_acquire_gpu();
-    pf.mark(tag);
-  }
-  consumer_sync();
-}
-
-// n floats (n % 4 == 0) from global memory written by other CTAs (read through L2, never L1) into shared memory
-__device__ __forceinline__ void load_vec4(float *dst_smem, const float *src, int n) {
-  const float4 *s4 = reinterpret_cast<const float4 *>(src);
-  float4 *d4 = reinterpret_cast<float4 *>(dst_smem);
-#pragma unroll 1
-  for (int i = threadIdx.x; i < (n >> 2); i += NCT) d4[i] = __ldcg(s4 + i);
-}
-
 // LayerNorm of the E-vector in smem `src` into smem `dst`; reference formula ops.zig:86-101.  The affine
 // parameters arrive in registers (element i = tid + j*NCT), fetched at the top of the phase so that their
 // global-memory latency overlaps the activation gather.
-constexpr int LNR = 7;  // E <= 7 * 256
 __device__ __forceinline__ void layer_norm_to_smem(const float *src_smem, float *dst, const float (&lg)[LNR],
                                                    const float (&lb)[LNR], int E, float eps, float *red) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -222,156 +280,147 @@ __device__ __forceinline__ void load_ln_params(const float *g, const float *b, i
 }
 
 // Attention work item (head h, split s of S) over cache rows [t0,t1) -- ops.zig:249-307 without the
-// whole-cache transposes: K/V are read in place from the time-major cache (head stride hd, time stride E).
-__device__ __noinline__ void attention_item(const DecodeParams &p, const Smem &sm, const LayerDesc &ld, int h, int s,
-                                            int S, int T) {
+// whole-cache transposes: K/V of earlier tokens are read in place from the time-major cache (head stride hd = 64,
+// time stride E); q and the current token's K/V row arrive through the flagged exchange (epoch `ep_in`).
+// One pass with an online softmax per warp, merged across warps in shared memory.
+__device__ __noinline__ void attention_item(const DecodeParams &p, const Smem &sm, int l, int h, int s, int S, int T,
+                                            unsigned ep_in, unsigned ep_out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int hd = p.hd, E = p.E;
+  constexpr int hd = 64;
+  const int E = p.E, pos = T - 1;
   const int chunk = (T + S - 1) / S;
-  const int t0 = s * chunk, t1 = min(T, t0 + chunk), n = t1 - t0;
-  const float scale = 1.0f / sqrtf((float)hd);
-  const float *qh = p.q + h * hd;
-  const float *kh = ld.k_cache + h * hd;
-  const float *vh = ld.v_cache + h * hd;
+  const int t0 = s * chunk, t1 = min(T, t0 + chunk);
+  const float scale = 0.125f;  // 1 / sqrt(64)
+  const float *kh = c_layers[l].k_cache + h * hd;
+  const float *vh = c_layers[l].v_cache + h * hd;
   float *po = sm.part;  // [NCW][hd] per-warp partial outputs
-  float m, l;
-  if (hd == 64) {
-    // fast path (every GPT-2 size): a cache row of one head is 256 B = one float2 per lane.  One pass with
-    // an online softmax per warp (K and V rows of 4 cache rows in flight together), merged across warps below.
-    const float2 qv = __ldcg(reinterpret_cast<const float2 *>(qh) + lane);
-    float mw = -INFINITY, lw = 0.0f;
-    float2 acc = make_float2(0.0f, 0.0f);
+
+  // cache rows do not depend on this step: put the first batch in flight before waiting for q
+  const bool has_new = (pos >= t0 && pos < t1);
+  float2 kv[4], vv[4];
+  const int tfirst = t0 + warp;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int tt = tfirst + u * NCW;
+    kv[u] = make_float2(0.0f, 0.0f);
+    vv[u] = make_float2(0.0f, 0.0f);
+    if (tt < t1 && tt != pos) {
+      kv[u] = __ldcg(reinterpret_cast<const float2 *>(kh + (size_t)tt * E) + lane);
+      vv[u] = __ldcg(reinterpret_cast<const float2 *>(vh + (size_t)tt * E) + lane);
+    }
+  }
+  ulonglong2 qw = ld_pair(p.q_f + h * hd + 2 * lane);
+  ulonglong2 kw = qw, vw = qw;
+  if (has_new) {
+    kw = ld_pair(p.kvn_f + h * hd + 2 * lane);
+    vw = ld_pair(p.kvn_f + E + h * hd + 2 * lane);
+  }
+  if (!pair_ok(qw, ep_in)) qw = spin_pair(p.q_f + h * hd + 2 * lane, ep_in, sm.wd);
+  if (has_new) {
+    if (!pair_ok(kw, ep_in)) kw = spin_pair(p.kvn_f + h * hd + 2 * lane, ep_in, sm.wd);
+    if (!pair_ok(vw, ep_in)) vw = spin_pair(p.kvn_f + E + h * hd + 2 * lane, ep_in, sm.wd);
+  }
+  const float2 qv = make_float2(lo_f(qw.x), lo_f(qw.y));
+  const float2 knew = make_float2(lo_f(kw.x), lo_f(kw.y)), vnew = make_float2(lo_f(vw.x), lo_f(vw.y));
+
+  float mw = -INFINITY, lw = 0.0f;
+  float2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll 1
-    for (int t = t0 + warp; t < t1; t += 4 * NCW) {
-      float2 kv[4], vv[4];
+  for (int t = tfirst; t < t1; t += 4 * NCW) {
+    if (t != tfirst) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int tt = t + u * NCW;
-        kv[u] = make_float2(0.0f, 0.0f);
-        vv[u] = make_float2(0.0f, 0.0f);
-        if (tt < t1) {
+        if (tt < t1 && tt != pos) {
           kv[u] = __ldcg(reinterpret_cast<const float2 *>(kh + (size_t)tt * E) + lane);
           vv[u] = __ldcg(reinterpret_cast<const float2 *>(vh + (size_t)tt * E) + lane);
         }
       }
-      float a[4];
+    }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) a[u] = fmaf(qv.x, kv[u].x, qv.y * kv[u].y);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) a[u] = warp_sum(a[u]) * scale;
-      float mnew = mw;
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (t + u * NCW < t1) mnew = fmaxf(mnew, a[u]);
-      const float corr = (mw == -INFINITY) ? 0.0f : expf(mw - mnew);
-      lw *= corr;
-      acc.x *= corr;
-      acc.y *= corr;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (t + u * NCW < t1) {
-          const float pt = expf(a[u] - mnew);
-          lw += pt;
-          acc.x = fmaf(pt, vv[u].x, acc.x);
-          acc.y = fmaf(pt, vv[u].y, acc.y);
-        }
+    for (int u = 0; u < 4; ++u) {
+      if (t + u * NCW == pos) {
+        kv[u] = knew;
+        vv[u] = vnew;
       }
-      mw = mnew;
     }
-    po[warp * hd + 2 * lane] = acc.x;
-    po[warp * hd + 2 * lane + 1] = acc.y;
-    if (lane == 0) {
-      sm.red[16 + warp] = mw;
-      sm.red[24 + warp] = lw;
+    float a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = fmaf(qv.x, kv[u].x, qv.y * kv[u].y);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = warp_sum(a[u]) * scale;
+    float mnew = mw;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (t + u * NCW < t1) mnew = fmaxf(mnew, a[u]);
+    const float corr = (mw == -INFINITY) ? 0.0f : expf(mw - mnew);
+    lw *= corr;
+    acc.x *= corr;
+    acc.y *= corr;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (t + u * NCW < t1) {
+        const float pt = expf(a[u] - mnew);
+        lw += pt;
+        acc.x = fmaf(pt, vv[u].x, acc.x);
+        acc.y = fmaf(pt, vv[u].y, acc.y);
+      }
     }
-    consumer_sync();
-    m = -INFINITY;
+    mw = mnew;
+  }
+  po[warp * hd + 2 * lane] = acc.x;
+  po[warp * hd + 2 * lane + 1] = acc.y;
+  if (lane == 0) {
+    sm.red[16 + warp] = mw;
+    sm.red[24 + warp] = lw;
+  }
+  consumer_sync();
+  if (tid < hd) {
+    float m = -INFINITY;
 #pragma unroll
     for (int w = 0; w < NCW; ++w) m = fmaxf(m, sm.red[16 + w]);
-    l = 0.0f;
-    float wsc[NCW];
+    float lsum = 0.0f, o = 0.0f;
 #pragma unroll
     for (int w = 0; w < NCW; ++w) {
       const float mwv = sm.red[16 + w];
-      wsc[w] = (mwv == -INFINITY) ? 0.0f : expf(mwv - m);
-      l = fmaf(sm.red[24 + w], wsc[w], l);
+      const float sc = (mwv == -INFINITY) ? 0.0f : expf(mwv - m);
+      lsum = fmaf(sm.red[24 + w], sc, lsum);
+      o = fmaf(po[w * hd + tid], sc, o);
     }
-    // rescale the per-warp partial outputs in place so the common tail below can just add them up
-    if (tid < hd) {
-#pragma unroll
-      for (int w = 0; w < NCW; ++w) po[w * hd + tid] *= wsc[w];
-    }
-  } else {
-    // generic head_dim: one cache row per warp iteration, hd spread over lanes
-#pragma unroll 1
-    for (int t = t0 + warp; t < t1; t += NCW) {
-      float a = 0.0f;
-      for (int d = lane; d < hd; d += 32) a = fmaf(__ldcg(qh + d), __ldcg(kh + (size_t)t * E + d), a);
-      a = warp_sum(a);
-      if (lane == 0) sm.sc[t - t0] = a * scale;
-    }
-    consumer_sync();
-    m = -INFINITY;
-    for (int i = lane; i < n; i += 32) m = fmaxf(m, sm.sc[i]);
-    m = warp_max(m);
-    l = 0.0f;
-    for (int i = lane; i < n; i += 32) l += expf(sm.sc[i] - m);
-    l = warp_sum(l);
-#pragma unroll 1
-    for (int d = lane; d < hd; d += 32) {
-      float a = 0.0f;
-      for (int t = t0 + warp; t < t1; t += NCW) a = fmaf(expf(sm.sc[t - t0] - m), __ldcg(vh + (size_t)t * E + d), a);
-      po[warp * hd + d] = a;
+    if (S == 1) {
+      st_flag(p.att_f + h * hd + tid, o / lsum, ep_out);
+    } else {  // flash-decoding partial: (m, l, unnormalised o)
+      float *mine = p.att_part + ((size_t)h * S + s) * (hd + 2);
+      mine[2 + tid] = o;
+      if (tid == 0) {
+        mine[0] = m;
+        mine[1] = lsum;
+      }
     }
   }
-  consumer_sync();
-  if (S == 1) {
-#pragma unroll 1
-    for (int d = tid; d < hd; d += NCT) {
-      float a = 0.0f;
-#pragma unroll
-      for (int w = 0; w < NCW; ++w) a += po[w * hd + d];
-      p.att[h * hd + d] = a / l;
-    }
-    return;
-  }
-  // flash-decoding partial (m, l, unnormalised o); the last split of this head to arrive combines them
-  float *mine = p.att_part + ((size_t)h * S + s) * (hd + 2);
-#pragma unroll 1
-  for (int d = tid; d < hd; d += NCT) {
-    float a = 0.0f;
-#pragma unroll
-    for (int w = 0; w < NCW; ++w) a += po[w * hd + d];
-    mine[2 + d] = a;
-  }
-  if (tid == 0) {
-    mine[0] = m;
-    mine[1] = l;
-  }
+  if (S == 1) return;
+  // the last split of this head to arrive combines the partials (the only fence left: long contexts only)
   __threadfence();
   consumer_sync();
   if (tid == 0) {
     const unsigned old = atomicAdd(p.head_count + h, 1u);
     const bool last = (old == (unsigned)(S - 1));
-    if (last) p.head_count[h] = 0u;  // ready for the next layer (ordered by the grid barrier that follows)
+    if (last) p.head_count[h] = 0u;
     sm.red[32] = last ? 1.0f : 0.0f;
     __threadfence();
   }
   consumer_sync();
-  if (sm.red[32] != 0.0f) {
+  if (sm.red[32] != 0.0f && tid < hd) {
     const float *base = p.att_part + (size_t)h * S * (hd + 2);
     float M = -INFINITY;
     for (int i = 0; i < S; ++i) M = fmaxf(M, __ldcg(base + (size_t)i * (hd + 2)));
-    float Lsum = 0.0f;
-    for (int i = 0; i < S; ++i)
-      Lsum += __ldcg(base + (size_t)i * (hd + 2) + 1) * expf(__ldcg(base + (size_t)i * (hd + 2)) - M);
-#pragma unroll 1
-    for (int d = tid; d < hd; d += NCT) {
-      float a = 0.0f;
-      for (int i = 0; i < S; ++i)
-        a += __ldcg(base + (size_t)i * (hd + 2) + 2 + d) * expf(__ldcg(base + (size_t)i * (hd + 2)) - M);
-      p.att[h * hd + d] = a / Lsum;
+    float Lsum = 0.0f, a = 0.0f;
+    for (int i = 0; i < S; ++i) {
+      const float sc = expf(__ldcg(base + (size_t)i * (hd + 2)) - M);
+      Lsum = fmaf(__ldcg(base + (size_t)i * (hd + 2) + 1), sc, Lsum);
+      a = fmaf(__ldcg(base + (size_t)i * (hd + 2) + 2 + tid), sc, a);
     }
+    st_flag(p.att_f + h * hd + tid, a / Lsum, ep_out);
   }
 }
 
@@ -381,25 +430,24 @@ __device__ __forceinline__ bool step_needs_logits(const DecodeParams &p, int ste
 
 __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const DecodeParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long mbar_store[2 * MAXSLOTS];
-  __shared__ unsigned wd_tripped;
+  __shared__ __align__(8) u64 mbar_store[2 * MAXSLOTS];
+  __shared__ unsigned wd_flag;
   const int G = gridDim.x, cta = blockIdx.x;
   const int E = p.E, E4 = 4 * p.E;
   const int nslot = p.nslot, slotf = p.slotf;
   Smem sm;
   sm.ring = reinterpret_cast<float *>(smem_raw);
   sm.vec = sm.ring + (size_t)nslot * slotf;
-  sm.xv = sm.vec + E4;
-  sm.sc = sm.xv + E;
-  sm.part = sm.sc + p.C;
+  sm.xv = sm.vec + 2 * E4;
+  sm.part = sm.xv + E;
   sm.red = sm.part + NCW * p.hd;
   sm.full0 = smem_u32(mbar_store);
   sm.empty0 = smem_u32(mbar_store + MAXSLOTS);
-  sm.wd.err_global = p.bar + 32;  // its own 128-byte line, away from the barrier word
-  sm.wd.tripped_smem = smem_u32(&wd_tripped);
+  sm.wd.err_global = p.err;
+  sm.wd.tripped_smem = smem_u32(&wd_flag);
 
   if (threadIdx.x == 0) {
-    wd_tripped = 0u;
+    wd_flag = 0u;
     for (int i = 0; i < nslot; ++i) {
       mbar_init(sm.full0 + 8u * i, 1);
       mbar_init(sm.empty0 + 8u * i, 1);  // one warp owns a ring unit and releases it
@@ -431,7 +479,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         const PhaseDesc d = phase_desc(p, l, ph, is_head, G);
         if (!is_head && ph == 0 && lane < 8) {
           // pull the layer's small vectors (LayerNorm affine + biases, 13E floats) into L2 ahead of the consumers
-          const LayerDesc &ld = p.layers[l];
+          const LayerDesc &ld = c_layers[l];
           const float *arr = lane == 0 ? ld.ln1_g : lane == 1 ? ld.ln1_b : lane == 2 ? ld.b_attn : lane == 3 ? ld.b_proj
                            : lane == 4 ? ld.ln2_g : lane == 5 ? ld.ln2_b : lane == 6 ? ld.b_fc : ld.b_proj2;
           const int len = lane == 2 ? 3 * E : lane == 6 ? E4 : E;
@@ -461,107 +509,127 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
 
   // ================================= consumer warps =================================
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned target = p.bar_base;
   Prof pf{(p.prof && cta == 0 && tid == 0) ? p.prof : nullptr, 0};
   pf.mark(0);
-  unsigned long long prev_token = 0;
-  unsigned useq = 0;  // ring units consumed by this CTA so far (slot = useq % nslot, parity = (useq / nslot) & 1)
+  u64 prev_token = 0;
+  unsigned useq = 0;            // ring units consumed by this CTA so far (slot = useq % nslot, parity = (useq / nslot) & 1)
+  unsigned ep = p.epoch_base;   // epoch of the phase being executed; its inputs carry ep - 1
+  int vsel = 0;                 // which half of sm.vec the current GEMV phase reads
 
 #pragma unroll 1
   for (int step = p.first_step; step <= last_step; ++step) {
     const int pos = step, T = step + 1;  // seq_len = step + 1 (main.zig:333,337)
-    unsigned long long tok;
+    u64 tok;
     if (step < p.n_prompt) tok = p.prompt ? p.prompt[step] : p.single_token;
     else if (step == p.first_step) tok = step > 0 ? __ldcg(p.tokens + step - 1) : 0ull;
     else tok = prev_token;
-    if (tok >= (unsigned long long)p.V) tok = 0;  // never index the embedding out of bounds, whatever came in
+    if (tok >= (u64)p.V) tok = 0;  // never index the embedding out of bounds, whatever came in
     const bool want_logits = step_needs_logits(p, step);
     const int nph = L5 + (want_logits ? 1 : 0);
-    unsigned long long out_tok = tok;
+    u64 out_tok = tok;
+    const float *te = p.wte + (size_t)tok * E, *pe = p.wpe + (size_t)pos * E;  // main.zig:179-180
 
 #pragma unroll 1
     for (int g = 0; g < nph; ++g) {
+      ++ep;
       const int l = g / 5, ph = g - 5 * l;
       const bool is_head = (g == L5);
       const int tag = is_head ? 96 : 16 * (ph + 1);
-      float best = -INFINITY;  // running argmax of the rows this lane finishes (lm_head only)
-      unsigned best_i = 0xffffffffu;
 
       if (!is_head && ph == 1) {
         // ---------------- attention over the cache (ops.zig:160-171) ----------------
         int S = (T + ATT_CHUNK - 1) / ATT_CHUNK;
         const int smax = G / p.H;
         if (S > smax) S = smax;
-        if (cta < p.H * S) attention_item(p, sm, p.layers[l], cta / S, cta % S, S, T);
-      } else {
-        const PhaseDesc d = phase_desc(p, l, ph, is_head, G);
-        // ---------------- phase-top prefetch: everything whose address is known before the activation arrives
-        int r0, r1;
-        row_range(cta, G, d.rot, d.N, r0, r1);
-        const int rps = slotf / d.K;  // rows per unit: 4 (K = E) or 1 (K = 4E)
-        const int nrows = r1 - r0;
-        const int n_units = (nrows + rps - 1) / rps;
-        const int rw = nslot < NCW ? nslot : NCW;
-        float bias0 = 0.0f, resid0 = 0.0f;
-        if (warp < rw && warp < n_units && lane < min(rps, nrows - warp * rps)) {
-          if (d.bias) bias0 = __ldg(d.bias + r0 + warp * rps + lane);
-          if (d.mode == M_RESID) resid0 = __ldcg(p.xres + r0 + warp * rps + lane);
-        }
-        float lg[LNR], lb[LNR];
-        if (d.ln_g != nullptr) load_ln_params(d.ln_g, d.ln_b, E, lg, lb);
-        // ---------------- activation vector -> shared memory ----------------
-        if (d.ln_g != nullptr) {
-          if (g == 0) {  // wte[token] + wpe[pos] (main.zig:179-183), recomputed by every CTA
-            const float *te = p.wte + (size_t)tok * E, *pe = p.wpe + (size_t)pos * E;
-#pragma unroll 1
-            for (int i = tid; i < E; i += NCT) {
-              const float v = __ldg(te + i) + __ldg(pe + i);
-              sm.xv[i] = v;
-              if (cta == 0) p.xres[i] = v;
-            }
-          } else {
-            load_vec4(sm.xv, d.src, E);
-          }
-          consumer_sync();
-          layer_norm_to_smem(sm.xv, sm.vec, lg, lb, E, 1e-5f, sm.red);  // main.zig:123,140,189
-          if (is_head && p.write_xout && step == last_step && cta == 0) {
-#pragma unroll 1
-            for (int i = tid; i < E; i += NCT) p.xout[i] = sm.vec[i];
-          }
-        } else {
-          load_vec4(sm.vec, d.src, d.K);
-          consumer_sync();
-        }
-        pf.mark(tag + 1);
+        if (cta < p.H * S) attention_item(p, sm, l, cta / S, cta % S, S, T, ep - 1, ep);
+        pf.mark(tag + 3);
+        continue;
+      }
 
-        // ---------------- GEMV: one warp per ring unit ----------------
-        float *kc = nullptr, *vc = nullptr;
-        if (d.mode == M_QKV) {
-          kc = p.layers[l].k_cache + (size_t)pos * E;
-          vc = p.layers[l].v_cache + (size_t)pos * E;
+      const PhaseDesc d = phase_desc(p, l, ph, is_head, G);
+      vsel ^= 1;
+      float *vec = sm.vec + vsel * E4;
+      // ---------------- phase top: everything whose address is known before the activation arrives ----------
+      int r0, r1;
+      row_range(cta, G, d.rot, d.N, r0, r1);
+      const int rps = slotf / d.K;  // rows per unit: 4 (K = E) or 1 (K = 4E)
+      const int nrows = r1 - r0;
+      const int n_units = (nrows + rps - 1) / rps;
+      const int rw = nslot < NCW ? nslot : NCW;
+      // residual operand of the rows this lane will finish: the embedding itself in the first block
+      // (main.zig:181-183), otherwise the stream word written two (P5) or three (P3) phases ago
+      const bool resid_from_emb = (l == 0 && ph == 2);
+      const unsigned ep_resid = ep - (ph == 2 ? 3u : 2u);
+      float bias0 = 0.0f, resid0 = 0.0f;
+      u64 resid_w = 0;
+      const bool own0 = (warp < rw && warp < n_units && lane < min(rps, nrows - warp * rps));
+      if (own0) {
+        const int r = r0 + warp * rps + lane;
+        if (d.bias) bias0 = __ldg(d.bias + r);
+        if (d.mode == M_RESID) {
+          if (resid_from_emb) resid0 = __ldg(te + r) + __ldg(pe + r);
+          else resid_w = ld_word(p.xres_f + r);
         }
-        float *logits = (is_head && p.store_logits && step == last_step) ? p.logits : nullptr;
-        const float4 *vec4 = reinterpret_cast<const float4 *>(sm.vec);
-        const int k4 = d.K >> 2;
-        // Warps advance through the ring in lockstep rounds of `rw` consecutive units with a CTA sync between
-        // rounds.  An mbarrier only tracks phase PARITY: a warp that waited on a slot's next fill while the
-        // current fill was still in flight would see the matching parity and read stale data.  Keeping every
-        // round's units on distinct slots (rw <= nslot) and finishing a round before the next starts rules
-        // that out.
+      }
+      float lg[LNR], lb[LNR];
+      if (d.ln_g != nullptr) load_ln_params(d.ln_g, d.ln_b, E, lg, lb);
+
+      // ---------------- activation vector -> shared memory ----------------
+      if (d.ln_g != nullptr) {
+        if (g == 0) {  // wte[token] + wpe[pos] (main.zig:179-183), recomputed by every CTA
 #pragma unroll 1
-        for (int ub = 0; ub < n_units; ub += rw) {
-          const int u = ub + warp;
-          if (warp < rw && u < n_units) {
+          for (int i = tid; i < E; i += NCT) sm.xv[i] = __ldg(te + i) + __ldg(pe + i);
+        } else {
+          gather_flagged(sm.xv, d.src, E, ep - 1, sm.wd);
+        }
+        consumer_sync();
+        layer_norm_to_smem(sm.xv, vec, lg, lb, E, 1e-5f, sm.red);  // main.zig:123,140,189
+        if (is_head && p.write_xout && step == last_step && cta == 0) {
+#pragma unroll 1
+          for (int i = tid; i < E; i += NCT) {
+            p.xout[i] = vec[i];
+            p.xres_out[i] = sm.xv[i];
+          }
+        }
+      } else {
+        gather_flagged(vec, d.src, d.K, ep - 1, sm.wd);
+        consumer_sync();
+      }
+      pf.mark(tag + 1);
+
+      // ---------------- GEMV: one warp per ring unit ----------------
+      float *kc = nullptr, *vc = nullptr;
+      if (d.mode == M_QKV) {
+        kc = c_layers[l].k_cache + (size_t)pos * E;
+        vc = c_layers[l].v_cache + (size_t)pos * E;
+      }
+      float *logits = (is_head && p.store_logits && step == last_step) ? p.logits : nullptr;
+      const float4 *vec4 = reinterpret_cast<const float4 *>(vec);
+      const int k4 = d.K >> 2;
+      float best = -INFINITY;  // running argmax of the rows this lane finishes (lm_head only)
+      unsigned best_i = 0xffffffffu;
+      // Warps advance through the ring in lockstep rounds of `rw` consecutive units with a CTA sync between
+      // rounds.  An mbarrier only tracks phase PARITY: a warp that waited on a slot's next fill while the
+      // current fill was still in flight would see the matching parity and read stale data.  Keeping every
+      // round's units on distinct slots (rw <= nslot) and finishing a round before the next starts rules
+      // that out.
+#pragma unroll 1
+      for (int ub = 0; ub < n_units; ub += rw) {
+        const int u = ub + warp;
+        if (warp < rw && u < n_units) {
           const unsigned n = useq + (unsigned)u;
           const int slot = (int)(n % (unsigned)nslot);
           const uint32_t parity = (n / (unsigned)nslot) & 1u;
           const int rbase = r0 + u * rps;
           const int rows_here = min(rps, r1 - rbase);
-          // epilogue operands are fetched before the wait so their L2 latency hides behind it
           float bias_v = bias0, resid_v = resid0;
+          u64 rw_word = resid_w;
           if (ub > 0 && lane < rows_here) {
             if (d.bias) bias_v = __ldg(d.bias + rbase + lane);
-            if (d.mode == M_RESID) resid_v = __ldcg(p.xres + rbase + lane);
+            if (d.mode == M_RESID) {
+              if (resid_from_emb) resid_v = __ldg(te + rbase + lane) + __ldg(pe + rbase + lane);
+              else rw_word = ld_word(p.xres_f + rbase + lane);
+            }
           }
           mbar_wait(sm.full0 + 8u * slot, parity, sm.wd);
           const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)slot * slotf);
@@ -601,61 +669,66 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
             const int r = rbase + lane;
             float v = lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : a3;
             v += bias_v;
-            if (d.mode == M_QKV) {  // q to scratch, k/v straight into cache row `pos` (ops.zig:146-158)
-              if (r < E) p.q[r] = v;
-              else if (r < 2 * E) kc[r - E] = v;
-              else vc[r - 2 * E] = v;
+            if (d.mode == M_QKV) {  // q to the exchange, k/v to cache row `pos` (ops.zig:146-158) and to the exchange
+              if (r < E) {
+                st_flag(p.q_f + r, v, ep);
+              } else if (r < 2 * E) {
+                kc[r - E] = v;
+                st_flag(p.kvn_f + (r - E), v, ep);
+              } else {
+                vc[r - 2 * E] = v;
+                st_flag(p.kvn_f + E + (r - 2 * E), v, ep);
+              }
             } else if (d.mode == M_RESID) {  // main.zig:136-139,142-145
-              p.xres[r] = v + resid_v;
+              if (!resid_from_emb) {
+                if ((unsigned)(rw_word >> 32) != ep_resid) rw_word = spin_word(p.xres_f + r, ep_resid, sm.wd);
+                resid_v = lo_f(rw_word);
+              }
+              st_flag(p.xres_f + r, v + resid_v, ep);
             } else if (d.mode == M_GELU) {  // main.zig:80
-              p.f[r] = gelu_ref(v);
+              st_flag(p.f_f + r, gelu_ref(v), ep);
             } else {  // tied lm_head (main.zig:193) + running argmax; this lane sees increasing r, so strict >
               if (logits) logits[r] = v;
               if (v > best) { best = v; best_i = (unsigned)r; }
             }
           }
-          }
-          if (ub + rw < n_units) consumer_sync();
         }
-        useq += (unsigned)n_units;
-        if (p.dbg & 4) consumer_sync();
-        pf.mark(tag + 3);
-
-        if (is_head) {
-          // CTA-level argmax (value desc, index asc), then one partial per CTA
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const unsigned oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-            if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
-          }
-          if (lane == 0) {
-            sm.red[16 + warp] = best;
-            sm.red[24 + warp] = __uint_as_float(best_i);
-          }
-          consumer_sync();
-          if (tid == 0) {
-            for (int w = 1; w < NCW; ++w) {
-              const float ov = sm.red[16 + w];
-              const unsigned oi = __float_as_uint(sm.red[24 + w]);
-              if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
-            }
-            p.amax_val[cta] = best;
-            p.amax_idx[cta] = best_i;
-          }
-        }
+        if (ub + rw < n_units) consumer_sync();
       }
-
-      grid_barrier(p, target, G, pf, tag + 4);
+      useq += (unsigned)n_units;
+      pf.mark(tag + 3);
 
       if (is_head) {
-        // every CTA reduces the G partials itself: the next step's embedding needs the token everywhere
+        // CTA-level argmax (value desc, index asc), one flagged partial per CTA, then every CTA reduces the G
+        // partials itself: the next step's embedding needs the token everywhere
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+          const unsigned oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+          if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+        }
+        if (lane == 0) {
+          sm.red[16 + warp] = best;
+          sm.red[24 + warp] = __uint_as_float(best_i);
+        }
+        consumer_sync();
+        if (tid == 0) {
+          for (int w = 1; w < NCW; ++w) {
+            const float ov = sm.red[16 + w];
+            const unsigned oi = __float_as_uint(sm.red[24 + w]);
+            if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+          }
+          st_flag(p.amax_f + 2 * cta, best, ep);
+          st_flag(p.amax_f + 2 * cta + 1, __uint_as_float(best_i), ep);
+        }
         if (tid < 32) {
           float bv = -INFINITY;
           unsigned bi = 0xffffffffu;
           for (int i = tid; i < G; i += 32) {
-            const float ov = __ldcg(p.amax_val + i);
-            const unsigned oi = __ldcg(p.amax_idx + i);
+            ulonglong2 w = ld_pair(p.amax_f + 2 * i);
+            if (!pair_ok(w, ep)) w = spin_pair(p.amax_f + 2 * i, ep, sm.wd);
+            const float ov = lo_f(w.x);
+            const unsigned oi = (unsigned)w.y;
             if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
           }
 #pragma unroll
@@ -667,10 +740,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           if (tid == 0) sm.red[40] = __uint_as_float(bi);
         }
         consumer_sync();
-        const unsigned long long amax = (unsigned long long)__float_as_uint(sm.red[40]);
+        const u64 amax = (u64)__float_as_uint(sm.red[40]);
         if (cta == 0 && tid == 0) *p.last_token = amax;
         if (step >= p.n_prompt) out_tok = amax;  // generate(): main.zig:335-338
         consumer_sync();
+        pf.mark(tag + 4);
       }
     }
 
@@ -678,11 +752,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
       // GPT.forward(compute_logits = false) still leaves ln_f(x) in state.x (main.zig:189)
       float lg[LNR], lb[LNR];
       load_ln_params(p.lnf_g, p.lnf_b, E, lg, lb);
-      load_vec4(sm.xv, p.xres, E);
+      gather_flagged(sm.xv, p.xres_f, E, ep, sm.wd);
       consumer_sync();
+      consumer_sync();  // every warp is past the last GEMV's reads of sm.vec
       layer_norm_to_smem(sm.xv, sm.vec, lg, lb, E, 1e-5f, sm.red);
 #pragma unroll 1
-      for (int i = tid; i < E; i += NCT) p.xout[i] = sm.vec[i];
+      for (int i = tid; i < E; i += NCT) {
+        p.xout[i] = sm.vec[i];
+        p.xres_out[i] = sm.xv[i];
+      }
     }
     if (cta == 0 && tid == 0) {
       p.tokens[step] = out_tok;
@@ -691,7 +769,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
     prev_token = out_tok;
   }
   pf.mark(1);
-  if (pf.buf) pf.buf[2 * PROF_MAX] = (unsigned long long)pf.i;
+  if (pf.buf) pf.buf[2 * PROF_MAX] = (u64)pf.i;
 }
 
 }  // namespace zg
@@ -705,24 +783,27 @@ struct zg_engine {
   zg_config cfg;
   zg_state state;
   DecodeParams base;
-  LayerDesc *layers_dev;
-  unsigned long long *prompt_dev;
-  unsigned long long *tokens_dev;
-  unsigned long long *tokens_host;  // pinned, mapped
-  unsigned long long *tokens_host_devptr;
-  unsigned long long *last_token_dev;
-  unsigned long long *prof_dev;
-  unsigned *bar_dev;
-  unsigned bar_count;  // host mirror of the monotonic barrier word
+  LayerDesc *layers_host;
+  u64 *exchange_dev;  // all flagged buffers, one allocation
+  u64 *prompt_dev;
+  u64 *tokens_dev;
+  u64 *tokens_host;  // pinned, mapped
+  u64 *tokens_host_devptr;
+  u64 *last_token_dev;
+  u64 *prof_dev;
+  unsigned *err_dev;
+  unsigned epoch_count;  // host mirror of the phase epoch (monotonic across launches)
   int grid;
   size_t smem_bytes;
   int n_prompt;
   int prof_enabled;
 };
 
+static zg_engine *g_table_owner = nullptr;  // whose layer table currently sits in __constant__ memory
+
 static size_t engine_smem_bytes(const zg_config &c, int nslot) {
   const size_t E = c.n_embed, hd = E / c.n_heads;
-  const size_t floats = (size_t)nslot * 4 * E + 4 * E + E + c.context_size + NCW * hd + 64;
+  const size_t floats = (size_t)nslot * 4 * E + 2 * 4 * E + E + NCW * hd + 64;
   return floats * sizeof(float);
 }
 
@@ -733,8 +814,8 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
   Context &c = ctx();
   const zg_config &cfg = gpt->config;
   const size_t E = cfg.n_embed;
-  if (E % 8 != 0 || E / cfg.n_heads * cfg.n_heads != E || E > (size_t)LNR * NCT) {
-    set_error(1, "zg_engine_create: n_embed must be a multiple of 8 and of n_heads, and at most 1792", __FILE__, __LINE__);
+  if (E % 8 != 0 || cfg.n_heads * 64 != E || E > (size_t)LNR * NCT || cfg.n_layer > (size_t)MAX_LAYERS) {
+    set_error(1, "zg_engine_create: needs head_dim 64, n_embed % 8 == 0, n_embed <= 1792, n_layer <= 64", __FILE__, __LINE__);
     return nullptr;
   }
   zg_engine *e = (zg_engine *)calloc(1, sizeof(zg_engine));
@@ -768,29 +849,27 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
     return nullptr;
   }
 
-  // device-side descriptor table (start-up only)
-  LayerDesc *lh = (LayerDesc *)calloc(cfg.n_layer, sizeof(LayerDesc));
+  // layer table (start-up only); copied into __constant__ memory before a launch when another engine owned it
+  e->layers_host = (LayerDesc *)calloc(MAX_LAYERS, sizeof(LayerDesc));
   for (size_t l = 0; l < cfg.n_layer; ++l) {
     const zg_block &b = gpt->h[l];
-    lh[l] = LayerDesc{b.ln_1.weight, b.ln_1.bias, b.attn.c_attn.weight, b.attn.c_attn.bias, b.attn.c_proj.weight,
-                      b.attn.c_proj.bias, b.ln_2.weight, b.ln_2.bias, b.mlp.c_fc.weight, b.mlp.c_fc.bias,
-                      b.mlp.c_proj.weight, b.mlp.c_proj.bias, b.k_cache, b.v_cache};
+    e->layers_host[l] = LayerDesc{b.ln_1.weight, b.ln_1.bias, b.attn.c_attn.weight, b.attn.c_attn.bias,
+                                  b.attn.c_proj.weight, b.attn.c_proj.bias, b.ln_2.weight, b.ln_2.bias,
+                                  b.mlp.c_fc.weight, b.mlp.c_fc.bias, b.mlp.c_proj.weight, b.mlp.c_proj.bias,
+                                  b.k_cache, b.v_cache};
   }
-  e->layers_dev = (LayerDesc *)zg_alloc(cfg.n_layer * sizeof(LayerDesc));
-  zg_upload(e->layers_dev, lh, cfg.n_layer * sizeof(LayerDesc));
-  free(lh);
 
-  const size_t C = cfg.context_size, hd = E / cfg.n_heads;
+  const size_t C = cfg.context_size, hd = 64;
   const int smax = e->grid / (int)cfg.n_heads > 0 ? e->grid / (int)cfg.n_heads : 1;
-  e->prompt_dev = (unsigned long long *)zg_alloc(C * 8);
-  e->tokens_dev = (unsigned long long *)zg_alloc(C * 8);
-  e->last_token_dev = (unsigned long long *)zg_alloc(8);
-  e->prof_dev = (unsigned long long *)zg_alloc((2 * PROF_MAX + 4) * 8);
-  e->bar_dev = (unsigned *)zg_alloc(1024);
+  const size_t n_exchange = E + E + 2 * E + E + 4 * E + 2 * (size_t)e->grid;
+  e->exchange_dev = (u64 *)zg_alloc(n_exchange * 8);
+  e->prompt_dev = (u64 *)zg_alloc(C * 8);
+  e->tokens_dev = (u64 *)zg_alloc(C * 8);
+  e->last_token_dev = (u64 *)zg_alloc(8);
+  e->prof_dev = (u64 *)zg_alloc((2 * PROF_MAX + 4) * 8);
+  e->err_dev = (unsigned *)zg_alloc(256);
   float *att_part = (float *)zg_alloc(cfg.n_heads * (size_t)smax * (hd + 2) * sizeof(float));
   unsigned *head_count = (unsigned *)zg_alloc(cfg.n_heads * sizeof(unsigned));
-  float *amax_val = (float *)zg_alloc(e->grid * sizeof(float));
-  unsigned *amax_idx = (unsigned *)zg_alloc(e->grid * sizeof(unsigned));
   ZG_CUDA(cudaHostAlloc(&e->tokens_host, C * 8, cudaHostAllocMapped));
   ZG_CUDA(cudaHostGetDevicePointer((void **)&e->tokens_host_devptr, e->tokens_host, 0));
   if (zg_last_error()) {
@@ -798,21 +877,27 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
     return nullptr;
   }
   memset(e->tokens_host, 0xff, C * 8);
-  zg_memset(e->bar_dev, 0, 1024);
+  zg_memset(e->exchange_dev, 0, n_exchange * 8);  // epoch 0 everywhere; the first phase of the first launch is epoch 1
+  zg_memset(e->err_dev, 0, 256);
   zg_memset(head_count, 0, cfg.n_heads * sizeof(unsigned));
   zg_memset(e->tokens_dev, 0, C * 8);
   zg_memset(e->prof_dev, 0, (2 * PROF_MAX + 4) * 8);
-  e->bar_count = 0;
+  e->epoch_count = 0;
 
   DecodeParams &p = e->base;
   memset(&p, 0, sizeof(p));
   p.E = (int)E; p.H = (int)cfg.n_heads; p.hd = (int)hd; p.L = (int)cfg.n_layer; p.V = (int)cfg.vocab_size; p.C = (int)C;
   p.nslot = nslot; p.slotf = 4 * (int)E;
   p.wte = gpt->wte.weight; p.wpe = gpt->wpe.weight; p.lnf_g = gpt->ln_f.weight; p.lnf_b = gpt->ln_f.bias;
-  p.layers = e->layers_dev;
-  p.xres = state->o; p.xout = state->x; p.q = state->_q; p.att = state->_h; p.f = state->_4xh; p.logits = state->logits;
-  p.att_part = att_part; p.head_count = head_count; p.bar = e->bar_dev;
-  p.amax_val = amax_val; p.amax_idx = amax_idx;
+  u64 *x = e->exchange_dev;
+  p.xres_f = x; x += E;
+  p.q_f = x; x += E;
+  p.kvn_f = x; x += 2 * E;
+  p.att_f = x; x += E;
+  p.f_f = x; x += 4 * E;
+  p.amax_f = x;
+  p.xres_out = state->o; p.xout = state->x; p.logits = state->logits;
+  p.att_part = att_part; p.head_count = head_count; p.err = e->err_dev;
   p.tokens = e->tokens_dev; p.tokens_host = e->tokens_host_devptr; p.last_token = e->last_token_dev;
   p.dbg = getenv("ZG_DEBUG") ? atoi(getenv("ZG_DEBUG")) : 0;
   zg_sync();
@@ -822,17 +907,18 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
 void zg_engine_destroy(zg_engine *e) {
   if (!e) return;
   zg_sync();
-  zg_free(e->layers_dev); zg_free(e->prompt_dev); zg_free(e->tokens_dev); zg_free(e->last_token_dev);
-  zg_free(e->prof_dev); zg_free(e->bar_dev); zg_free(e->base.att_part); zg_free(e->base.head_count);
-  zg_free(e->base.amax_val); zg_free(e->base.amax_idx);
+  if (g_table_owner == e) g_table_owner = nullptr;
+  zg_free(e->exchange_dev); zg_free(e->prompt_dev); zg_free(e->tokens_dev); zg_free(e->last_token_dev);
+  zg_free(e->prof_dev); zg_free(e->err_dev); zg_free(e->base.att_part); zg_free(e->base.head_count);
   cudaFreeHost(e->tokens_host);
+  free(e->layers_host);
   free(e);
 }
 
 }  // extern "C"
 
-// number of grid barriers a launch will execute (the barrier word is monotonic across launches)
-static unsigned barriers_for(const zg_engine *e, const DecodeParams &p) {
+// number of phases a launch executes (the exchange epoch is monotonic across launches)
+static unsigned phases_for(const zg_engine *e, const DecodeParams &p) {
   unsigned n = 0;
   for (int s = p.first_step; s < p.first_step + p.n_steps; ++s)
     n += 5u * (unsigned)e->cfg.n_layer + ((p.force_logits || s >= p.n_prompt) ? 1u : 0u);
@@ -845,9 +931,14 @@ static void engine_launch(zg_engine *e, DecodeParams &p) {
     set_error(1, "decode engine: step range exceeds context_size", __FILE__, __LINE__);
     return;
   }
-  p.bar_base = e->bar_count;
+  if (g_table_owner != e) {  // stream-ordered, so a launch in flight keeps the table it was given
+    ZG_CUDA(cudaMemcpyToSymbolAsync(c_layers, e->layers_host, sizeof(LayerDesc) * MAX_LAYERS, 0,
+                                    cudaMemcpyHostToDevice, ctx().stream));
+    g_table_owner = e;
+  }
+  p.epoch_base = e->epoch_count;
   p.prof = e->prof_enabled ? e->prof_dev : nullptr;
-  e->bar_count += barriers_for(e, p) * (unsigned)e->grid;
+  e->epoch_count += phases_for(e, p);
   void *args[] = {(void *)&p};
   ZG_CUDA(cudaLaunchCooperativeKernel((const void *)decode_persistent_kernel, dim3(e->grid), dim3(NTHREADS), args,
                                       e->smem_bytes, ctx().stream));
@@ -857,11 +948,11 @@ static void engine_launch(zg_engine *e, DecodeParams &p) {
 // after a synchronisation: did the in-kernel watchdog fire (a wait exceeded ~2 s)?
 static int engine_check_watchdog(zg_engine *e) {
   unsigned w = 0;
-  ZG_CUDA(cudaMemcpyAsync(&w, e->bar_dev + 32, sizeof(w), cudaMemcpyDeviceToHost, ctx().stream));
+  ZG_CUDA(cudaMemcpyAsync(&w, e->err_dev, sizeof(w), cudaMemcpyDeviceToHost, ctx().stream));
   ZG_CUDA(cudaStreamSynchronize(ctx().stream));
   if (w != 0) {
-    set_error(1, w == 1 ? "decode engine watchdog: grid barrier timed out" : "decode engine watchdog: mbarrier wait timed out",
-              __FILE__, __LINE__);
+    set_error(1, w == 2 ? "decode engine watchdog: mbarrier wait timed out"
+                        : "decode engine watchdog: flagged-exchange wait timed out", __FILE__, __LINE__);
     return 1;
   }
   return zg_last_error();
@@ -942,12 +1033,12 @@ int zg_engine_generate_greedy(zg_engine *e, const size_t *inputs, size_t n_input
 
 size_t zg_engine_read_profile(zg_engine *e, unsigned long long *out, size_t max_entries) {
   if (!require_ready("zg_engine_read_profile")) return 0;
-  if (out == nullptr) {  // toggle: calling with NULL enables profiling for subsequent launches
+  if (out == nullptr) {  // toggle: calling with NULL enables (max_entries != 0) or disables profiling
     e->prof_enabled = max_entries ? 1 : 0;
     return 0;
   }
   // out receives (tag, ns) pairs; returns the number of pairs
-  unsigned long long *tmp = (unsigned long long *)malloc((2 * PROF_MAX + 4) * 8);
+  u64 *tmp = (u64 *)malloc((2 * PROF_MAX + 4) * 8);
   zg_download(tmp, e->prof_dev, (2 * PROF_MAX + 4) * 8);
   size_t n = (size_t)tmp[2 * PROF_MAX];
   if (n > PROF_MAX) n = PROF_MAX;
