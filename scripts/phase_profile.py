@@ -55,8 +55,8 @@ for i in range(max(first, 1), n):
     seg[(int(tags[i - 1]), int(tags[i]))].append((ts[i] - ts[i - 1]) / 1e3)
 names = {1: "P1 qkv", 2: "P2 attn", 3: "P3 proj", 4: "P4 fc", 5: "P5 proj2", 6: "lm_head"}
 pts = {0: "start", 1: "vec gathered", 3: "phase done", 4: "token reduced"}
-fine = {257: "B:after sync1", 258: "B:after red", 259: "B:poll done", 260: "V:prefetch issued", 261: "V:gather issued",
-        262: "V:gather sync", 263: "G:wait done", 264: "G:dot done", 265: "G:arrive done", 266: "G:shuffles done"}
+fine = {260: "V:prefetch issued", 261: "V:gather done", 262: "V:gather sync", 263: "G:wait done", 264: "G:dot done",
+        265: "G:arrive done", 266: "G:shuffles done", 267: "G:before wait"}
 def nm(t):
     if t in fine: return fine[t]
     ph, pt = t // 16, t % 16

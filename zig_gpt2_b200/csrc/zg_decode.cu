@@ -88,14 +88,19 @@ struct DecodeParams {
 struct Prof {
   u64 *buf;
   int i;
+  bool fine;
+  __device__ __forceinline__ void fmark(int tag) {
+    if (fine) mark(tag);
+  }
   __device__ __forceinline__ void mark(int tag) {
-    if (buf != nullptr) {
-      if (i < PROF_MAX) {
-        buf[2 * i] = (u64)tag;
-        buf[2 * i + 1] = globaltimer();
-      }
-      ++i;
+    if (buf != nullptr) record(tag);
+  }
+  __device__ __noinline__ void record(int tag) {
+    if (i < PROF_MAX) {
+      buf[2 * i] = (u64)tag;
+      buf[2 * i + 1] = globaltimer();
     }
+    ++i;
   }
 };
 
@@ -159,7 +164,7 @@ __device__ __noinline__ u64 spin_word(const u64 *p, unsigned ep, Watchdog wd) {
 }
 // gather n floats (n even) whose words must carry epoch `ep` into shared memory; all loads of a thread are
 // issued before the first check, so the common case costs one L2 round trip
-__device__ __forceinline__ void gather_flagged(float *dst_smem, const u64 *src, int n, unsigned ep, const Watchdog &wd) {
+__device__ __noinline__ void gather_flagged(float *dst_smem, const u64 *src, int n, unsigned ep, Watchdog wd) {
   const int npairs = n >> 1;
 #pragma unroll 1
   for (int base = 0; base < npairs; base += GB * NCT) {
@@ -232,14 +237,21 @@ struct Smem {
   Watchdog wd;             // sticky global error word + CTA-local tripped flag
 };
 
-// LayerNorm of the E-vector in smem `src` into smem `dst`; reference formula ops.zig:86-101.  The affine
-// parameters arrive in registers (element i = tid + j*NCT), fetched at the top of the phase so that their
-// global-memory latency overlaps the activation gather.
-__device__ __forceinline__ void layer_norm_to_smem(const float *src_smem, float *dst, const float (&lg)[LNR],
-                                                   const float (&lb)[LNR], int E, float eps, float *red) {
+// LayerNorm of the E-vector in smem `src` into smem `dst`; reference formula ops.zig:86-101 (single pass E[x],
+// E[x^2]; std = sqrt(var + eps)).  The affine parameters are fetched first so that their latency overlaps the
+// two block reductions.  One copy of this code serves every call site (instruction-cache footprint matters:
+// each phase executes its code exactly once).
+__device__ __noinline__ void layer_norm_to_smem(const float *src_smem, float *dst, const float *__restrict__ g,
+                                                const float *__restrict__ b, int E, float eps, float *red) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float xr[LNR];
+  float xr[LNR], lg[LNR], lb[LNR];
   float s = 0.0f, ss = 0.0f;
+#pragma unroll
+  for (int j = 0; j < LNR; ++j) {
+    const int i = tid + j * NCT;
+    lg[j] = (i < E) ? __ldg(g + i) : 0.0f;
+    lb[j] = (i < E) ? __ldg(b + i) : 0.0f;
+  }
 #pragma unroll
   for (int j = 0; j < LNR; ++j) {
     const int i = tid + j * NCT;
@@ -262,21 +274,13 @@ __device__ __forceinline__ void layer_norm_to_smem(const float *src_smem, float 
   }
   const float n = (float)E;
   const float mean = ts / n;
-  const float std_ = sqrtf(tss / n - mean * mean + eps);
+  const float rstd = 1.0f / sqrtf(tss / n - mean * mean + eps);
 #pragma unroll
   for (int j = 0; j < LNR; ++j) {
     const int i = tid + j * NCT;
-    if (i < E) dst[i] = (xr[j] - mean) / std_ * lg[j] + lb[j];
+    if (i < E) dst[i] = (xr[j] - mean) * rstd * lg[j] + lb[j];
   }
   consumer_sync();
-}
-__device__ __forceinline__ void load_ln_params(const float *g, const float *b, int E, float (&lg)[LNR], float (&lb)[LNR]) {
-#pragma unroll
-  for (int j = 0; j < LNR; ++j) {
-    const int i = threadIdx.x + j * NCT;
-    lg[j] = (i < E) ? __ldg(g + i) : 0.0f;
-    lb[j] = (i < E) ? __ldg(b + i) : 0.0f;
-  }
 }
 
 // Attention work item (head h, split s of S) over cache rows [t0,t1) -- ops.zig:249-307 without the
@@ -428,6 +432,42 @@ __device__ __forceinline__ bool step_needs_logits(const DecodeParams &p, int ste
   return p.force_logits || step >= p.n_prompt;
 }
 
+// ---- phase table ------------------------------------------------------------------------------------
+// Everything about a GEMV phase that does not depend on the token is worked out once per launch and kept in
+// shared memory, so that the top of a phase is a handful of LDS instead of integer divisions and branches
+// (each phase executes its code exactly once: every instruction on its critical path is latency).
+struct PhaseEnt {
+  const float *W, *bias, *ln_g, *ln_b;
+  const u64 *src;
+  int r0, nrows;  // rows of W this CTA owns in this phase
+  int K, mode;
+  int n_units, rps;
+};
+
+// up to 8 ring units at once: issue every try_wait before looking at any result, so their latencies overlap
+__device__ __forceinline__ bool mbar_try8(const uint32_t (&bar)[8], uint32_t parity_bits) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p0, p1, p2, p3, p4, p5, p6, p7;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p0, [%1], %9;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p1, [%2], %10;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p2, [%3], %11;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p3, [%4], %12;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p4, [%5], %13;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p5, [%6], %14;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p6, [%7], %15;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p7, [%8], %16;\n\t"
+      "and.pred p0, p0, p1;\n\tand.pred p2, p2, p3;\n\tand.pred p4, p4, p5;\n\tand.pred p6, p6, p7;\n\t"
+      "and.pred p0, p0, p2;\n\tand.pred p4, p4, p6;\n\tand.pred p0, p0, p4;\n\t"
+      "selp.u32 %0, 1, 0, p0;\n\t}"
+      : "=r"(ok)
+      : "r"(bar[0]), "r"(bar[1]), "r"(bar[2]), "r"(bar[3]), "r"(bar[4]), "r"(bar[5]), "r"(bar[6]), "r"(bar[7]),
+        "r"(parity_bits & 1u), "r"((parity_bits >> 1) & 1u), "r"((parity_bits >> 2) & 1u), "r"((parity_bits >> 3) & 1u),
+        "r"((parity_bits >> 4) & 1u), "r"((parity_bits >> 5) & 1u), "r"((parity_bits >> 6) & 1u), "r"((parity_bits >> 7) & 1u)
+      : "memory");
+  return ok != 0;
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const DecodeParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) u64 mbar_store[2 * MAXSLOTS];
@@ -435,12 +475,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
   const int G = gridDim.x, cta = blockIdx.x;
   const int E = p.E, E4 = 4 * p.E;
   const int nslot = p.nslot, slotf = p.slotf;
+  const int L5 = 5 * p.L;
   Smem sm;
   sm.ring = reinterpret_cast<float *>(smem_raw);
   sm.vec = sm.ring + (size_t)nslot * slotf;
   sm.xv = sm.vec + 2 * E4;
   sm.part = sm.xv + E;
   sm.red = sm.part + NCW * p.hd;
+  PhaseEnt *table = reinterpret_cast<PhaseEnt *>(sm.red + 64);
   sm.full0 = smem_u32(mbar_store);
   sm.empty0 = smem_u32(mbar_store + MAXSLOTS);
   sm.wd.err_global = p.err;
@@ -450,15 +492,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
     wd_flag = 0u;
     for (int i = 0; i < nslot; ++i) {
       mbar_init(sm.full0 + 8u * i, 1);
-      mbar_init(sm.empty0 + 8u * i, 1);  // one warp owns a ring unit and releases it
+      mbar_init(sm.empty0 + 8u * i, NCW);  // every consumer warp reads its slice of a unit, then releases it
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  for (int g = threadIdx.x; g <= L5; g += blockDim.x) {
+    const int l = g / 5, ph = g - 5 * l;
+    const bool is_head = (g == L5);
+    PhaseEnt e;
+    e.W = nullptr; e.bias = nullptr; e.ln_g = nullptr; e.ln_b = nullptr; e.src = nullptr;
+    e.r0 = 0; e.nrows = 0; e.K = E; e.mode = -1; e.n_units = 0; e.rps = 4;
+    if (is_head || ph != 1) {
+      const PhaseDesc d = phase_desc(p, l, ph, is_head, G);
+      int r0, r1;
+      row_range(cta, G, d.rot, d.N, r0, r1);
+      e.W = d.W; e.bias = d.bias; e.ln_g = d.ln_g; e.ln_b = d.ln_b; e.src = d.src;
+      e.r0 = r0; e.nrows = r1 - r0; e.K = d.K; e.mode = d.mode;
+      e.rps = (d.K == E) ? 4 : 1;
+      e.n_units = (e.nrows + e.rps - 1) / e.rps;
+    }
+    table[g] = e;
+  }
   __syncthreads();
 
   const int last_step = p.first_step + p.n_steps - 1;
-  const int L5 = 5 * p.L;
+  const int bsz = nslot < 8 ? nslot : 8;  // ring units handled per GEMV batch (all on distinct slots)
 
   if (threadIdx.x >= NCT) {
     // =============================== producer warp ===============================
@@ -473,13 +532,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
       const int nph = L5 + (step_needs_logits(p, step) ? 1 : 0);
 #pragma unroll 1
       for (int g = 0; g < nph; ++g) {
-        const int l = g / 5, ph = g - 5 * l;
-        const bool is_head = (g == L5);
-        if (!is_head && ph == 1) continue;
-        const PhaseDesc d = phase_desc(p, l, ph, is_head, G);
-        if (!is_head && ph == 0 && lane < 8) {
+        const PhaseEnt &e = table[g];
+        if (e.mode < 0) continue;
+        if (e.mode == M_QKV && lane < 8) {
           // pull the layer's small vectors (LayerNorm affine + biases, 13E floats) into L2 ahead of the consumers
-          const LayerDesc &ld = c_layers[l];
+          const LayerDesc &ld = c_layers[g / 5];
           const float *arr = lane == 0 ? ld.ln1_g : lane == 1 ? ld.ln1_b : lane == 2 ? ld.b_attn : lane == 3 ? ld.b_proj
                            : lane == 4 ? ld.ln2_g : lane == 5 ? ld.ln2_b : lane == 6 ? ld.b_fc : ld.b_proj2;
           const int len = lane == 2 ? 3 * E : lane == 6 ? E4 : E;
@@ -487,17 +544,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           for (int i = cta; i < nlines; i += G) prefetch_l2(reinterpret_cast<const char *>(arr) + (size_t)i * 128);
         }
         if (lane == 0) {
-          int r0, r1;
-          row_range(cta, G, d.rot, d.N, r0, r1);
-          const int rps = slotf / d.K;
+          const int rps = e.rps, K = e.K;
+          const float *W = e.W + (size_t)e.r0 * K;
 #pragma unroll 1
-          for (int r = r0; r < r1; r += rps) {
-            const int nr = min(rps, r1 - r);
-            const uint32_t bytes = (uint32_t)nr * (uint32_t)d.K * 4u;
+          for (int r = 0; r < e.nrows; r += rps) {
+            const int nr = min(rps, e.nrows - r);
+            const uint32_t bytes = (uint32_t)nr * (uint32_t)K * 4u;
             mbar_wait(sm.empty0 + 8u * slot, parity ^ 1u, sm.wd);
             const uint32_t fb = sm.full0 + 8u * slot;
             mbar_expect_tx(fb, bytes);
-            bulk_g2s(smem_u32(sm.ring + (size_t)slot * slotf), d.W + (size_t)r * d.K, bytes, fb, pol);
+            bulk_g2s(smem_u32(sm.ring + (size_t)slot * slotf), W + (size_t)r * K, bytes, fb, pol);
             if (++slot == nslot) { slot = 0; parity ^= 1u; }
           }
         }
@@ -509,12 +565,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
 
   // ================================= consumer warps =================================
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  Prof pf{(p.prof && cta == 0 && tid == 0) ? p.prof : nullptr, 0};
+  Prof pf{(p.prof && cta == 0 && tid == 0) ? p.prof : nullptr, 0, (p.dbg & 8) != 0};
   pf.mark(0);
   u64 prev_token = 0;
-  unsigned useq = 0;            // ring units consumed by this CTA so far (slot = useq % nslot, parity = (useq / nslot) & 1)
-  unsigned ep = p.epoch_base;   // epoch of the phase being executed; its inputs carry ep - 1
-  int vsel = 0;                 // which half of sm.vec the current GEMV phase reads
+  int bslot = 0;               // ring slot / parity of the first unit of the current GEMV batch
+  uint32_t bpar = 0;
+  unsigned ep = p.epoch_base;  // epoch of the phase being executed; its inputs carry ep - 1
+  int vsel = 0;                // which half of sm.vec the current GEMV phase reads
+  // each warp reduces one eighth of every ring unit: floats [warp * slice, (warp + 1) * slice) of the slot
+  const int slice4 = slotf >> 5;           // float4 per warp slice (slotf / 8 / 4)
+  const bool small_slice = slice4 <= 96;   // E <= 768: the warp's x-slice fits 3 float4 per lane (registers)
 
 #pragma unroll 1
   for (int step = p.first_step; step <= last_step; ++step) {
@@ -532,58 +592,94 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
 #pragma unroll 1
     for (int g = 0; g < nph; ++g) {
       ++ep;
-      const int l = g / 5, ph = g - 5 * l;
+      const PhaseEnt ent = table[g];
       const bool is_head = (g == L5);
-      const int tag = is_head ? 96 : 16 * (ph + 1);
+      const int tag = is_head ? 96 : 16 * (g % 5 + 1);
 
-      if (!is_head && ph == 1) {
+      if (ent.mode < 0) {
         // ---------------- attention over the cache (ops.zig:160-171) ----------------
         int S = (T + ATT_CHUNK - 1) / ATT_CHUNK;
         const int smax = G / p.H;
         if (S > smax) S = smax;
-        if (cta < p.H * S) attention_item(p, sm, l, cta / S, cta % S, S, T, ep - 1, ep);
+        if (cta < p.H * S) attention_item(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep);
         pf.mark(tag + 3);
         continue;
       }
 
-      const PhaseDesc d = phase_desc(p, l, ph, is_head, G);
       vsel ^= 1;
       float *vec = sm.vec + vsel * E4;
-      // ---------------- phase top: everything whose address is known before the activation arrives ----------
-      int r0, r1;
-      row_range(cta, G, d.rot, d.N, r0, r1);
-      const int rps = slotf / d.K;  // rows per unit: 4 (K = E) or 1 (K = 4E)
-      const int nrows = r1 - r0;
-      const int n_units = (nrows + rps - 1) / rps;
-      const int rw = nslot < NCW ? nslot : NCW;
-      // residual operand of the rows this lane will finish: the embedding itself in the first block
-      // (main.zig:181-183), otherwise the stream word written two (P5) or three (P3) phases ago
-      const bool resid_from_emb = (l == 0 && ph == 2);
-      const unsigned ep_resid = ep - (ph == 2 ? 3u : 2u);
-      float bias0 = 0.0f, resid0 = 0.0f;
+      const int rps = ent.rps, K = ent.K, mode = ent.mode;
+      // ---------------- phase top: issue every load whose address is known before the activation arrives ----
+      // thread t finishes row r0 + t of the first batch: bias and residual operand.  The residual is the
+      // embedding itself in the first block (main.zig:181-183), otherwise the stream word written two (P5) or
+      // three (P3) phases ago.
+      const bool resid_from_emb = (g == 2);
+      const unsigned ep_resid = ep - (K == E ? 3u : 2u);
+      float bias_v = 0.0f, resid_v = 0.0f;
       u64 resid_w = 0;
-      const bool own0 = (warp < rw && warp < n_units && lane < min(rps, nrows - warp * rps));
-      if (own0) {
-        const int r = r0 + warp * rps + lane;
-        if (d.bias) bias0 = __ldg(d.bias + r);
-        if (d.mode == M_RESID) {
-          if (resid_from_emb) resid0 = __ldg(te + r) + __ldg(pe + r);
+      const bool own_row = tid < min(ent.nrows, bsz * rps);
+      if (own_row) {
+        const int r = ent.r0 + tid;
+        if (ent.bias) bias_v = __ldg(ent.bias + r);
+        if (mode == M_RESID) {
+          if (resid_from_emb) resid_v = __ldg(te + r) + __ldg(pe + r);
           else resid_w = ld_word(p.xres_f + r);
         }
       }
       float lg[LNR], lb[LNR];
-      if (d.ln_g != nullptr) load_ln_params(d.ln_g, d.ln_b, E, lg, lb);
+      if (ent.ln_g != nullptr) {
+#pragma unroll
+        for (int j = 0; j < LNR; ++j) {
+          const int i = tid + j * NCT;
+          lg[j] = (i < E) ? __ldg(ent.ln_g + i) : 0.0f;
+          lb[j] = (i < E) ? __ldg(ent.ln_b + i) : 0.0f;
+        }
+      }
+      pf.fmark(256 + 4);
 
       // ---------------- activation vector -> shared memory ----------------
-      if (d.ln_g != nullptr) {
+      if (ent.ln_g != nullptr) {
         if (g == 0) {  // wte[token] + wpe[pos] (main.zig:179-183), recomputed by every CTA
 #pragma unroll 1
           for (int i = tid; i < E; i += NCT) sm.xv[i] = __ldg(te + i) + __ldg(pe + i);
         } else {
-          gather_flagged(sm.xv, d.src, E, ep - 1, sm.wd);
+          gather_flagged(sm.xv, ent.src, E, ep - 1, sm.wd);
+        }
+        pf.fmark(256 + 5);
+        consumer_sync();
+        pf.fmark(256 + 6);
+        // LayerNorm, reference formula ops.zig:86-101 (single pass E[x], E[x^2]; std = sqrt(var + eps))
+        float xr[LNR];
+        float s = 0.0f, ss = 0.0f;
+#pragma unroll
+        for (int j = 0; j < LNR; ++j) {
+          const int i = tid + j * NCT;
+          xr[j] = (i < E) ? sm.xv[i] : 0.0f;
+          s += xr[j];
+          ss = fmaf(xr[j], xr[j], ss);
+        }
+        s = warp_sum(s);
+        ss = warp_sum(ss);
+        if (lane == 0) {
+          sm.red[warp] = s;
+          sm.red[NCW + warp] = ss;
         }
         consumer_sync();
-        layer_norm_to_smem(sm.xv, vec, lg, lb, E, 1e-5f, sm.red);  // main.zig:123,140,189
+        float ts = 0.0f, tss = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NCW; ++w) {
+          ts += sm.red[w];
+          tss += sm.red[NCW + w];
+        }
+        const float nE = (float)E;
+        const float mean = ts / nE;
+        const float rstd = 1.0f / sqrtf(tss / nE - mean * mean + 1e-5f);
+#pragma unroll
+        for (int j = 0; j < LNR; ++j) {
+          const int i = tid + j * NCT;
+          if (i < E) vec[i] = (xr[j] - mean) * rstd * lg[j] + lb[j];
+        }
+        consumer_sync();
         if (is_head && p.write_xout && step == last_step && cta == 0) {
 #pragma unroll 1
           for (int i = tid; i < E; i += NCT) {
@@ -592,136 +688,160 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           }
         }
       } else {
-        gather_flagged(vec, d.src, d.K, ep - 1, sm.wd);
+        gather_flagged(vec, ent.src, K, ep - 1, sm.wd);
+        pf.fmark(256 + 5);
         consumer_sync();
       }
       pf.mark(tag + 1);
 
-      // ---------------- GEMV: one warp per ring unit ----------------
+      // ---------------- GEMV: every warp reduces its eighth of every ring unit ----------------
+      // A unit is slotf floats: 4 rows of K = E (warp w covers half of row w / 2) or one row of K = 4E (warp w
+      // covers an eighth of it).  Either way the warp's activation slice is the same for every unit of the
+      // phase, so it is read once.  Per-unit partial sums stay in registers until the whole batch is consumed;
+      // then 8 interleaved shuffle reductions, one CTA sync, and the first threads finish one row each.
       float *kc = nullptr, *vc = nullptr;
-      if (d.mode == M_QKV) {
-        kc = c_layers[l].k_cache + (size_t)pos * E;
-        vc = c_layers[l].v_cache + (size_t)pos * E;
+      if (mode == M_QKV) {
+        kc = c_layers[g / 5].k_cache + (size_t)pos * E;
+        vc = c_layers[g / 5].v_cache + (size_t)pos * E;
       }
       float *logits = (is_head && p.store_logits && step == last_step) ? p.logits : nullptr;
-      const float4 *vec4 = reinterpret_cast<const float4 *>(vec);
-      const int k4 = d.K >> 2;
-      float best = -INFINITY;  // running argmax of the rows this lane finishes (lm_head only)
+      const int xoff4 = (rps == 4) ? (warp & 1) * slice4 : warp * slice4;  // the warp's slice of the activation vector
+      const int row_in_unit = (rps == 4) ? (warp >> 1) : 0;
+      const float4 *vec4 = reinterpret_cast<const float4 *>(vec) + xoff4;
+      float4 xs0 = make_float4(0.f, 0.f, 0.f, 0.f), xs1 = xs0, xs2 = xs0;
+      if (small_slice) {
+        if (lane < slice4) xs0 = vec4[lane];
+        if (lane + 32 < slice4) xs1 = vec4[lane + 32];
+        if (lane + 64 < slice4) xs2 = vec4[lane + 64];
+      }
+      float best = -INFINITY;  // running argmax of the rows this thread finishes (lm_head only)
       unsigned best_i = 0xffffffffu;
-      // Warps advance through the ring in lockstep rounds of `rw` consecutive units with a CTA sync between
-      // rounds.  An mbarrier only tracks phase PARITY: a warp that waited on a slot's next fill while the
-      // current fill was still in flight would see the matching parity and read stale data.  Keeping every
-      // round's units on distinct slots (rw <= nslot) and finishing a round before the next starts rules
-      // that out.
+      const int spr = NCW / rps;  // warp slices per row
+
 #pragma unroll 1
-      for (int ub = 0; ub < n_units; ub += rw) {
-        const int u = ub + warp;
-        if (warp < rw && u < n_units) {
-          const unsigned n = useq + (unsigned)u;
-          const int slot = (int)(n % (unsigned)nslot);
-          const uint32_t parity = (n / (unsigned)nslot) & 1u;
-          const int rbase = r0 + u * rps;
-          const int rows_here = min(rps, r1 - rbase);
-          float bias_v = bias0, resid_v = resid0;
-          u64 rw_word = resid_w;
-          if (ub > 0 && lane < rows_here) {
-            if (d.bias) bias_v = __ldg(d.bias + rbase + lane);
-            if (d.mode == M_RESID) {
-              if (resid_from_emb) resid_v = __ldg(te + rbase + lane) + __ldg(pe + rbase + lane);
-              else rw_word = ld_word(p.xres_f + rbase + lane);
-            }
-          }
-          mbar_wait(sm.full0 + 8u * slot, parity, sm.wd);
-          const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)slot * slotf);
-          float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-          if (rps == 4) {
-            // 4 rows share the activation vector: one x load feeds four row accumulators
-#pragma unroll 2
-            for (int i = lane; i < k4; i += 32) {
-              const float4 xv = vec4[i];
-              const float4 w0 = w4[i];
-              const float4 w1 = (rows_here > 1) ? w4[k4 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
-              const float4 w2 = (rows_here > 2) ? w4[2 * k4 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
-              const float4 w3 = (rows_here > 3) ? w4[3 * k4 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
-              a0 = fmaf(w0.x, xv.x, a0); a0 = fmaf(w0.y, xv.y, a0); a0 = fmaf(w0.z, xv.z, a0); a0 = fmaf(w0.w, xv.w, a0);
-              a1 = fmaf(w1.x, xv.x, a1); a1 = fmaf(w1.y, xv.y, a1); a1 = fmaf(w1.z, xv.z, a1); a1 = fmaf(w1.w, xv.w, a1);
-              a2 = fmaf(w2.x, xv.x, a2); a2 = fmaf(w2.y, xv.y, a2); a2 = fmaf(w2.z, xv.z, a2); a2 = fmaf(w2.w, xv.w, a2);
-              a3 = fmaf(w3.x, xv.x, a3); a3 = fmaf(w3.y, xv.y, a3); a3 = fmaf(w3.z, xv.z, a3); a3 = fmaf(w3.w, xv.w, a3);
-            }
-          } else {
-            // one long row (K = 4E): four independent accumulators for ILP, summed below
-#pragma unroll 4
-            for (int i = lane; i < k4; i += 32) {
-              const float4 xv = vec4[i];
-              const float4 w0 = w4[i];
-              a0 = fmaf(w0.x, xv.x, a0); a1 = fmaf(w0.y, xv.y, a1); a2 = fmaf(w0.z, xv.z, a2); a3 = fmaf(w0.w, xv.w, a3);
-            }
-            a0 = (a0 + a1) + (a2 + a3);
-            a1 = a2 = a3 = 0.0f;
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(sm.empty0 + 8u * slot);  // ring slot free again
-          a0 = warp_sum(a0);
-          a1 = warp_sum(a1);
-          a2 = warp_sum(a2);
-          a3 = warp_sum(a3);
-          if (lane < rows_here) {
-            const int r = rbase + lane;
-            float v = lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : a3;
-            v += bias_v;
-            if (d.mode == M_QKV) {  // q to the exchange, k/v to cache row `pos` (ops.zig:146-158) and to the exchange
-              if (r < E) {
-                st_flag(p.q_f + r, v, ep);
-              } else if (r < 2 * E) {
-                kc[r - E] = v;
-                st_flag(p.kvn_f + (r - E), v, ep);
+      for (int ub = 0; ub < ent.n_units; ub += bsz) {
+        const int nb = min(bsz, ent.n_units - ub);
+        uint32_t fbar[8];
+        int slotj[8];
+        uint32_t pbits = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          int sj = bslot + (j < nb ? j : 0);
+          uint32_t pj = bpar;
+          if (sj >= nslot) { sj -= nslot; pj ^= 1u; }
+          slotj[j] = sj;
+          fbar[j] = sm.full0 + 8u * sj;
+          pbits |= pj << j;
+        }
+        if (!mbar_try8(fbar, pbits)) {
+#pragma unroll 1
+          for (int j = 0; j < nb; ++j) mbar_wait(fbar[j], (pbits >> j) & 1u, sm.wd);
+        }
+        pf.fmark(256 + 7);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] = 0.0f;
+          if (j < nb) {
+            const int rows_here = min(rps, ent.nrows - (ub + j) * rps);
+            if (row_in_unit < rows_here) {
+              const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)slotj[j] * slotf) + warp * slice4;
+              float a0 = 0.0f, a1 = 0.0f;
+              if (small_slice) {
+                if (lane < slice4) {
+                  const float4 w = w4[lane];
+                  a0 = fmaf(w.x, xs0.x, a0); a1 = fmaf(w.y, xs0.y, a1); a0 = fmaf(w.z, xs0.z, a0); a1 = fmaf(w.w, xs0.w, a1);
+                }
+                if (lane + 32 < slice4) {
+                  const float4 w = w4[lane + 32];
+                  a0 = fmaf(w.x, xs1.x, a0); a1 = fmaf(w.y, xs1.y, a1); a0 = fmaf(w.z, xs1.z, a0); a1 = fmaf(w.w, xs1.w, a1);
+                }
+                if (lane + 64 < slice4) {
+                  const float4 w = w4[lane + 64];
+                  a0 = fmaf(w.x, xs2.x, a0); a1 = fmaf(w.y, xs2.y, a1); a0 = fmaf(w.z, xs2.z, a0); a1 = fmaf(w.w, xs2.w, a1);
+                }
               } else {
-                vc[r - 2 * E] = v;
-                st_flag(p.kvn_f + E + (r - 2 * E), v, ep);
+#pragma unroll 1
+                for (int i = lane; i < slice4; i += 32) {
+                  const float4 w = w4[i];
+                  const float4 x = vec4[i];
+                  a0 = fmaf(w.x, x.x, a0); a1 = fmaf(w.y, x.y, a1); a0 = fmaf(w.z, x.z, a0); a1 = fmaf(w.w, x.w, a1);
+                }
               }
-            } else if (d.mode == M_RESID) {  // main.zig:136-139,142-145
-              if (!resid_from_emb) {
-                if ((unsigned)(rw_word >> 32) != ep_resid) rw_word = spin_word(p.xres_f + r, ep_resid, sm.wd);
-                resid_v = lo_f(rw_word);
-              }
-              st_flag(p.xres_f + r, v + resid_v, ep);
-            } else if (d.mode == M_GELU) {  // main.zig:80
-              st_flag(p.f_f + r, gelu_ref(v), ep);
-            } else {  // tied lm_head (main.zig:193) + running argmax; this lane sees increasing r, so strict >
-              if (logits) logits[r] = v;
-              if (v > best) { best = v; best_i = (unsigned)r; }
+              acc[j] = a0 + a1;
             }
           }
         }
-        if (ub + rw < n_units) consumer_sync();
+        __syncwarp();
+        if (lane < nb) mbar_arrive(sm.empty0 + 8u * (uint32_t)((bslot + lane >= nslot) ? bslot + lane - nslot : bslot + lane));
+        pf.fmark(256 + 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = warp_sum(acc[j]);
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sm.part[j * NCW + warp] = acc[j];
+        }
+        bslot += nb;
+        if (bslot >= nslot) { bslot -= nslot; bpar ^= 1u; }
+        consumer_sync();
+        pf.fmark(256 + 9);
+        // ---------------- epilogue: thread t finishes row (ub * rps + t) of this phase ----------------
+        const int rr = ub * rps + tid;
+        if (tid < nb * rps && rr < ent.nrows) {
+          const int j = tid / rps, ri = tid - j * rps;
+          const int r = ent.r0 + rr;
+          float v = 0.0f;
+          for (int sgm = 0; sgm < spr; ++sgm) v += sm.part[j * NCW + ri * spr + sgm];
+          if (ub > 0) {  // operands of later batches were not prefetched at the top of the phase
+            bias_v = ent.bias ? __ldg(ent.bias + r) : 0.0f;
+            if (mode == M_RESID) {
+              if (resid_from_emb) resid_v = __ldg(te + r) + __ldg(pe + r);
+              else resid_w = ld_word(p.xres_f + r);
+            }
+          }
+          v += bias_v;
+          if (mode == M_QKV) {  // q to the exchange, k/v to cache row `pos` (ops.zig:146-158) and to the exchange
+            if (r < E) {
+              st_flag(p.q_f + r, v, ep);
+            } else if (r < 2 * E) {
+              kc[r - E] = v;
+              st_flag(p.kvn_f + (r - E), v, ep);
+            } else {
+              vc[r - 2 * E] = v;
+              st_flag(p.kvn_f + E + (r - 2 * E), v, ep);
+            }
+          } else if (mode == M_RESID) {  // main.zig:136-139,142-145
+            if (!resid_from_emb) {
+              if ((unsigned)(resid_w >> 32) != ep_resid) resid_w = spin_word(p.xres_f + r, ep_resid, sm.wd);
+              resid_v = lo_f(resid_w);
+            }
+            st_flag(p.xres_f + r, v + resid_v, ep);
+          } else if (mode == M_GELU) {  // main.zig:80
+            st_flag(p.f_f + r, gelu_ref(v), ep);
+          } else {  // tied lm_head (main.zig:193) + running argmax; this thread sees increasing r, so strict >
+            if (logits) logits[r] = v;
+            if (v > best) { best = v; best_i = (unsigned)r; }
+          }
+        }
+        if (ub + bsz < ent.n_units) consumer_sync();  // sm.part is rewritten by the next batch
       }
-      useq += (unsigned)n_units;
       pf.mark(tag + 3);
 
       if (is_head) {
-        // CTA-level argmax (value desc, index asc), one flagged partial per CTA, then every CTA reduces the G
-        // partials itself: the next step's embedding needs the token everywhere
+        // CTA-level argmax (value desc, index asc): the finishing threads all live in warp 0.  One flagged
+        // partial per CTA, then every CTA reduces the G partials itself: the next step's embedding needs the
+        // token everywhere.
+        if (tid < 32) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-          const unsigned oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-          if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
-        }
-        if (lane == 0) {
-          sm.red[16 + warp] = best;
-          sm.red[24 + warp] = __uint_as_float(best_i);
-        }
-        consumer_sync();
-        if (tid == 0) {
-          for (int w = 1; w < NCW; ++w) {
-            const float ov = sm.red[16 + w];
-            const unsigned oi = __float_as_uint(sm.red[24 + w]);
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const unsigned oi = __shfl_xor_sync(0xffffffffu, best_i, o);
             if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
           }
-          st_flag(p.amax_f + 2 * cta, best, ep);
-          st_flag(p.amax_f + 2 * cta + 1, __uint_as_float(best_i), ep);
-        }
-        if (tid < 32) {
+          if (tid == 0) {
+            st_flag(p.amax_f + 2 * cta, best, ep);
+            st_flag(p.amax_f + 2 * cta + 1, __uint_as_float(best_i), ep);
+          }
           float bv = -INFINITY;
           unsigned bi = 0xffffffffu;
           for (int i = tid; i < G; i += 32) {
@@ -750,12 +870,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
 
     if (!want_logits && p.write_xout && step == last_step && cta == 0) {
       // GPT.forward(compute_logits = false) still leaves ln_f(x) in state.x (main.zig:189)
-      float lg[LNR], lb[LNR];
-      load_ln_params(p.lnf_g, p.lnf_b, E, lg, lb);
       gather_flagged(sm.xv, p.xres_f, E, ep, sm.wd);
-      consumer_sync();
-      consumer_sync();  // every warp is past the last GEMV's reads of sm.vec
-      layer_norm_to_smem(sm.xv, sm.vec, lg, lb, E, 1e-5f, sm.red);
+      consumer_sync();  // also: every warp is past the last GEMV's reads of sm.vec
+      layer_norm_to_smem(sm.xv, sm.vec, p.lnf_g, p.lnf_b, E, 1e-5f, sm.red);
 #pragma unroll 1
       for (int i = tid; i < E; i += NCT) {
         p.xout[i] = sm.vec[i];
@@ -804,7 +921,7 @@ static zg_engine *g_table_owner = nullptr;  // whose layer table currently sits 
 static size_t engine_smem_bytes(const zg_config &c, int nslot) {
   const size_t E = c.n_embed, hd = E / c.n_heads;
   const size_t floats = (size_t)nslot * 4 * E + 2 * 4 * E + E + NCW * hd + 64;
-  return floats * sizeof(float);
+  return floats * sizeof(float) + (5 * c.n_layer + 1) * sizeof(PhaseEnt);
 }
 
 extern "C" {
