@@ -630,9 +630,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
       if (ent.ln_g != nullptr) {
 #pragma unroll
         for (int j = 0; j < LNR; ++j) {
-          const int i = tid + j * NCT;
-          lg[j] = (i < E) ? __ldg(ent.ln_g + i) : 0.0f;
-          lb[j] = (i < E) ? __ldg(ent.ln_b + i) : 0.0f;
+          lg[j] = lb[j] = 0.0f;
+          if (j * NCT < E) {  // uniform: skips the iterations a narrow model does not need
+            const int i = tid + j * NCT;
+            if (i < E) {
+              lg[j] = __ldg(ent.ln_g + i);
+              lb[j] = __ldg(ent.ln_b + i);
+            }
+          }
         }
       }
       pf.fmark(256 + 4);
@@ -653,10 +658,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         float s = 0.0f, ss = 0.0f;
 #pragma unroll
         for (int j = 0; j < LNR; ++j) {
-          const int i = tid + j * NCT;
-          xr[j] = (i < E) ? sm.xv[i] : 0.0f;
-          s += xr[j];
-          ss = fmaf(xr[j], xr[j], ss);
+          xr[j] = 0.0f;
+          if (j * NCT < E) {
+            const int i = tid + j * NCT;
+            if (i < E) xr[j] = sm.xv[i];
+            s += xr[j];
+            ss = fmaf(xr[j], xr[j], ss);
+          }
         }
         s = warp_sum(s);
         ss = warp_sum(ss);
@@ -676,8 +684,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         const float rstd = 1.0f / sqrtf(tss / nE - mean * mean + 1e-5f);
 #pragma unroll
         for (int j = 0; j < LNR; ++j) {
-          const int i = tid + j * NCT;
-          if (i < E) vec[i] = (xr[j] - mean) * rstd * lg[j] + lb[j];
+          if (j * NCT < E) {
+            const int i = tid + j * NCT;
+            if (i < E) vec[i] = (xr[j] - mean) * rstd * lg[j] + lb[j];
+          }
         }
         consumer_sync();
         if (is_head && p.write_xout && step == last_step && cta == 0) {
@@ -739,34 +749,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         }
         pf.fmark(256 + 7);
         float acc[8];
+        if (small_slice) {
+          // branch-free: every load is unconditional (slots past nb alias slot 0, lanes past the slice are clamped and
+          // meet a zero activation), so the compiler can put all 24 LDS.128 in flight before the first FMA
+          const int i0 = min(lane, slice4 - 1), i1 = min(lane + 32, slice4 - 1), i2 = min(lane + 64, slice4 - 1);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc[j] = 0.0f;
-          if (j < nb) {
-            const int rows_here = min(rps, ent.nrows - (ub + j) * rps);
-            if (row_in_unit < rows_here) {
+          for (int j = 0; j < 8; ++j) {
+            const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)slotj[j] * slotf) + warp * slice4;
+            const float4 wa = w4[i0], wb = w4[i1], wc = w4[i2];
+            float a0 = wa.x * xs0.x, a1 = wa.y * xs0.y;
+            a0 = fmaf(wa.z, xs0.z, a0); a1 = fmaf(wa.w, xs0.w, a1);
+            a0 = fmaf(wb.x, xs1.x, a0); a1 = fmaf(wb.y, xs1.y, a1); a0 = fmaf(wb.z, xs1.z, a0); a1 = fmaf(wb.w, xs1.w, a1);
+            a0 = fmaf(wc.x, xs2.x, a0); a1 = fmaf(wc.y, xs2.y, a1); a0 = fmaf(wc.z, xs2.z, a0); a1 = fmaf(wc.w, xs2.w, a1);
+            const bool valid = (j < nb) && (row_in_unit < min(rps, ent.nrows - (ub + j) * rps));
+            acc[j] = valid ? a0 + a1 : 0.0f;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc[j] = 0.0f;
+            if (j < nb && row_in_unit < min(rps, ent.nrows - (ub + j) * rps)) {
               const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)slotj[j] * slotf) + warp * slice4;
               float a0 = 0.0f, a1 = 0.0f;
-              if (small_slice) {
-                if (lane < slice4) {
-                  const float4 w = w4[lane];
-                  a0 = fmaf(w.x, xs0.x, a0); a1 = fmaf(w.y, xs0.y, a1); a0 = fmaf(w.z, xs0.z, a0); a1 = fmaf(w.w, xs0.w, a1);
-                }
-                if (lane + 32 < slice4) {
-                  const float4 w = w4[lane + 32];
-                  a0 = fmaf(w.x, xs1.x, a0); a1 = fmaf(w.y, xs1.y, a1); a0 = fmaf(w.z, xs1.z, a0); a1 = fmaf(w.w, xs1.w, a1);
-                }
-                if (lane + 64 < slice4) {
-                  const float4 w = w4[lane + 64];
-                  a0 = fmaf(w.x, xs2.x, a0); a1 = fmaf(w.y, xs2.y, a1); a0 = fmaf(w.z, xs2.z, a0); a1 = fmaf(w.w, xs2.w, a1);
-                }
-              } else {
 #pragma unroll 1
-                for (int i = lane; i < slice4; i += 32) {
-                  const float4 w = w4[i];
-                  const float4 x = vec4[i];
-                  a0 = fmaf(w.x, x.x, a0); a1 = fmaf(w.y, x.y, a1); a0 = fmaf(w.z, x.z, a0); a1 = fmaf(w.w, x.w, a1);
-                }
+              for (int i = lane; i < slice4; i += 32) {
+                const float4 w = w4[i];
+                const float4 x = vec4[i];
+                a0 = fmaf(w.x, x.x, a0); a1 = fmaf(w.y, x.y, a1); a0 = fmaf(w.z, x.z, a0); a1 = fmaf(w.w, x.w, a1);
               }
               acc[j] = a0 + a1;
             }
@@ -775,11 +784,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         __syncwarp();
         if (lane < nb) mbar_arrive(sm.empty0 + 8u * (uint32_t)((bslot + lane >= nslot) ? bslot + lane - nslot : bslot + lane));
         pf.fmark(256 + 8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = warp_sum(acc[j]);
-        if (lane == 0) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) sm.part[j * NCW + warp] = acc[j];
+        // packed reduction of the 8 per-unit sums: exchange halves (xor 16, 8, 4), then two plain steps;
+        // afterwards lane L (L % 4 == 0) holds the warp total of unit ((L >> 4) & 1) * 4 + ((L >> 3) & 1) * 2 + ((L >> 2) & 1)
+        {
+          const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+          float b0 = h16 ? acc[4] : acc[0], b1 = h16 ? acc[5] : acc[1], b2 = h16 ? acc[6] : acc[2], b3 = h16 ? acc[7] : acc[3];
+          const float s0 = h16 ? acc[0] : acc[4], s1 = h16 ? acc[1] : acc[5], s2 = h16 ? acc[2] : acc[6], s3 = h16 ? acc[3] : acc[7];
+          b0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+          b1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          b2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+          b3 += __shfl_xor_sync(0xffffffffu, s3, 16);
+          float c0 = h8 ? b2 : b0, c1 = h8 ? b3 : b1;
+          const float t0 = h8 ? b0 : b2, t1 = h8 ? b1 : b3;
+          c0 += __shfl_xor_sync(0xffffffffu, t0, 8);
+          c1 += __shfl_xor_sync(0xffffffffu, t1, 8);
+          float d0 = h4 ? c1 : c0;
+          const float u0 = h4 ? c0 : c1;
+          d0 += __shfl_xor_sync(0xffffffffu, u0, 4);
+          d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+          d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+          if ((lane & 3) == 0) sm.part[(lane >> 2) * NCW + warp] = d0;
         }
         bslot += nb;
         if (bslot >= nslot) { bslot -= nslot; bpar ^= 1u; }
@@ -788,7 +812,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         // ---------------- epilogue: thread t finishes row (ub * rps + t) of this phase ----------------
         const int rr = ub * rps + tid;
         if (tid < nb * rps && rr < ent.nrows) {
-          const int j = tid / rps, ri = tid - j * rps;
+          const int j = (rps == 4) ? (tid >> 2) : tid, ri = tid - j * rps;
           const int r = ent.r0 + rr;
           float v = 0.0f;
           for (int sgm = 0; sgm < spr; ++sgm) v += sm.part[j * NCW + ri * spr + sgm];
