@@ -230,14 +230,24 @@ def run_ours(args):
     tokens = out.astype(np.int64)
 
     if dist is not None:
-        import torch
+        from zig_gpt2_b200.sharding import max_over_ranks
 
-        t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s = float(t[0]), float(t[1])
+        ms_total, e2e_s = max_over_ranks(dist, [ms_total, e2e_s], device="cuda")
 
     bytes_per_launch = sum(cfg.decode_bytes(seq_len=s + 1) for s in range(first, first + K))
     peak, peak_kind = peaks()
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/), scaled to K steps
+    traffic = None
+    try:
+        import csv
+
+        with open(os.path.join(ROOT, "profiles", "r01_decode_persistent_ncu_full.csv")) as f:
+            m = {r["metric"]: (float(r["value"]), r["unit"]) for r in csv.DictReader(f)}
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        per64 = sum(m[k][0] * scale[m[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        traffic = per64 / 64.0 * K  # the capture was a 64-step launch
+    except Exception:
+        traffic = None
     achieved = bytes_per_launch / (float(np.median(trials)) * 1e-3) / 1e9
     value = world * K / (ms_total * 1e-3)
     e2e_value = world * (W + K) / e2e_s
@@ -258,7 +268,7 @@ def run_ours(args):
                         "generated tokens / wall time"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_kind": peak_kind, "kernel": "decode_persistent_kernel",
+                     "traffic": traffic, "peak_kind": peak_kind, "kernel": "decode_persistent_kernel",
                      "bytes_per_launch": bytes_per_launch, "frac_of_nominal_8TBs": achieved / 8000.0},
         "clocks": clocks,
         "tokens_tail": [int(t) for t in tokens[-4:]],

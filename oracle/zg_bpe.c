@@ -6,6 +6,7 @@
  */
 #include "zg_oracle.h"
 
+#include <locale.h>
 #include <regex.h>
 #include <stdlib.h>
 #include <string.h>
@@ -48,6 +49,7 @@ struct zo_encoder { /* bpe.zig:8-12 */
   char *byte_to_unicode[256]; size_t byte_to_unicode_len[256];
   char *arena; /* owns every key string */
   regex_t regex;
+  locale_t c_locale; /* the Zig program never calls setlocale, so the reference's regex runs in the "C" locale */
 };
 
 /* bpe.zig:14-49 */
@@ -85,13 +87,18 @@ zo_encoder *zo_encoder_init(const char *const *tokens, const size_t *token_lens,
       "|[[:space:]]?[[:digit:]]+"
       "|[[:space:]]?[^[:space:][:alpha:][:digit:]]+"
       "|[[:space:]]+";
-  if (regcomp(&e->regex, pattern, REG_EXTENDED) != 0) return NULL;
+  e->c_locale = newlocale(LC_ALL_MASK, "C", (locale_t)0);
+  locale_t prev = uselocale(e->c_locale);
+  const int rc = regcomp(&e->regex, pattern, REG_EXTENDED);
+  uselocale(prev);
+  if (rc != 0) return NULL;
   return e;
 }
 
 void zo_encoder_deinit(zo_encoder *e) { /* :51-57 */
   if (!e) return;
   regfree(&e->regex);
+  if (e->c_locale) freelocale(e->c_locale);
   free(e->token_to_idx.slots); free(e->unicode_to_byte.slots);
   free(e->idx_to_token); free(e->idx_to_token_len); free(e->arena); free(e);
 }
@@ -100,8 +107,14 @@ void zo_encoder_deinit(zo_encoder *e) { /* :51-57 */
 size_t zo_encoder_encode(const zo_encoder *e, const char *inputs, size_t len, size_t *outputs, size_t max_out) {
   regmatch_t matches[1];
   size_t token_idx = 0, offset = 0;
+  locale_t prev = uselocale(e->c_locale);
   while (offset < len) {
-    regexec(&e->regex, inputs + offset, 1, matches, 0); /* :65, return code ignored */
+    /* :65 -- the reference ignores the return code; a failed or empty match would make it spin forever on
+     * stale offsets (only an embedded NUL can cause that in the C locale), so the oracle reports it instead */
+    if (regexec(&e->regex, inputs + offset, 1, matches, 0) != 0 || matches[0].rm_eo <= 0) {
+      uselocale(prev);
+      return (size_t)-1;
+    }
     const size_t match_so = offset + (size_t)matches[0].rm_so;
     const size_t match_eo = offset + (size_t)matches[0].rm_eo;
 
@@ -110,9 +123,9 @@ size_t zo_encoder_encode(const zo_encoder *e, const char *inputs, size_t len, si
     for (size_t i = match_so; i < match_eo; ++i) { /* :73-78 bytes -> unicode */
       const unsigned char byte = (unsigned char)inputs[i];
       const char *u = e->byte_to_unicode[byte];
-      if (!u) return (size_t)-1; /* `.?` unwrap panic in the reference */
+      if (!u) { uselocale(prev); return (size_t)-1; } /* `.?` unwrap panic in the reference */
       for (size_t j = 0; j < e->byte_to_unicode_len[byte]; ++j) {
-        if (word_eo >= sizeof(word)) return (size_t)-1; /* reference overflows here (UB) */
+        if (word_eo >= sizeof(word)) { uselocale(prev); return (size_t)-1; } /* reference overflows here (UB) */
         word[word_eo++] = u[j];
       }
     }
@@ -120,7 +133,7 @@ size_t zo_encoder_encode(const zo_encoder *e, const char *inputs, size_t len, si
     while (token_so < token_eo) {
       const zo_slot *s = zo_map_get(&e->token_to_idx, word + token_so, token_eo - token_so);
       if (s) {
-        if (token_idx >= max_out) return (size_t)-1;
+        if (token_idx >= max_out) { uselocale(prev); return (size_t)-1; }
         outputs[token_idx++] = s->val;
         token_so = token_eo;
         token_eo = word_eo;
@@ -130,6 +143,7 @@ size_t zo_encoder_encode(const zo_encoder *e, const char *inputs, size_t len, si
     }
     offset = match_eo; /* :94 */
   }
+  uselocale(prev);
   return token_idx;
 }
 

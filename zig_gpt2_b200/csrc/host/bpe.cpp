@@ -119,6 +119,8 @@ Encoder::~Encoder() { deinit(); }
 void Encoder::deinit() {  // bpe.zig:51-57
   if (compiled_) regfree(&regex_);
   compiled_ = false;
+  if (c_locale_) freelocale(c_locale_);
+  c_locale_ = (locale_t)0;
   token_to_idx_.clear();
   idx_to_token_.clear();
   unicode_to_byte_.clear();
@@ -146,7 +148,10 @@ bool Encoder::init(const std::vector<std::pair<std::string, long>> &token_to_idx
       "|[[:space:]]?[[:digit:]]+"
       "|[[:space:]]?[^[:space:][:alpha:][:digit:]]+"
       "|[[:space:]]+";
+  c_locale_ = newlocale(LC_ALL_MASK, "C", (locale_t)0);
+  locale_t prev = uselocale(c_locale_);
   compiled_ = regcomp(&regex_, kPattern, REG_EXTENDED) == 0;
+  uselocale(prev);
   return compiled_;
 }
 
@@ -164,6 +169,11 @@ size_t Encoder::encode(const std::string &inputs, std::vector<size_t> *outputs) 
   regmatch_t matches[1];
   size_t offset = 0, emitted = 0;
   std::string word;
+  struct LocaleGuard {
+    locale_t prev;
+    explicit LocaleGuard(locale_t l) : prev(uselocale(l)) {}
+    ~LocaleGuard() { uselocale(prev); }
+  } guard(c_locale_);
   while (offset < len) {
     if (regexec(&regex_, base + offset, 1, matches, 0) != 0 || matches[0].rm_eo <= 0) break;  // embedded NUL ends the text
     const size_t match_so = offset + (size_t)matches[0].rm_so, match_eo = offset + (size_t)matches[0].rm_eo;

@@ -6,6 +6,7 @@
 // Documented divergence: the reference's fixed [20]u8 word buffer (bpe.zig:71) and 20-byte decode buffer
 // (main.zig:52) overflow on longer words; here words and outputs are unbounded std::string/vector.
 #pragma once
+#include <locale.h>
 #include <regex.h>
 
 #include <cstddef>
@@ -45,6 +46,7 @@ class Encoder {
   bool have_byte_[256] = {false};
   regex_t regex_;
   bool compiled_ = false;
+  locale_t c_locale_ = (locale_t)0;  // the Zig program never calls setlocale: its regex runs in the "C" locale
 };
 
 }  // namespace zgh

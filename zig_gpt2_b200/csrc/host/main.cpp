@@ -1,0 +1,63 @@
+// main.cpp -- `zig_gpt2 "<prompt>"` (main.zig:344-371) over the CUDA shim.
+//   zig_gpt2 [--size 124M] [--model-dir models/124M] [--device 0] [--greedy] [--temp 0.8] [--seed N]
+//            [--max-tokens N] "<prompt>"
+// Build: g++ -O2 -std=c++17 main.cpp bpe.cpp -L../.. -lzg_b200 -o zig_gpt2   
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <iostream>
+
+#include "gpt2.hpp"
+
+int main(int argc, char **argv) {
+  std::string size = "124M", model_dir, prompt;
+  int device = 0;
+  bool greedy = false;
+  float temp = 0.8f;  // main.zig:345
+  uint64_t seed = (uint64_t)time(nullptr);
+  size_t max_tokens = 0;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    auto next = [&](const char *what) -> const char * {
+      if (i + 1 >= argc) { std::cerr << what << " needs a value\n"; exit(2); }
+      return argv[++i];
+    };
+    if (a == "--size") size = next("--size");
+    else if (a == "--model-dir") model_dir = next("--model-dir");
+    else if (a == "--device") device = atoi(next("--device"));
+    else if (a == "--greedy") greedy = true;
+    else if (a == "--temp") temp = (float)atof(next("--temp"));
+    else if (a == "--seed") seed = strtoull(next("--seed"), nullptr, 10);
+    else if (a == "--max-tokens") max_tokens = strtoull(next("--max-tokens"), nullptr, 10);
+    else prompt = a;
+  }
+  if (prompt.empty()) {  // the reference indexes args[1] unchecked (main.zig:361)
+    std::cerr << "usage: zig_gpt2 [--size S] [--model-dir D] [--greedy] [--temp T] [--seed N] [--max-tokens N] \"<prompt>\"\n";
+    return 2;
+  }
+  if (model_dir.empty()) model_dir = "models/" + size;
+  zgh::GPTConfig config;
+  if (!zgh::config_for_size(size, &config)) { std::cerr << "unknown size " << size << "\n"; return 2; }
+
+  zgh::Encoder encoder;  // load_encoder, main.zig:316-320
+  if (!encoder.init_from_files(model_dir + "/encoder.json", model_dir + "/byte_encoder.json")) {
+    std::cerr << "cannot load " << model_dir << "/encoder.json + byte_encoder.json\n";
+    return 1;
+  }
+  zgh::GPT gpt;
+  if (!gpt.load(config, model_dir, device)) {
+    std::cerr << "cannot load model: " << zg_last_error_string() << "\n";
+    return 1;
+  }
+  std::vector<size_t> inputs;
+  if (encoder.encode(prompt, &inputs) == (size_t)-1 || inputs.empty() || inputs.size() > config.context_size) {
+    std::cerr << "prompt does not tokenize into 1.." << config.context_size << " tokens\n";
+    return 1;
+  }
+  const size_t n_total = max_tokens ? std::min(config.context_size, inputs.size() + max_tokens) : config.context_size;
+  zgh::generate(gpt, encoder, temp, inputs, n_total, greedy, seed,
+                [](const std::string &piece) { std::cerr << piece << std::flush; });  // main.zig:340 prints to stderr
+  std::cerr << "\n";
+  if (zg_last_error()) { std::cerr << zg_last_error_string() << "\n"; return 1; }
+  return 0;
+}
