@@ -66,6 +66,18 @@ typedef struct { /* ops.zig:4-19 */
  * fp32 SIMT path (warp-per-row GEMV, exact fp32 accumulation). */
 void zg_linear_forward(const zg_linear *self, const float *inputs, size_t inputs_len, float *outputs);
 
+/* Linear.forward on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed shared-memory ring),
+ * the replacement of the reference's cblas_sgemm(RowMajor, NoTrans, Trans) call (ops.zig:30-45) when M >= 16.
+ *   precision 0: fp32 operands read in place as kind::tf32 (`inputs` fp32, weight = self->weight);
+ *   precision 1: bf16 operands (`inputs` and `weight_lowp` are bf16 copies made with zg_to_bf16), fp32 accumulation.
+ *   epi: 0 = bias only, 1 = bias + GELU (main.zig:79-80 fused), 2 = bias + residual add of `resid` [M,N] (main.zig:136-145).
+ *   tile_n: 0 = automatic, else 32/64/128/256 (N width of the CTA tile).
+ * zg_linear_forward itself takes this path (precision 0) when M >= 16. */
+void zg_linear_forward_tc(const zg_linear *self, const void *inputs, size_t inputs_len, float *outputs, int precision,
+                          const void *weight_lowp, int epi, const float *resid, int tile_n);
+void zg_to_bf16(const float *src, void *dst_bf16, size_t n); /* fp32 -> bf16 round-to-nearest-even copy (start-up) */
+int zg_tc_error(void); /* watchdog word of the tensor-core kernels (0 = clean); synchronises */
+
 typedef struct { size_t emb_dim; const float *weight; } zg_embedding; /* ops.zig:49-57 */
 /* Embedding.forward, ops.zig:59-67.  `idxs` is a HOST array of 64-bit indices (the reference passes
  * `&[1]usize{token}`, main.zig:179-180); `embeddings` is a device pointer. */

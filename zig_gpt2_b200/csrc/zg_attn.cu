@@ -1,0 +1,368 @@
+// zg_attn.cu -- attention kernels of the batched paths.
+//
+// (1) attn_prefill_kernel: causal self-attention over whole prompts (what the reference computes one token at a time
+//     through CausalSelfAttention.forward, ops.zig:129-173, with the implicit causality of a growing KV cache) as a
+//     fused flash-style kernel on the tensor cores.  One CTA per (128-query tile, head, sequence):
+//       warp 0      TMA: Q tile once, K/V tiles of the sequence double-buffered (128-byte swizzle)
+//       warp 1      tcgen05.mma: S = Q K^T (128x128x64, K-major x K-major) into TMEM, then O_j = P V (128x64x128,
+//                   K-major P from shared memory x MN-major V exactly as TMA delivered it)
+//       warps 2..5  one query row per thread: tcgen05.ld S -> online softmax in registers (thread-local row max /
+//                   sum, no shuffles) -> P as bf16 into swizzled shared memory -> running O in registers
+//     bf16 operands, fp32 accumulation and softmax.  Two CTAs fit per SM so one CTA's softmax overlaps the other's MMAs.
+//
+// (2) attn_decode_batch_kernel: one new token per sequence against that sequence's fp32 KV cache (ops.zig:249-307,
+//     query length 1, no mask) for B sequences at once; one CTA per (head, sequence), each K/V row read exactly once
+//     with 128-bit loads straight from the time-major cache (no transposed copies), online softmax across warps.
+#include "zg_attn.cuh"
+
+namespace zg {
+
+namespace {
+
+constexpr int QT = 128, KT = 128, HD = 64;
+constexpr int TILE_BYTES = QT * HD * 2;  // 16 KB: 128 rows x 128 bytes
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_SMEM = TILE_BYTES * (1 + 2 + 2) + 2 * TILE_BYTES + 128;  // Q, K x2, V x2, P (2 atoms), barriers
+constexpr uint32_t ATT_TMEM_COLS = 256;                                   // S: 128 columns, PV: 64 columns
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16 *__restrict__ out, int T, int H, int E,
+                    int n_bh, unsigned *err) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = tc::smem_addr(smem_raw);
+  const uint32_t sQ = base, sK = base + TILE_BYTES, sV = sK + 2 * TILE_BYTES, sP = sV + 2 * TILE_BYTES;
+  const uint32_t bars = sP + 2 * TILE_BYTES;
+  const uint32_t q_full = bars, kv_full = bars + 8, kv_empty = bars + 24, s_full = bars + 40, p_full = bars + 48,
+                 pv_full = bars + 56, slot = bars + 64, abort_flag = bars + 68;
+  const tc::Guard guard{err, abort_flag};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // heavy (late) query tiles first: tile qt attends to qt + 1 key tiles
+  const int num_qt = (T + QT - 1) / QT;
+  const int qt = num_qt - 1 - (int)(blockIdx.x / n_bh);
+  const int bh = blockIdx.x % n_bh, b = bh / H, h = bh % H;
+  const int q0 = qt * QT, n_kv = qt + 1;
+  const int row_base = b * T;
+
+  if (threadIdx.x == 0) {
+    if (base & 1023u) atomicExch(err, 4u);  // swizzled tiles need a 1024-byte aligned base
+    tc::mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(kv_full + 8 * s, 1);
+      tc::mbar_init(kv_empty + 8 * s, 1);
+    }
+    tc::mbar_init(s_full, 1);
+    tc::mbar_init(p_full, 4);
+    tc::mbar_init(pv_full, 1);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(abort_flag), "r"(0u));
+    tc::fence_mbar_init();
+    tc::prefetch_tmap(&tm_qkv);
+  }
+  if (warp == 1) tc::tmem_alloc<ATT_TMEM_COLS>(slot);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *reinterpret_cast<uint32_t *>(smem_raw + (slot - base));
+  const uint32_t tS = tmem, tO = tmem + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer ----------------
+      tc::mbar_expect_tx(q_full, TILE_BYTES);
+      tc::tma_load_2d(sQ, &tm_qkv, h * HD, row_base + q0, q_full);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        if (!tc::mbar_wait(kv_empty + 8 * s, ((j >> 1) & 1) ^ 1, guard)) break;
+        tc::mbar_expect_tx(kv_full + 8 * s, 2 * TILE_BYTES);
+        tc::tma_load_2d(sK + s * TILE_BYTES, &tm_qkv, E + h * HD, row_base + j * KT, kv_full + 8 * s);
+        tc::tma_load_2d(sV + s * TILE_BYTES, &tm_qkv, 2 * E + h * HD, row_base + j * KT, kv_full + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc_s = tc::umma_idesc(1, QT, KT, 0, 0);  // Q (K-major) x K (K-major)
+      constexpr uint32_t idesc_o = tc::umma_idesc(1, QT, HD, 0, 1);  // P (K-major) x V (MN-major: head dim contiguous)
+      bool ok = tc::mbar_wait(q_full, 0, guard);
+      for (int j = 0; j < n_kv && ok; ++j) {
+        const int s = j & 1;
+        if (!tc::mbar_wait(kv_full + 8 * s, (j >> 1) & 1, guard)) break;
+        tc::fence_after_sync();
+        const uint32_t k_addr = sK + s * TILE_BYTES, v_addr = sV + s * TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc::umma<false>(tS, tc::umma_desc_sw128(sQ + 32 * k, 16, 1024), tc::umma_desc_sw128(k_addr + 32 * k, 16, 1024),
+                          idesc_s, (uint32_t)(k != 0));
+        tc::umma_commit(s_full);
+        if (!tc::mbar_wait(p_full, j & 1, guard)) break;
+        tc::fence_after_sync();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)  // 16 keys per MMA: P atom i/4, 32-byte step i%4; V rows 16 i .. 16 i + 15
+          tc::umma<false>(tO, tc::umma_desc_sw128(sP + (i >> 2) * TILE_BYTES + 32 * (i & 3), 16, 1024),
+                          tc::umma_desc_sw128(v_addr + 2048 * i, 1024, 1024), idesc_o, (uint32_t)(i != 0));
+        tc::umma_commit(pv_full);
+        tc::umma_commit(kv_empty + 8 * s);
+      }
+    }
+  } else {  // ---------------- softmax / output warps: one query row per thread ----------------
+    const int quad = warp & 3, r = quad * 32 + lane;  // TMEM lane == tile row
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const float scale2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    float m = -INFINITY, l = 0.0f, alpha_prev = 0.0f;
+    float o[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = 0.0f;
+    bool ok = true;
+    for (int j = 0; j < n_kv; ++j) {
+      if (!tc::mbar_wait(s_full, j & 1, guard)) { ok = false; break; }
+      tc::fence_after_sync();
+      const bool diag = (j == qt);  // only the last key tile crosses the causal boundary
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < KT; c += 32) {
+        uint32_t sr[32];
+        tc::tmem_ld32(tS + lane_base + c, sr);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float v = __uint_as_float(sr[i]);
+          if (!diag || c + i <= r) mx = fmaxf(mx, v);
+        }
+      }
+      const float m_new = fmaxf(m, mx * scale2);
+      const float alpha = fast_exp2(m - m_new);
+      if (j > 0) {  // fold the previous tile's P V (it was computed against the previous running maximum)
+        if (!tc::mbar_wait(pv_full, (j - 1) & 1, guard)) { ok = false; break; }
+        tc::fence_after_sync();
+#pragma unroll
+        for (int c = 0; c < HD; c += 32) {
+          uint32_t pr[32];
+          tc::tmem_ld32(tO + lane_base + c, pr);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha_prev, __uint_as_float(pr[i]));
+        }
+      }
+      alpha_prev = alpha;
+      m = m_new;
+      float sum = 0.0f;
+#pragma unroll 1
+      for (int c = 0; c < KT; c += 32) {
+        uint32_t sr[32];
+        tc::tmem_ld32(tS + lane_base + c, sr);
+        tc::tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), scale2, -m_new));
+          float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), scale2, -m_new));
+          if (diag && c + i > r) p0 = 0.0f;
+          if (diag && c + i + 1 > r) p1 = 0.0f;
+          sum += p0 + p1;
+          __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
+          pk[i >> 1] = *reinterpret_cast<uint32_t *>(&t);
+        }
+        // K-major SWIZZLE_128B: atom = 64 keys; row r at r * 128 bytes; 16-byte chunk index XOR (r % 8)
+        const uint32_t atom = sP + (c >> 6) * TILE_BYTES + r * 128;
+        const int ch0 = (c & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t a = atom + ((uint32_t)((ch0 + q) ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                       "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                       : "memory");
+        }
+      }
+      l = fmaf(l, alpha, sum);
+      tc::fence_proxy_async_smem();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(p_full);
+    }
+    if (ok && tc::mbar_wait(pv_full, (n_kv - 1) & 1, guard)) {
+      tc::fence_after_sync();
+#pragma unroll
+      for (int c = 0; c < HD; c += 32) {
+        uint32_t pr[32];
+        tc::tmem_ld32(tO + lane_base + c, pr);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha_prev, __uint_as_float(pr[i]));
+      }
+      if (q0 + r < T) {
+        const float inv = 1.0f / l;
+        __nv_bfloat16 *dst = out + (size_t)(row_base + q0 + r) * E + h * HD;
+#pragma unroll
+        for (int d = 0; d < HD; d += 8) {
+          uint4 pk;
+          __nv_bfloat162 t0 = __floats2bfloat162_rn(o[d] * inv, o[d + 1] * inv),
+                         t1 = __floats2bfloat162_rn(o[d + 2] * inv, o[d + 3] * inv),
+                         t2 = __floats2bfloat162_rn(o[d + 4] * inv, o[d + 5] * inv),
+                         t3 = __floats2bfloat162_rn(o[d + 6] * inv, o[d + 7] * inv);
+          pk.x = *reinterpret_cast<uint32_t *>(&t0); pk.y = *reinterpret_cast<uint32_t *>(&t1);
+          pk.z = *reinterpret_cast<uint32_t *>(&t2); pk.w = *reinterpret_cast<uint32_t *>(&t3);
+          *reinterpret_cast<uint4 *>(dst + d) = pk;
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (warp == 1) tc::tmem_dealloc<ATT_TMEM_COLS>(tmem);
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// Batched single-query attention off the fp32 caches.  cache layout: [B][C][E] (time-major, heads interleaved -- the
+// reference's per-block cache, main.zig:298-299, once per sequence).  q: [B, ldq] (row b holds q at columns h*64..).
+// T = *pos_dev + pos_base + 1 rows are attended (the new token's K/V row is already in the cache).
+// -------------------------------------------------------------------------------------------------------------------
+constexpr int DEC_WARPS = 8;
+
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+attn_decode_batch_kernel(const float *__restrict__ q, int ldq, const float *__restrict__ k_cache,
+                         const float *__restrict__ v_cache, long long seq_stride, int E, float *__restrict__ out, int ldo,
+                         const int *pos_dev, int pos_base) {
+  __shared__ float s_m[DEC_WARPS], s_l[DEC_WARPS];
+  __shared__ float s_o[DEC_WARPS][HD];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int T = pos_base + (pos_dev ? *pos_dev : 0) + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = lane >> 4, l16 = lane & 15;  // a half-warp covers one 256-byte head row with float4 loads
+  const float4 qv = *reinterpret_cast<const float4 *>(q + (size_t)b * ldq + h * HD + 4 * l16);
+  const float *kb = k_cache + (size_t)b * seq_stride + h * HD + 4 * l16;
+  const float *vb = v_cache + (size_t)b * seq_stride + h * HD + 4 * l16;
+  const float scale = 0.125f;
+  float m = -INFINITY, l = 0.0f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // each half-warp walks rows t = 2 * (warp + DEC_WARPS * i) + half, four rows in flight
+  constexpr int STEP = 2 * DEC_WARPS;
+  for (int t0 = 2 * warp + half; t0 < T; t0 += 4 * STEP) {
+    float4 kk[4], vv[4];
+    float s[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * STEP;
+      if (t < T) {
+        kk[u] = ld_stream(reinterpret_cast<const float4 *>(kb + (size_t)t * E));
+        vv[u] = ld_stream(reinterpret_cast<const float4 *>(vb + (size_t)t * E));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * STEP;
+      float d = (t < T) ? (qv.x * kk[u].x + qv.y * kk[u].y + qv.z * kk[u].z + qv.w * kk[u].w) : 0.0f;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      s[u] = (t < T) ? d * scale : -INFINITY;
+    }
+    float mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
+    const float m_new = fmaxf(m, mx);
+    if (m_new > -INFINITY) {
+      const float a = __expf(m - m_new);
+      acc.x *= a; acc.y *= a; acc.z *= a; acc.w *= a;
+      l *= a;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (s[u] > -INFINITY) {
+          const float p = __expf(s[u] - m_new);
+          l += p;
+          acc.x = fmaf(p, vv[u].x, acc.x); acc.y = fmaf(p, vv[u].y, acc.y);
+          acc.z = fmaf(p, vv[u].z, acc.z); acc.w = fmaf(p, vv[u].w, acc.w);
+        }
+      }
+      m = m_new;
+    }
+  }
+  // merge the two half-warps, then the warps
+  {
+    const float m_o = __shfl_xor_sync(0xffffffffu, m, 16), l_o = __shfl_xor_sync(0xffffffffu, l, 16);
+    float4 a_o;
+    a_o.x = __shfl_xor_sync(0xffffffffu, acc.x, 16); a_o.y = __shfl_xor_sync(0xffffffffu, acc.y, 16);
+    a_o.z = __shfl_xor_sync(0xffffffffu, acc.z, 16); a_o.w = __shfl_xor_sync(0xffffffffu, acc.w, 16);
+    const float mm = fmaxf(m, m_o);
+    const float f0 = (m > -INFINITY) ? __expf(m - mm) : 0.0f, f1 = (m_o > -INFINITY) ? __expf(m_o - mm) : 0.0f;
+    acc.x = acc.x * f0 + a_o.x * f1; acc.y = acc.y * f0 + a_o.y * f1;
+    acc.z = acc.z * f0 + a_o.z * f1; acc.w = acc.w * f0 + a_o.w * f1;
+    l = l * f0 + l_o * f1;
+    m = mm;
+  }
+  if (lane < 16) {
+    if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
+    *reinterpret_cast<float4 *>(&s_o[warp][4 * l16]) = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < HD) {
+    float mm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < DEC_WARPS; ++w) mm = fmaxf(mm, s_m[w]);
+    float num = 0.0f, den = 0.0f;
+#pragma unroll
+    for (int w = 0; w < DEC_WARPS; ++w) {
+      const float f = (s_m[w] > -INFINITY) ? __expf(s_m[w] - mm) : 0.0f;
+      num = fmaf(f, s_o[w][threadIdx.x], num);
+      den = fmaf(f, s_l[w], den);
+    }
+    out[(size_t)b * ldo + h * HD + threadIdx.x] = num / den;
+  }
+}
+
+}  // namespace
+
+bool attn_prefill_plan(AttnPrefillPlan *p, const void *qkv_bf16, void *out_bf16, int B, int T, int H, int E) {
+  if (E != H * HD) {
+    set_error(1, "prefill attention: head_dim must be 64", __FILE__, __LINE__);
+    return false;
+  }
+  p->out = out_bf16;
+  p->B = B; p->T = T; p->H = H; p->E = E;
+  return make_tmap_2d(&p->tm_qkv, qkv_bf16, 1, (uint64_t)B * T, (uint64_t)3 * E, (uint64_t)3 * E * 2, QT, HD);
+}
+
+void attn_prefill_launch(const AttnPrefillPlan &p) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    ZG_CUDA(cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    attr_set = true;
+  }
+  const int num_qt = (p.T + QT - 1) / QT, n_bh = p.B * p.H;
+  attn_prefill_kernel<<<num_qt * n_bh, ATT_THREADS, ATT_SMEM, ctx().stream>>>(
+      p.tm_qkv, reinterpret_cast<__nv_bfloat16 *>(p.out), p.T, p.H, p.E, n_bh, gemm_error_word());
+  ZG_LAUNCH_CHECK();
+}
+
+void attn_decode_batch_launch(const float *q, int ldq, const float *k_cache, const float *v_cache, long long seq_stride,
+                              int B, int H, int E, float *out, int ldo, const int *pos_dev, int pos_base) {
+  attn_decode_batch_kernel<<<dim3(H, B), DEC_WARPS * 32, 0, ctx().stream>>>(q, ldq, k_cache, v_cache, seq_stride, E, out,
+                                                                             ldo, pos_dev, pos_base);
+  ZG_LAUNCH_CHECK();
+}
+
+}  // namespace zg
+
+using namespace zg;
+
+extern "C" {
+
+// Causal self-attention over B prompts of T tokens: qkv bf16 [B*T, 3E] (the c_attn output) -> out bf16 [B*T, E].
+void zg_attention_prefill(const void *qkv_bf16, void *out_bf16, size_t B, size_t T, size_t n_heads, size_t n_embed) {
+  if (!require_ready("zg_attention_prefill")) return;
+  AttnPrefillPlan p;
+  if (!attn_prefill_plan(&p, qkv_bf16, out_bf16, (int)B, (int)T, (int)n_heads, (int)n_embed)) return;
+  attn_prefill_launch(p);
+}
+
+// One-token attention for B sequences off their fp32 caches ([B][context][E] each): q [B,E] -> out [B,E];
+// rows [0, seq_len) of every cache are attended.
+void zg_attention_decode_batch(const float *q, const float *k_cache, const float *v_cache, size_t B, size_t context,
+                               size_t n_heads, size_t n_embed, size_t seq_len, float *out) {
+  if (!require_ready("zg_attention_decode_batch") || seq_len == 0) return;
+  attn_decode_batch_launch(q, (int)n_embed, k_cache, v_cache, (long long)(context * n_embed), (int)B, (int)n_heads,
+                           (int)n_embed, out, (int)n_embed, nullptr, (int)seq_len - 1);
+}
+
+}  // extern "C"

@@ -1,0 +1,413 @@
+// zg_gemm.cu -- Linear.forward (ops.zig:21-46) for M >= 16 as a hand-written Blackwell GEMM:
+//   out[M,N] = epilogue(bias + A[M,K] . W[N,K]^T)
+// Both operands are K-major, exactly the reference's `cblas_sgemm(RowMajor, NoTrans, Trans)` call (ops.zig:30-45),
+// so the weights stay in the reference's [out, in] layout.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer   cp.async.bulk.tensor (UTMALDG) of 128-byte-swizzled A / W tiles into a shared-memory ring
+//   warp 1      MMA issuer     one elected thread issues tcgen05.mma (UTC*MMA), accumulators in TMEM, double-buffered
+//   warps 2..9  epilogue       tcgen05.ld (LDTM) -> bias / GELU / residual / K-V cache append -> global
+// Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).  The epilogue of tile i
+// overlaps the main loop of tile i+1.  kind::tf32 reads the fp32 tensors as they are; kind::f16 reads bf16 copies.
+#include <initializer_list>
+
+#include "zg_gemm.cuh"
+
+namespace zg {
+
+namespace {
+
+constexpr int BM = 128;           // UMMA M (cta_group::1): TMEM lane i <-> tile row i
+constexpr int ROW_BYTES = 128;    // one swizzle row = BLOCK_K elements
+constexpr int A_STAGE = BM * ROW_BYTES;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = (2 + EPI_WARPS) * 32;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_STAGE = BN * ROW_BYTES;
+  static constexpr int STAGE = A_STAGE + B_STAGE;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE) > 10 ? 10 : (SMEM_BUDGET / STAGE);
+  static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;  // two accumulator stages
+  static constexpr int HALVES = BN >= 64 ? 2 : 1;               // epilogue warps e and e+4 split the columns
+  static constexpr int COLS_PER_HALF = BN / HALVES;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_fast(float x) {
+  float t;
+  const float u = x * 0.7978845608f * (1.0f + 0.044715f * x * x);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return 0.5f * x * (1.0f + t);
+}
+
+// One 32-column chunk of one accumulator row: v[j] is out[row, col0 + j] before the epilogue.
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float (&v)[32], int row, int col0, int pos_now) {
+  const bool full = (col0 + 32 <= g.N);
+  if (g.bias) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + col0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < g.N) v[j] += __ldg(g.bias + col0 + j);
+    }
+  }
+  if (g.epi == TC_EPI_GELU) {
+    if (g.gelu_fast) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_ref(v[j]);
+    }
+  }
+  if (row >= g.M) return;
+  if (g.epi == TC_EPI_RESIDUAL) {
+    const float *rr = g.resid + (size_t)row * g.ldr + col0;
+    if (full && (g.ldr & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4 *>(rr + j);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < g.N) v[j] += rr[j];
+    }
+  }
+  if (g.out_bf16) {
+    __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(g.out) + (size_t)row * g.ldo + col0;
+    if (full && (g.ldo & 7) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 pk;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]),
+                       t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+        pk.x = *reinterpret_cast<uint32_t *>(&t0); pk.y = *reinterpret_cast<uint32_t *>(&t1);
+        pk.z = *reinterpret_cast<uint32_t *>(&t2); pk.w = *reinterpret_cast<uint32_t *>(&t3);
+        *reinterpret_cast<uint4 *>(o + j) = pk;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < g.N) o[j] = __float2bfloat16_rn(v[j]);
+    }
+  } else {
+    float *o = reinterpret_cast<float *>(g.out) + (size_t)row * g.ldo + col0;
+    if (full && (g.ldo & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < g.N) o[j] = v[j];
+    }
+  }
+  if (g.k_cache && col0 >= g.E) {  // K / V rows of this token -> the caches (fp32), E % 32 == 0 so a chunk never straddles
+    const int part = col0 / g.E;   // 1 = K, 2 = V
+    float *cache = (part == 1) ? g.k_cache : g.v_cache;
+    const int seq = row / g.rows_per_seq, t = pos_now + row % g.rows_per_seq;
+    float *d = cache + (size_t)seq * g.cache_seq_stride + (size_t)t * g.E + (col0 - part * g.E);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  }
+}
+
+template <bool TF32, int BN>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ GemmArgs g) {
+  using C = Cfg<BN>;
+  constexpr int BK = TF32 ? 32 : 64;  // elements per 128-byte swizzle row
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = tc::smem_addr(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t sA = base, sB = base + C::STAGES * A_STAGE;
+  const uint32_t bars = base + C::STAGES * C::STAGE;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * C::STAGES;
+  const uint32_t tfull_bar = bars + 16 * C::STAGES, tempty_bar = tfull_bar + 16;
+  const uint32_t slot = tempty_bar + 16, abort_flag = slot + 4;
+  uint32_t *slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (slot - raw));
+  const tc::Guard guard{g.err, abort_flag};
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      tc::mbar_init(full_bar + 8 * s, 1);
+      tc::mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      tc::mbar_init(tfull_bar + 8 * a, 1);
+      tc::mbar_init(tempty_bar + 8 * a, 4 * C::HALVES);
+    }
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(abort_flag), "r"(0u));
+    tc::fence_mbar_init();
+    tc::prefetch_tmap(&tm_a);
+    tc::prefetch_tmap(&tm_b);
+  }
+  if (warp == 1) tc::tmem_alloc<C::TMEM_COLS>(slot);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *slot_ptr;
+
+  const int num_m = (g.M + BM - 1) / BM, num_n = (g.N + BN - 1) / BN, tiles = num_m * num_n;
+  const int num_kb = (g.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer ----------------
+      uint32_t stage = 0, phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < tiles && ok; tile += gridDim.x) {
+        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (!tc::mbar_wait(empty_bar + 8 * stage, phase ^ 1, guard)) { ok = false; break; }
+          tc::mbar_expect_tx(full_bar + 8 * stage, C::STAGE);
+          tc::tma_load_2d(sA + stage * A_STAGE, &tm_a, kb * BK, m_blk * BM, full_bar + 8 * stage);
+          tc::tma_load_2d(sB + stage * C::B_STAGE, &tm_b, kb * BK, n_blk * BN, full_bar + 8 * stage);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc = tc::umma_idesc(TF32 ? 2u : 1u, BM, BN, 0, 0);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < tiles && ok; tile += gridDim.x) {
+        if (!tc::mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1, guard)) break;
+        tc::fence_after_sync();
+        const uint32_t d = tmem + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (!tc::mbar_wait(full_bar + 8 * stage, phase, guard)) { ok = false; break; }
+          tc::fence_after_sync();
+          const uint32_t a = sA + stage * A_STAGE, b = sB + stage * C::B_STAGE;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 4 x 32 bytes of K per swizzle row: UMMA_K = 8 (tf32) / 16 (bf16)
+            tc::umma<TF32>(d, tc::umma_desc_sw128(a + 32 * k, 16, 1024), tc::umma_desc_sw128(b + 32 * k, 16, 1024),
+                           idesc, (uint32_t)((kb | k) != 0));
+          tc::umma_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs have read it
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (ok) tc::umma_commit(tfull_bar + 8 * acc);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {  // ---------------- epilogue warps ----------------
+    const int e = warp - 2, quad = warp & 3, half = e >> 2;  // tcgen05.ld: warp w may touch TMEM lanes 32 (w % 4) ..
+    if (half < C::HALVES) {
+      uint32_t acc = 0, acc_phase = 0;
+      const int pos_now = g.pos_base + (g.pos_dev ? *g.pos_dev : 0);
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        if (!tc::mbar_wait(tfull_bar + 8 * acc, acc_phase, guard)) break;
+        tc::fence_after_sync();
+        const int row = m_blk * BM + quad * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < C::COLS_PER_HALF; c += 32) {
+          const int col_in_tile = half * C::COLS_PER_HALF + c;
+          const int col0 = n_blk * BN + col_in_tile;
+          uint32_t r[32];
+          tc::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + acc * BN + col_in_tile, r);
+          tc::tmem_ld_wait();
+          if (col0 < g.N) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            epilogue_chunk(g, v, row, col0, pos_now);
+          }
+        }
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tempty_bar + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (warp == 1) tc::tmem_dealloc<C::TMEM_COLS>(tmem);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+template <bool TF32, int BN>
+void launch_one(const GemmPlan &p) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ZG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TF32, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set = true;
+  }
+  gemm_tc_kernel<TF32, BN><<<p.grid, THREADS, C::SMEM, ctx().stream>>>(p.tm_a, p.tm_b, p.args);
+  ZG_LAUNCH_CHECK();
+}
+
+unsigned *g_err_word = nullptr;
+
+}  // namespace
+
+unsigned *gemm_error_word() {
+  if (!g_err_word) {
+    ZG_CUDA(cudaMalloc(&g_err_word, sizeof(unsigned)));
+    ZG_CUDA(cudaMemset(g_err_word, 0, sizeof(unsigned)));
+  }
+  return g_err_word;
+}
+
+bool make_tmap_2d(CUtensorMap *out, const void *base, int dtype, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                  uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error(1, "cuTensorMapEncodeTiled is not available from this driver", __FILE__, __LINE__);
+    return false;
+  }
+  if (((uintptr_t)base & 15) || (pitch_bytes & 15)) {
+    set_error(1, "tensor map: base address and row pitch must be multiples of 16 bytes", __FILE__, __LINE__);
+    return false;
+  }
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {pitch_bytes};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUtensorMapDataType dt = dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUresult r = fn(out, dt, 2, const_cast<void *>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error(1, "cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
+    return false;
+  }
+  return true;
+}
+
+bool gemm_plan(GemmPlan *p, int tf32, const void *A, size_t lda, const void *W, const GemmArgs &args, int bn) {
+  const int es = tf32 ? 4 : 2, bk = 128 / es;
+  if (args.M <= 0 || args.N <= 0 || args.K <= 0) return false;
+  if ((args.K * es) % 16 != 0) {
+    set_error(1, "Linear (tensor-core path): in_features * sizeof(element) must be a multiple of 16", __FILE__, __LINE__);
+    return false;
+  }
+  if (args.k_cache && (args.E % 32 != 0)) {
+    set_error(1, "Linear (tensor-core path): n_embed must be a multiple of 32 for the fused cache append", __FILE__, __LINE__);
+    return false;
+  }
+  const int sms = ctx().sm_count > 0 ? ctx().sm_count : 148;
+  if (bn == 0) {  // widest tile that still gives every SM a tile; skinny problems stream W with narrow tiles
+    const int num_m = (args.M + BM - 1) / BM;
+    bn = 32;
+    for (int cand : {256, 128, 64}) {
+      if (num_m * ((args.N + cand - 1) / cand) >= sms) { bn = cand; break; }
+    }
+  }
+  p->bn = bn;
+  p->tf32 = tf32;
+  p->args = args;
+  if (!p->args.err) p->args.err = gemm_error_word();
+  const int tiles = ((args.M + BM - 1) / BM) * ((args.N + bn - 1) / bn);
+  p->grid = tiles < sms ? tiles : sms;
+  if (!make_tmap_2d(&p->tm_a, A, tf32 ? 0 : 1, (uint64_t)args.M, (uint64_t)args.K, lda * es, BM, bk)) return false;
+  if (!make_tmap_2d(&p->tm_b, W, tf32 ? 0 : 1, (uint64_t)args.N, (uint64_t)args.K, (uint64_t)args.K * es, bn, bk)) return false;
+  return true;
+}
+
+void gemm_launch(const GemmPlan &p) {
+  if (p.tf32) {
+    switch (p.bn) {
+      case 256: launch_one<true, 256>(p); break;
+      case 128: launch_one<true, 128>(p); break;
+      case 64: launch_one<true, 64>(p); break;
+      default: launch_one<true, 32>(p); break;
+    }
+  } else {
+    switch (p.bn) {
+      case 256: launch_one<false, 256>(p); break;
+      case 128: launch_one<false, 128>(p); break;
+      case 64: launch_one<false, 64>(p); break;
+      default: launch_one<false, 32>(p); break;
+    }
+  }
+}
+
+}  // namespace zg
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+using namespace zg;
+
+extern "C" {
+
+// Linear.forward on the tensor cores.  precision: 0 = fp32 operands as kind::tf32 (no copies), 1 = bf16 operands
+// (inputs_bf16 / weight_bf16 are device pointers to bf16 copies made by zg_to_bf16).  epi: 0 none, 1 GELU, 2 residual.
+void zg_linear_forward_tc(const zg_linear *self, const void *inputs, size_t inputs_len, float *outputs, int precision,
+                          const void *weight_lowp, int epi, const float *resid, int tile_n) {
+  if (!require_ready("zg_linear_forward_tc")) return;
+  GemmArgs a;
+  a.M = (int)(inputs_len / self->in_features);
+  a.N = (int)self->out_features;
+  a.K = (int)self->in_features;
+  a.bias = self->bias;
+  a.out = outputs;
+  a.ldo = a.N;
+  a.epi = epi;
+  a.resid = resid;
+  a.ldr = a.N;
+  GemmPlan p;
+  const void *w = precision == 0 ? (const void *)self->weight : weight_lowp;
+  if (!gemm_plan(&p, precision == 0, inputs, self->in_features, w, a, tile_n)) return;
+  gemm_launch(p);
+}
+
+// fp32 -> bf16 (round to nearest even) copy: start-up conversion of weights for the kind::f16 path.
+__global__ void to_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, size_t n) {
+  for (size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4; i < n; i += (size_t)blockDim.x * gridDim.x * 4) {
+    if (i + 4 <= n) {
+      const float4 v = *reinterpret_cast<const float4 *>(src + i);
+      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t *>(&a);
+      pk.y = *reinterpret_cast<uint32_t *>(&b);
+      *reinterpret_cast<uint2 *>(dst + i) = pk;
+    } else {
+      for (size_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+    }
+  }
+}
+void zg_to_bf16(const float *src, void *dst_bf16, size_t n) {
+  if (!require_ready("zg_to_bf16") || n == 0) return;
+  const size_t want = (n / 4 + 255) / 256;
+  to_bf16_kernel<<<(unsigned)(want < 2368 ? (want ? want : 1) : 2368), 256, 0, ctx().stream>>>(
+      src, reinterpret_cast<__nv_bfloat16 *>(dst_bf16), n);
+  ZG_LAUNCH_CHECK();
+}
+
+int zg_tc_error(void) {  // watchdog word of the tensor-core kernels; 0 when clean (synchronises)
+  if (!require_ready("zg_tc_error")) return 1;
+  unsigned v = 0;
+  unsigned *w = gemm_error_word();
+  ZG_CUDA(cudaStreamSynchronize(ctx().stream));
+  ZG_CUDA(cudaMemcpy(&v, w, sizeof(v), cudaMemcpyDeviceToHost));
+  return (int)v;
+}
+
+}  // extern "C"

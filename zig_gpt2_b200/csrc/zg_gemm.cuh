@@ -1,0 +1,46 @@
+// zg_gemm.cuh -- interface of the tcgen05 GEMM behind Linear.forward for M >= 16 (zg_gemm.cu).
+#pragma once
+#include "zg_common.cuh"
+#include "zg_tc.cuh"
+
+namespace zg {
+
+enum { TC_EPI_NONE = 0, TC_EPI_GELU = 1, TC_EPI_RESIDUAL = 2 };
+
+// Epilogue description of one Linear call: out[M,N] = epi(bias + A[M,K] . W[N,K]^T).
+struct GemmArgs {
+  int M = 0, N = 0, K = 0;
+  const float *bias = nullptr;  // [N] or null (lm_head, main.zig:312)
+  void *out = nullptr;          // [M, ldo] fp32 or bf16
+  int ldo = 0;
+  int out_bf16 = 0;
+  int epi = TC_EPI_NONE;
+  int gelu_fast = 0;            // tanh.approx instead of tanhf (bf16 pipelines only)
+  const float *resid = nullptr;  // [M, ldr] fp32, added after the bias (main.zig:136-139,142-145); may alias out
+  int ldr = 0;
+  // c_attn only: columns [E, 2E) / [2E, 3E) are additionally appended, as fp32, to the K / V caches
+  // (ops.zig:151-152,156-157): cache row = pos_base + *pos_dev + (row % rows_per_seq) of sequence row / rows_per_seq.
+  float *k_cache = nullptr, *v_cache = nullptr;
+  int E = 0, rows_per_seq = 1;
+  long long cache_seq_stride = 0;  // floats between consecutive sequences' caches
+  const int *pos_dev = nullptr;
+  int pos_base = 0;
+  unsigned *err = nullptr;  // sticky device error word (watchdog)
+};
+
+// A prepared launch: tensor maps are encoded once (start-up for the engines, per call for the op-level API).
+struct GemmPlan {
+  CUtensorMap tm_a, tm_b;
+  GemmArgs args;
+  int bn = 256;
+  int tf32 = 1;
+  int grid = 0;
+};
+
+// A: [M, K] row-major with pitch lda elements; W: [N, K] row-major (the reference's Linear.weight layout, ops.zig:9).
+// tf32 != 0: fp32 operands fed to kind::tf32; else bf16 operands fed to kind::f16.  bn = 0 picks the tile width.
+bool gemm_plan(GemmPlan *p, int tf32, const void *A, size_t lda, const void *W, const GemmArgs &args, int bn);
+void gemm_launch(const GemmPlan &p);
+unsigned *gemm_error_word();  // device word shared by every tensor-core kernel of this library
+
+}  // namespace zg
