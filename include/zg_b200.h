@@ -69,13 +69,15 @@ void zg_linear_forward(const zg_linear *self, const float *inputs, size_t inputs
 /* Linear.forward on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed shared-memory ring),
  * the replacement of the reference's cblas_sgemm(RowMajor, NoTrans, Trans) call (ops.zig:30-45) when M >= 16.
  *   precision 0: fp32 operands read in place as kind::tf32 (`inputs` fp32, weight = self->weight);
- *   precision 1: bf16 operands (`inputs` and `weight_lowp` are bf16 copies made with zg_to_bf16), fp32 accumulation.
+ *   precision 2: as 0 with 3xTF32 error compensation (hi/lo operand split in shared memory, three MMAs per K step):
+ *                fp32-class accuracy on the tensor cores, used by the HBM-bound batched decode step;
+ *   precision 1: f16 operands (`inputs` and `weight_lowp` are f16 copies made with zg_to_f16), fp32 accumulation.
  *   epi: 0 = bias only, 1 = bias + GELU (main.zig:79-80 fused), 2 = bias + residual add of `resid` [M,N] (main.zig:136-145).
  *   tile_n: 0 = automatic, else 32/64/128/256 (N width of the CTA tile).
  * zg_linear_forward itself takes this path (precision 0) when M >= 16. */
 void zg_linear_forward_tc(const zg_linear *self, const void *inputs, size_t inputs_len, float *outputs, int precision,
                           const void *weight_lowp, int epi, const float *resid, int tile_n);
-void zg_to_bf16(const float *src, void *dst_bf16, size_t n); /* fp32 -> bf16 round-to-nearest-even copy (start-up) */
+void zg_to_f16(const float *src, void *dst_f16, size_t n); /* fp32 -> f16 round-to-nearest-even copy (start-up) */
 int zg_tc_error(void); /* watchdog word of the tensor-core kernels (0 = clean); synchronises */
 
 typedef struct { size_t emb_dim; const float *weight; } zg_embedding; /* ops.zig:49-57 */
@@ -180,6 +182,41 @@ void zg_engine_run_steps(zg_engine *e, size_t first_step, size_t n_steps);
 int zg_engine_read_tokens(zg_engine *e, size_t first_step, size_t n_steps, size_t *out_tokens);
 /* Per-phase device timestamps of the last launch (ns, CTA 0), for profiling; returns entries written. */
 size_t zg_engine_read_profile(zg_engine *e, unsigned long long *out, size_t max_entries);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched paths (BASELINE configs 3-5): B independent sequences as B rows of every Linear, so the reference's
+ * M=1 sgemm calls become tensor-core GEMMs.  Sequences never interact (no cross-sequence op in ops.zig/main.zig).
+ *   decode step: kind::tf32 GEMMs over the fp32 weights in place + batched single-query attention over per-sequence
+ *                fp32 KV caches [cache_rows, n_embed] per block (main.zig:298-299 once per sequence), one CUDA graph per step;
+ *   prefill:     whole prompts at once -- f16 copies of the weights (made here), kind::f16 GEMMs with fused
+ *                bias/GELU/residual/KV-append epilogues and causal flash attention (tcgen05); replaces the
+ *                token-at-a-time prompt loop of generate() (main.zig:331-334) and leaves the same caches behind.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct zg_batch zg_batch;
+/* start-up: caches for n_seqs sequences of up to cache_rows positions, activation sets, plans (tensor maps), f16
+ * weight copies when max_prompt > 0 (prefill enabled for prompts up to max_prompt tokens).  flags bit 0: no CUDA graph;
+ * bit 1: single-pass TF32 decode GEMMs instead of the error-compensated 3xTF32 default. */
+zg_batch *zg_batch_create(const zg_gpt *gpt, size_t n_seqs, size_t cache_rows, size_t max_prompt, int flags);
+void zg_batch_destroy(zg_batch *e);
+/* GPT.forward(seq_len, tokens[b], compute_logits) for every sequence b (tokens: HOST, n_seqs entries). */
+void zg_batch_forward(zg_batch *e, size_t seq_len, const size_t *tokens, int compute_logits);
+const float *zg_batch_logits(const zg_batch *e);      /* device, [n_seqs, pitch] */
+size_t zg_batch_logits_pitch(const zg_batch *e);      /* floats per row (vocab_size rounded up to 4) */
+/* all prompt positions at once: tokens[b*T + t] (HOST); equals T calls of GPT.forward per sequence (cache rows [0,T),
+ * logits of the last position when compute_logits). */
+int zg_batch_prefill(zg_batch *e, const size_t *tokens, size_t T, int compute_logits);
+int zg_batch_prefill_resident(zg_batch *e, size_t T, int compute_logits); /* tokens of the last prefill, no upload (timing) */
+/* generate() (main.zig:322-342), greedy, per sequence: prompts[b*n_inputs + s] (HOST) -> out_tokens[b*n_total + s] (HOST). */
+int zg_batch_generate_greedy(zg_batch *e, const size_t *prompts, size_t n_inputs, size_t n_total, size_t *out_tokens,
+                             int use_prefill);
+void zg_batch_set_position(zg_batch *e, size_t pos); /* next step attends to cache rows [0, pos] (timing at a given context) */
+void zg_batch_run_steps(zg_batch *e, size_t n_steps); /* n greedy steps from the current position, device resident, async */
+const float *zg_batch_k_cache(const zg_batch *e, size_t layer); /* device, [n_seqs, cache_rows, n_embed] */
+const float *zg_batch_v_cache(const zg_batch *e, size_t layer);
+/* the two attention kernels on their own (per-op parity tests) */
+void zg_attention_prefill(const void *qkv_f16, void *out_f16, size_t B, size_t T, size_t n_heads, size_t n_embed);
+void zg_attention_decode_batch(const float *q, const float *k_cache, const float *v_cache, size_t B, size_t context,
+                               size_t n_heads, size_t n_embed, size_t seq_len, float *out);
 
 #ifdef __cplusplus
 }

@@ -18,14 +18,12 @@ def to_tf32(a):
     return (u & np.uint32(0xFFFFE000)).view(np.float32)
 
 
-def to_bf16_bits(a):
-    u = a.astype(np.float32).view(np.uint32).astype(np.uint64)
-    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
-    return r
+def to_f16_bits(a):
+    return a.astype(np.float16).view(np.uint16)
 
 
-def bf16_to_f32(b):
-    return (b.astype(np.uint32) << 16).view(np.float32)
+def f16_to_f32(b):
+    return b.view(np.float16).astype(np.float32)
 
 
 def gelu(x):
@@ -37,14 +35,17 @@ def run_case(L, M, N, K, prec, epi, bn, rng, with_bias=True):
     w = (rng.standard_normal((N, K)) * 0.05).astype(np.float32)
     b = rng.standard_normal(N).astype(np.float32) if with_bias else None
     res = rng.standard_normal((M, N)).astype(np.float32) if epi == 2 else None
-    if prec == 0:
-        x, w = to_tf32(x), to_tf32(w)
+    if prec in (0, 2, 3):
+        if prec == 0:
+            x, w = to_tf32(x), to_tf32(w)
+        if prec == 3:  # single-pass tf32 on operands that are NOT representable: shows the truncation error
+            prec = 0
         dx, dw = DeviceBuffer.from_numpy(x), DeviceBuffer.from_numpy(w)
         lowp = None
         xin = dx.ptr
     else:
-        xb, wb = to_bf16_bits(x), to_bf16_bits(w)
-        x, w = bf16_to_f32(xb), bf16_to_f32(wb)
+        xb, wb = to_f16_bits(x), to_f16_bits(w)
+        x, w = f16_to_f32(xb), f16_to_f32(wb)
         dxb, dwb = DeviceBuffer.from_numpy(xb), DeviceBuffer.from_numpy(wb)
         dw = DeviceBuffer.from_numpy(w)
         lowp = dwb.ptr
@@ -83,6 +84,8 @@ def main():
         (1024, 3072, 768, 0, 1, 0), (1024, 3072, 768, 1, 1, 0), (2048, 768, 3072, 1, 2, 0),
         (4096, 4800, 1600, 0, 0, 0), (4096, 1600, 6400, 1, 0, 0),
         (1000, 1000, 1000, 0, 0, 64), (1000, 1000, 1000, 0, 0, 32), (1000, 1000, 1000, 1, 2, 128),
+        (128, 256, 64, 2, 0, 256), (64, 2304, 768, 2, 0, 0), (64, 768, 3072, 2, 2, 0), (1000, 1000, 1000, 2, 1, 64),
+        (1000, 1000, 1000, 2, 0, 128), (1024, 50257, 768, 2, 0, 0), (64, 2304, 768, 3, 0, 0),
     ]
     for (M, N, K, prec, epi, bn) in cases:
         t0 = time.time()
@@ -90,7 +93,7 @@ def main():
             e, err = run_case(L, M, N, K, prec, epi, bn, rng)
         except Exception as ex:  # noqa: BLE001
             e, err = float("nan"), str(ex)
-        good = (err == 0) and (e < 2e-5)
+        good = (err == 0) and (e < (2e-3 if prec == 3 else 2e-5))
         ok_all &= bool(good)
         results.append(dict(M=M, N=N, K=K, prec=prec, epi=epi, bn=bn, rel_err=e, tc_err=err, ok=bool(good), s=round(time.time() - t0, 2)))
         print(results[-1], flush=True)
@@ -100,8 +103,8 @@ def main():
     # timing: cfg 3 shapes (355M, M = 16384)
     if ok_all:
         for (M, N, K, prec) in [(16384, 3072, 1024, 1), (16384, 1024, 1024, 1), (16384, 4096, 1024, 1), (16384, 1024, 4096, 1),
-                                (16384, 3072, 1024, 0), (16384, 4096, 1024, 0), (8192, 8192, 8192, 1), (8192, 8192, 8192, 0)]:
-            es = 4 if prec == 0 else 2
+                                (16384, 3072, 1024, 0), (16384, 4096, 1024, 0), (8192, 8192, 8192, 1), (8192, 8192, 8192, 0), (64, 4800, 1600, 2), (64, 6400, 1600, 2), (64, 1600, 6400, 2), (1024, 2304, 768, 2), (1024, 50257, 768, 2), (64, 50257, 1600, 2)]:
+            es = 2 if prec == 1 else 4
             dx = DeviceBuffer(M * K * es // 4)
             dw = DeviceBuffer(N * K)
             dwl = DeviceBuffer(N * K * es // 4)
@@ -118,7 +121,7 @@ def main():
             ms = L.zg_timer_end_ms() / reps
             lib.check()
             tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
-            r = dict(timing=True, M=M, N=N, K=K, prec=prec, ms=round(ms, 4), tflops=round(tf, 1))
+            r = dict(timing=True, M=M, N=N, K=K, prec=prec, ms=round(ms, 4), tflops=round(tf, 1), w_gbs=round(N * K * es / (ms * 1e-3) / 1e9, 1))
             results.append(r)
             print(r, flush=True)
             for b in (dx, dw, dwl, db, out):

@@ -7,8 +7,8 @@
 //       warp 1      tcgen05.mma: S = Q K^T (128x128x64, K-major x K-major) into TMEM, then O_j = P V (128x64x128,
 //                   K-major P from shared memory x MN-major V exactly as TMA delivered it)
 //       warps 2..5  one query row per thread: tcgen05.ld S -> online softmax in registers (thread-local row max /
-//                   sum, no shuffles) -> P as bf16 into swizzled shared memory -> running O in registers
-//     bf16 operands, fp32 accumulation and softmax.  Two CTAs fit per SM so one CTA's softmax overlaps the other's MMAs.
+//                   sum, no shuffles) -> P as f16 into swizzled shared memory -> running O in registers
+//     f16 operands, fp32 accumulation and softmax.  Two CTAs fit per SM so one CTA's softmax overlaps the other's MMAs.
 //
 // (2) attn_decode_batch_kernel: one new token per sequence against that sequence's fp32 KV cache (ops.zig:249-307,
 //     query length 1, no mask) for B sequences at once; one CTA per (head, sequence), each K/V row read exactly once
@@ -32,7 +32,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
-attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16 *__restrict__ out, int T, int H, int E,
+attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_qkv, __half *__restrict__ out, int T, int H, int E,
                     int n_bh, unsigned *err) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = tc::smem_addr(smem_raw);
@@ -85,8 +85,8 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16 *_
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc_s = tc::umma_idesc(1, QT, KT, 0, 0);  // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = tc::umma_idesc(1, QT, HD, 0, 1);  // P (K-major) x V (MN-major: head dim contiguous)
+      constexpr uint32_t idesc_s = tc::umma_idesc(0, QT, KT, 0, 0);  // Q (K-major) x K (K-major)
+      constexpr uint32_t idesc_o = tc::umma_idesc(0, QT, HD, 0, 1);  // P (K-major) x V (MN-major: head dim contiguous)
       bool ok = tc::mbar_wait(q_full, 0, guard);
       for (int j = 0; j < n_kv && ok; ++j) {
         const int s = j & 1;
@@ -163,7 +163,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16 *_
           if (diag && c + i > r) p0 = 0.0f;
           if (diag && c + i + 1 > r) p1 = 0.0f;
           sum += p0 + p1;
-          __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
+          __half2 t = __floats2half2_rn(p0, p1);
           pk[i >> 1] = *reinterpret_cast<uint32_t *>(&t);
         }
         // K-major SWIZZLE_128B: atom = 64 keys; row r at r * 128 bytes; 16-byte chunk index XOR (r % 8)
@@ -195,14 +195,14 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16 *_
       }
       if (q0 + r < T) {
         const float inv = 1.0f / l;
-        __nv_bfloat16 *dst = out + (size_t)(row_base + q0 + r) * E + h * HD;
+        __half *dst = out + (size_t)(row_base + q0 + r) * E + h * HD;
 #pragma unroll
         for (int d = 0; d < HD; d += 8) {
           uint4 pk;
-          __nv_bfloat162 t0 = __floats2bfloat162_rn(o[d] * inv, o[d + 1] * inv),
-                         t1 = __floats2bfloat162_rn(o[d + 2] * inv, o[d + 3] * inv),
-                         t2 = __floats2bfloat162_rn(o[d + 4] * inv, o[d + 5] * inv),
-                         t3 = __floats2bfloat162_rn(o[d + 6] * inv, o[d + 7] * inv);
+          __half2 t0 = __floats2half2_rn(o[d] * inv, o[d + 1] * inv),
+                         t1 = __floats2half2_rn(o[d + 2] * inv, o[d + 3] * inv),
+                         t2 = __floats2half2_rn(o[d + 4] * inv, o[d + 5] * inv),
+                         t3 = __floats2half2_rn(o[d + 6] * inv, o[d + 7] * inv);
           pk.x = *reinterpret_cast<uint32_t *>(&t0); pk.y = *reinterpret_cast<uint32_t *>(&t1);
           pk.z = *reinterpret_cast<uint32_t *>(&t2); pk.w = *reinterpret_cast<uint32_t *>(&t3);
           *reinterpret_cast<uint4 *>(dst + d) = pk;
@@ -241,7 +241,8 @@ attn_decode_batch_kernel(const float *__restrict__ q, int ldq, const float *__re
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   // each half-warp walks rows t = 2 * (warp + DEC_WARPS * i) + half, four rows in flight
   constexpr int STEP = 2 * DEC_WARPS;
-  for (int t0 = 2 * warp + half; t0 < T; t0 += 4 * STEP) {
+  for (int tb = 2 * warp; tb < T; tb += 4 * STEP) {  // warp-uniform trip count: the shuffles below need all 32 lanes
+    const int t0 = tb + half;
     float4 kk[4], vv[4];
     float s[4];
 #pragma unroll
@@ -313,25 +314,29 @@ attn_decode_batch_kernel(const float *__restrict__ q, int ldq, const float *__re
 
 }  // namespace
 
-bool attn_prefill_plan(AttnPrefillPlan *p, const void *qkv_bf16, void *out_bf16, int B, int T, int H, int E) {
+bool attn_prefill_plan(AttnPrefillPlan *p, const void *qkv_f16, void *out_f16, int B, int T, int H, int E) {
   if (E != H * HD) {
     set_error(1, "prefill attention: head_dim must be 64", __FILE__, __LINE__);
     return false;
   }
-  p->out = out_bf16;
+  p->out = out_f16;
   p->B = B; p->T = T; p->H = H; p->E = E;
-  return make_tmap_2d(&p->tm_qkv, qkv_bf16, 1, (uint64_t)B * T, (uint64_t)3 * E, (uint64_t)3 * E * 2, QT, HD);
+  return make_tmap_2d(&p->tm_qkv, qkv_f16, 1, (uint64_t)B * T, (uint64_t)3 * E, (uint64_t)3 * E * 2, QT, HD);
 }
 
-void attn_prefill_launch(const AttnPrefillPlan &p) {
+void attn_init_attrs() {
   static bool attr_set = false;
   if (!attr_set) {
     ZG_CUDA(cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     attr_set = true;
   }
+}
+
+void attn_prefill_launch(const AttnPrefillPlan &p) {
+  attn_init_attrs();
   const int num_qt = (p.T + QT - 1) / QT, n_bh = p.B * p.H;
   attn_prefill_kernel<<<num_qt * n_bh, ATT_THREADS, ATT_SMEM, ctx().stream>>>(
-      p.tm_qkv, reinterpret_cast<__nv_bfloat16 *>(p.out), p.T, p.H, p.E, n_bh, gemm_error_word());
+      p.tm_qkv, reinterpret_cast<__half *>(p.out), p.T, p.H, p.E, n_bh, gemm_error_word());
   ZG_LAUNCH_CHECK();
 }
 
@@ -348,11 +353,11 @@ using namespace zg;
 
 extern "C" {
 
-// Causal self-attention over B prompts of T tokens: qkv bf16 [B*T, 3E] (the c_attn output) -> out bf16 [B*T, E].
-void zg_attention_prefill(const void *qkv_bf16, void *out_bf16, size_t B, size_t T, size_t n_heads, size_t n_embed) {
+// Causal self-attention over B prompts of T tokens: qkv f16 [B*T, 3E] (the c_attn output) -> out f16 [B*T, E].
+void zg_attention_prefill(const void *qkv_f16, void *out_f16, size_t B, size_t T, size_t n_heads, size_t n_embed) {
   if (!require_ready("zg_attention_prefill")) return;
   AttnPrefillPlan p;
-  if (!attn_prefill_plan(&p, qkv_bf16, out_bf16, (int)B, (int)T, (int)n_heads, (int)n_embed)) return;
+  if (!attn_prefill_plan(&p, qkv_f16, out_f16, (int)B, (int)T, (int)n_heads, (int)n_embed)) return;
   attn_prefill_launch(p);
 }
 

@@ -5,11 +5,12 @@
 namespace zg {
 
 struct AttnPrefillPlan {
-  CUtensorMap tm_qkv;  // bf16 [B*T, 3E], box 128 rows x 64 columns, 128-byte swizzle
-  void *out = nullptr; // bf16 [B*T, E]
+  CUtensorMap tm_qkv;  // f16 [B*T, 3E], box 128 rows x 64 columns, 128-byte swizzle
+  void *out = nullptr; // f16 [B*T, E]
   int B = 0, T = 0, H = 0, E = 0;
 };
-bool attn_prefill_plan(AttnPrefillPlan *p, const void *qkv_bf16, void *out_bf16, int B, int T, int H, int E);
+bool attn_prefill_plan(AttnPrefillPlan *p, const void *qkv_f16, void *out_f16, int B, int T, int H, int E);
+void attn_init_attrs();
 void attn_prefill_launch(const AttnPrefillPlan &p);
 void attn_decode_batch_launch(const float *q, int ldq, const float *k_cache, const float *v_cache, long long seq_stride,
                               int B, int H, int E, float *out, int ldo, const int *pos_dev, int pos_base);

@@ -1,0 +1,547 @@
+// zg_batch.cu -- GPT.forward / generate (main.zig:178-207, 322-342) for B independent sequences at once.
+//
+// The reference forwards one token of one sequence per call; sequences never interact (no cross-sequence op exists
+// in ops.zig / main.zig), so B sequences are B rows of every activation matrix and the Linear layers become GEMMs:
+//   * decode step   rows = B (one new token per sequence, all at the same position): tcgen05 kind::tf32 GEMMs that read
+//                   the reference's fp32 weights in place, fp32 KV caches, batched single-query attention; the
+//                   whole step is one CUDA graph whose kernels read the position from a device word.
+//   * prefill       rows = B*T (whole prompts): f16 operand copies of the weights (made once at create), kind::f16
+//                   GEMMs with fused bias / GELU / residual / KV-cache-append epilogues, causal flash attention on the
+//                   tensor cores; replaces the reference's token-at-a-time prompt loop (main.zig:331-334).
+// Nothing here allocates after zg_batch_create.
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "zg_attn.cuh"
+#include "zg_gemm.cuh"
+
+namespace zg {
+
+namespace {
+
+typedef unsigned long long u64;
+
+// x[m,:] = wte[tok(m)] + wpe[pos(m)]  (main.zig:179-183).  decode: one row per sequence, pos = *pos_dev;
+// prefill: row m = b*T + t, pos = t.
+__global__ void embed_rows_kernel(const float *__restrict__ wte, const float *__restrict__ wpe,
+                                  const u64 *__restrict__ tok, int T, const int *pos_dev, int E, float *__restrict__ x) {
+  const int m = blockIdx.x;
+  const size_t token = (size_t)tok[m];
+  const int pos = pos_dev ? *pos_dev : (m % T);
+  const float4 *a = reinterpret_cast<const float4 *>(wte + token * E), *p = reinterpret_cast<const float4 *>(wpe + (size_t)pos * E);
+  float4 *o = reinterpret_cast<float4 *>(x + (size_t)m * E);
+  for (int i = threadIdx.x; i < (E >> 2); i += blockDim.x) {
+    const float4 u = __ldg(a + i), v = __ldg(p + i);
+    o[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+  }
+}
+
+// LayerNorm.forward (ops.zig:82-104: single pass, eps inside the square root, division) over rows that may be
+// strided in the input (row r starts at in + r * in_stride); output dense, fp32 or f16.
+template <bool OUT_F16>
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float *__restrict__ in, size_t in_stride, void *out,
+                                                      const float *__restrict__ g, const float *__restrict__ b, int E,
+                                                      float eps) {
+  __shared__ float red[32];
+  const float *row = in + (size_t)blockIdx.x * in_stride;
+  float s = 0.0f, ss = 0.0f;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    const float v = row[i];
+    s += v;
+    ss = fmaf(v, v, ss);
+  }
+  s = block_sum(s, red);
+  ss = block_sum(ss, red);
+  const float n = (float)E, mean = s / n;
+  const float std_ = sqrtf(ss / n - mean * mean + eps);
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    const float y = (row[i] - mean) / std_ * g[i] + b[i];
+    if (OUT_F16) reinterpret_cast<__half *>(out)[(size_t)blockIdx.x * E + i] = __float2half_rn(y);
+    else reinterpret_cast<float *>(out)[(size_t)blockIdx.x * E + i] = y;
+  }
+}
+
+// greedy argmax per row (first maximum wins, like the oracle); writes the next token and the history row
+__global__ void __launch_bounds__(256) argmax_rows_kernel(const float *__restrict__ logits, size_t pitch, int V,
+                                                          u64 *__restrict__ tok, u64 *__restrict__ hist, int B,
+                                                          const int *pos_dev) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const float *row = logits + (size_t)blockIdx.x * pitch;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float v = row[i];
+    if (v > best) { best = v; bi = i; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { sv[w] = best; si[w] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k)
+      if (sv[k] > best || (sv[k] == best && si[k] < bi)) { best = sv[k]; bi = si[k]; }
+    tok[blockIdx.x] = (u64)bi;
+    if (hist) hist[(size_t)(*pos_dev) * B + blockIdx.x] = (u64)bi;
+  }
+}
+
+// prompt step: tok[b] = prompts[b][s], hist[s][b] = tok[b]  with s = *pos_dev
+__global__ void load_prompt_tokens_kernel(const u64 *__restrict__ prompts, int n_inputs, u64 *__restrict__ tok,
+                                          u64 *__restrict__ hist, int B, const int *pos_dev) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int s = *pos_dev;
+  const u64 t = prompts[(size_t)b * n_inputs + s];
+  tok[b] = t;
+  if (hist) hist[(size_t)s * B + b] = t;
+}
+// after a prefill: hist[s][b] = prompts[b][s] for every prompt position, tok[b] = last prompt token
+__global__ void prompts_to_hist_kernel(const u64 *__restrict__ prompts, int n_inputs, u64 *__restrict__ tok,
+                                       u64 *__restrict__ hist, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * n_inputs) return;
+  const int b = i / n_inputs, s = i % n_inputs;
+  const u64 t = prompts[i];
+  hist[(size_t)s * B + b] = t;
+  if (s == n_inputs - 1) tok[b] = t;
+}
+__global__ void set_pos_kernel(int *pos, int v, int add) { *pos = add ? *pos + v : v; }
+
+struct LayerW {
+  const float *ln1_g, *ln1_b, *attn_w, *attn_b, *proj_w, *proj_b, *ln2_g, *ln2_b, *fc_w, *fc_b, *proj2_w, *proj2_b;
+  const __half *attn_w16, *proj_w16, *fc_w16, *proj2_w16;
+};
+
+struct LayerPlans {
+  GemmPlan attn, proj, fc, proj2;
+};
+
+}  // namespace
+
+}  // namespace zg
+
+using namespace zg;
+
+struct zg_batch {
+  zg_config cfg;
+  int B = 0, cap = 0, max_prompt = 0, Vp = 0;
+  bool f16_prefill = false;
+  const float *wte = nullptr, *wpe = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
+  const __half *wte16 = nullptr;
+  std::vector<LayerW> layers;
+  // caches: per layer [B][cap][E]
+  float *k_cache = nullptr, *v_cache = nullptr;
+  size_t layer_stride = 0, seq_stride = 0;
+  // decode-step activations (rows = B)
+  float *x = nullptr, *h = nullptr, *qkv = nullptr, *att = nullptr, *h4 = nullptr, *logits = nullptr;
+  // prefill activations (rows = B * max_prompt)
+  float *px = nullptr, *plast = nullptr;
+  __half *ph = nullptr, *pqkv = nullptr, *patt = nullptr, *ph4 = nullptr, *plast16 = nullptr;
+  u64 *tok = nullptr, *hist = nullptr, *prompts = nullptr, *ptok = nullptr;
+  size_t hist_cap = 0;
+  int *pos = nullptr;
+  // plans
+  std::vector<LayerPlans> dec_plans, pre_plans;
+  GemmPlan dec_head, pre_head;
+  std::vector<AttnPrefillPlan> pre_attn;
+  int pre_T = -1;
+  cudaGraphExec_t graph_sample = nullptr, graph_prompt = nullptr;
+  int graph_n_inputs = -1;
+  int host_pos = 0;  // host mirror of *pos (every entry point that moves the position updates it)
+  bool use_graph = true;
+  int dec_mode = 2;  // decode-step GEMMs: 2 = 3xTF32 (fp32-class accuracy), 1 = single-pass TF32
+  std::vector<void *> owned;
+};
+
+namespace {
+
+template <typename T>
+T *balloc(zg_batch *e, size_t n) {
+  void *p = zg_alloc(n * sizeof(T));
+  if (p) e->owned.push_back(p);
+  return (T *)p;
+}
+
+const __half *f16_copy(zg_batch *e, const float *src, size_t n) {
+  __half *d = balloc<__half>(e, n);
+  if (d) zg_to_f16(src, d, n);
+  return d;
+}
+
+GemmArgs base_args(int M, int N, int K, const float *bias, void *out, int ldo, int out_f16) {
+  GemmArgs a;
+  a.M = M; a.N = N; a.K = K; a.bias = bias; a.out = out; a.ldo = ldo; a.out_f16 = out_f16;
+  return a;
+}
+
+bool build_decode_plans(zg_batch *e) {
+  const int B = e->B, E = (int)e->cfg.n_embed, V = (int)e->cfg.vocab_size;
+  e->dec_plans.resize(e->layers.size());
+  for (size_t l = 0; l < e->layers.size(); ++l) {
+    const LayerW &w = e->layers[l];
+    LayerPlans &p = e->dec_plans[l];
+    GemmArgs a = base_args(B, 3 * E, E, w.attn_b, e->qkv, 3 * E, 0);
+    a.k_cache = e->k_cache + l * e->layer_stride;
+    a.v_cache = e->v_cache + l * e->layer_stride;
+    a.E = E; a.rows_per_seq = 1; a.cache_seq_stride = (long long)e->seq_stride; a.pos_dev = e->pos;
+    if (!gemm_plan(&p.attn, e->dec_mode, e->h, E, w.attn_w, a, 0)) return false;
+    a = base_args(B, E, E, w.proj_b, e->x, E, 0);
+    a.epi = TC_EPI_RESIDUAL; a.resid = e->x; a.ldr = E;
+    if (!gemm_plan(&p.proj, e->dec_mode, e->att, E, w.proj_w, a, 0)) return false;
+    a = base_args(B, 4 * E, E, w.fc_b, e->h4, 4 * E, 0);
+    a.epi = TC_EPI_GELU;
+    if (!gemm_plan(&p.fc, e->dec_mode, e->h, E, w.fc_w, a, 0)) return false;
+    a = base_args(B, E, 4 * E, w.proj2_b, e->x, E, 0);
+    a.epi = TC_EPI_RESIDUAL; a.resid = e->x; a.ldr = E;
+    if (!gemm_plan(&p.proj2, e->dec_mode, e->h4, 4 * E, w.proj2_w, a, 0)) return false;
+  }
+  GemmArgs a = base_args(B, V, E, nullptr, e->logits, e->Vp, 0);
+  return gemm_plan(&e->dec_head, e->dec_mode, e->h, E, e->wte, a, 0);
+}
+
+bool build_prefill_plans(zg_batch *e, int T) {
+  if (e->pre_T == T) return true;
+  const int B = e->B, E = (int)e->cfg.n_embed, V = (int)e->cfg.vocab_size, M = B * T, H = (int)e->cfg.n_heads;
+  e->pre_plans.resize(e->layers.size());
+  e->pre_attn.resize(e->layers.size());
+  for (size_t l = 0; l < e->layers.size(); ++l) {
+    const LayerW &w = e->layers[l];
+    LayerPlans &p = e->pre_plans[l];
+    GemmArgs a = base_args(M, 3 * E, E, w.attn_b, e->pqkv, 3 * E, 1);
+    a.k_cache = e->k_cache + l * e->layer_stride;
+    a.v_cache = e->v_cache + l * e->layer_stride;
+    a.E = E; a.rows_per_seq = T; a.cache_seq_stride = (long long)e->seq_stride; a.pos_dev = nullptr; a.pos_base = 0;
+    if (!gemm_plan(&p.attn, 0, e->ph, E, w.attn_w16, a, 0)) return false;
+    if (!attn_prefill_plan(&e->pre_attn[l], e->pqkv, e->patt, B, T, H, E)) return false;
+    a = base_args(M, E, E, w.proj_b, e->px, E, 0);
+    a.epi = TC_EPI_RESIDUAL; a.resid = e->px; a.ldr = E;
+    if (!gemm_plan(&p.proj, 0, e->patt, E, w.proj_w16, a, 0)) return false;
+    a = base_args(M, 4 * E, E, w.fc_b, e->ph4, 4 * E, 1);
+    a.epi = TC_EPI_GELU; a.gelu_fast = 1;
+    if (!gemm_plan(&p.fc, 0, e->ph, E, w.fc_w16, a, 0)) return false;
+    a = base_args(M, E, 4 * E, w.proj2_b, e->px, E, 0);
+    a.epi = TC_EPI_RESIDUAL; a.resid = e->px; a.ldr = E;
+    if (!gemm_plan(&p.proj2, 0, e->ph4, 4 * E, w.proj2_w16, a, 0)) return false;
+  }
+  GemmArgs a = base_args(B, V, E, nullptr, e->logits, e->Vp, 0);
+  if (!gemm_plan(&e->pre_head, 0, e->plast16, E, e->wte16, a, 0)) return false;
+  e->pre_T = T;
+  return true;
+}
+
+// One decode step for every sequence at position *pos: GPT.forward(seq_len = *pos + 1, tok[b]) (main.zig:178-195).
+void enqueue_step(zg_batch *e, bool from_prompt, int n_inputs, bool with_logits) {
+  cudaStream_t s = ctx().stream;
+  const int B = e->B, E = (int)e->cfg.n_embed, H = (int)e->cfg.n_heads, V = (int)e->cfg.vocab_size;
+  if (from_prompt) {
+    load_prompt_tokens_kernel<<<(B + 127) / 128, 128, 0, s>>>(e->prompts, n_inputs, e->tok, e->hist, B, e->pos);
+    ZG_LAUNCH_CHECK();
+  }
+  embed_rows_kernel<<<B, 128, 0, s>>>(e->wte, e->wpe, e->tok, 1, e->pos, E, e->x);
+  ZG_LAUNCH_CHECK();
+  for (size_t l = 0; l < e->layers.size(); ++l) {
+    const LayerW &w = e->layers[l];
+    const LayerPlans &p = e->dec_plans[l];
+    ln_rows_kernel<false><<<B, 256, 0, s>>>(e->x, E, e->h, w.ln1_g, w.ln1_b, E, 1e-5f);  // main.zig:121-123
+    ZG_LAUNCH_CHECK();
+    gemm_launch(p.attn);  // c_attn + K/V append at row *pos (ops.zig:143,151-152,156-157)
+    attn_decode_batch_launch(e->qkv, 3 * E, e->k_cache + l * e->layer_stride, e->v_cache + l * e->layer_stride,
+                             (long long)e->seq_stride, B, H, E, e->att, E, e->pos, 0);  // ops.zig:160-169
+    gemm_launch(p.proj);  // c_proj + residual (ops.zig:172, main.zig:136-139)
+    ln_rows_kernel<false><<<B, 256, 0, s>>>(e->x, E, e->h, w.ln2_g, w.ln2_b, E, 1e-5f);  // main.zig:140
+    ZG_LAUNCH_CHECK();
+    gemm_launch(p.fc);     // c_fc + GELU (main.zig:79-80)
+    gemm_launch(p.proj2);  // c_proj + residual (main.zig:81,142-145)
+  }
+  if (with_logits) {
+    ln_rows_kernel<false><<<B, 256, 0, s>>>(e->x, E, e->h, e->lnf_g, e->lnf_b, E, 1e-5f);  // main.zig:189
+    ZG_LAUNCH_CHECK();
+    gemm_launch(e->dec_head);  // tied lm_head (main.zig:192-194)
+    argmax_rows_kernel<<<B, 256, 0, s>>>(e->logits, (size_t)e->Vp, V, e->tok, e->hist, B, e->pos);
+    ZG_LAUNCH_CHECK();
+  }
+  set_pos_kernel<<<1, 1, 0, s>>>(e->pos, 1, 1);
+  ZG_LAUNCH_CHECK();
+}
+
+void enqueue_prefill(zg_batch *e, int T, bool with_logits) {
+  cudaStream_t s = ctx().stream;
+  const int B = e->B, E = (int)e->cfg.n_embed, M = B * T;
+  embed_rows_kernel<<<M, 128, 0, s>>>(e->wte, e->wpe, e->ptok, T, nullptr, E, e->px);
+  ZG_LAUNCH_CHECK();
+  for (size_t l = 0; l < e->layers.size(); ++l) {
+    const LayerW &w = e->layers[l];
+    const LayerPlans &p = e->pre_plans[l];
+    ln_rows_kernel<true><<<M, 256, 0, s>>>(e->px, E, e->ph, w.ln1_g, w.ln1_b, E, 1e-5f);
+    ZG_LAUNCH_CHECK();
+    gemm_launch(p.attn);
+    attn_prefill_launch(e->pre_attn[l]);
+    gemm_launch(p.proj);
+    ln_rows_kernel<true><<<M, 256, 0, s>>>(e->px, E, e->ph, w.ln2_g, w.ln2_b, E, 1e-5f);
+    ZG_LAUNCH_CHECK();
+    gemm_launch(p.fc);
+    gemm_launch(p.proj2);
+  }
+  if (with_logits) {  // last position of every prompt only (main.zig:192)
+    ln_rows_kernel<true><<<B, 256, 0, s>>>(e->px + (size_t)(T - 1) * E, (size_t)T * E, e->plast16, e->lnf_g, e->lnf_b, E, 1e-5f);
+    ZG_LAUNCH_CHECK();
+    gemm_launch(e->pre_head);
+  }
+}
+
+bool capture(zg_batch *e, cudaGraphExec_t *exec, bool from_prompt, int n_inputs, bool with_logits) {
+  cudaStream_t s = ctx().stream;
+  cudaGraph_t g = nullptr;
+  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return false;
+  enqueue_step(e, from_prompt, n_inputs, with_logits);
+  if (cudaStreamEndCapture(s, &g) != cudaSuccess || !g) {
+    cudaGetLastError();
+    return false;
+  }
+  const cudaError_t r = cudaGraphInstantiate(exec, g, 0);
+  cudaGraphDestroy(g);
+  return r == cudaSuccess;
+}
+
+}  // namespace
+
+extern "C" {
+
+zg_batch *zg_batch_create(const zg_gpt *gpt, size_t n_seqs, size_t cache_rows, size_t max_prompt, int flags) {
+  if (!require_ready("zg_batch_create")) return nullptr;
+  const zg_config &c = gpt->config;
+  const size_t E = c.n_embed, V = c.vocab_size, L = c.n_layer;
+  if (E != c.n_heads * 64 || n_seqs == 0 || cache_rows == 0 || cache_rows > c.context_size || max_prompt > cache_rows) {
+    set_error(1, "zg_batch_create: head_dim must be 64, 0 < max_prompt <= cache_rows <= context_size", __FILE__, __LINE__);
+    return nullptr;
+  }
+  zg_batch *e = new zg_batch();
+  e->cfg = c;
+  e->B = (int)n_seqs;
+  e->cap = (int)cache_rows;
+  e->max_prompt = (int)max_prompt;
+  e->Vp = (int)((V + 3) & ~(size_t)3);
+  e->f16_prefill = max_prompt > 0;
+  e->use_graph = !(flags & 1);
+  e->dec_mode = (flags & 2) ? 1 : 2;
+  e->wte = gpt->wte.weight;
+  e->wpe = gpt->wpe.weight;
+  e->lnf_g = gpt->ln_f.weight;
+  e->lnf_b = gpt->ln_f.bias;
+  e->layers.resize(L);
+  for (size_t l = 0; l < L; ++l) {
+    const zg_block &b = gpt->h[l];
+    LayerW &w = e->layers[l];
+    w.ln1_g = b.ln_1.weight; w.ln1_b = b.ln_1.bias;
+    w.attn_w = b.attn.c_attn.weight; w.attn_b = b.attn.c_attn.bias;
+    w.proj_w = b.attn.c_proj.weight; w.proj_b = b.attn.c_proj.bias;
+    w.ln2_g = b.ln_2.weight; w.ln2_b = b.ln_2.bias;
+    w.fc_w = b.mlp.c_fc.weight; w.fc_b = b.mlp.c_fc.bias;
+    w.proj2_w = b.mlp.c_proj.weight; w.proj2_b = b.mlp.c_proj.bias;
+    w.attn_w16 = w.proj_w16 = w.fc_w16 = w.proj2_w16 = nullptr;
+    if (e->f16_prefill) {
+      w.attn_w16 = f16_copy(e, w.attn_w, 3 * E * E);
+      w.proj_w16 = f16_copy(e, w.proj_w, E * E);
+      w.fc_w16 = f16_copy(e, w.fc_w, 4 * E * E);
+      w.proj2_w16 = f16_copy(e, w.proj2_w, 4 * E * E);
+    }
+  }
+  if (e->f16_prefill) e->wte16 = f16_copy(e, e->wte, V * E);
+  const size_t B = n_seqs;
+  e->seq_stride = cache_rows * E;
+  e->layer_stride = B * e->seq_stride;
+  e->k_cache = balloc<float>(e, L * e->layer_stride);
+  e->v_cache = balloc<float>(e, L * e->layer_stride);
+  e->x = balloc<float>(e, B * E);
+  e->h = balloc<float>(e, B * E);
+  e->qkv = balloc<float>(e, B * 3 * E);
+  e->att = balloc<float>(e, B * E);
+  e->h4 = balloc<float>(e, B * 4 * E);
+  e->logits = balloc<float>(e, B * (size_t)e->Vp);
+  e->tok = balloc<u64>(e, B);
+  e->hist_cap = (size_t)c.context_size;
+  e->hist = balloc<u64>(e, e->hist_cap * B);
+  e->prompts = balloc<u64>(e, B * (size_t)c.context_size);
+  e->pos = balloc<int>(e, 4);
+  if (e->f16_prefill) {
+    const size_t M = B * max_prompt;
+    e->px = balloc<float>(e, M * E);
+    e->ph = balloc<__half>(e, M * E);
+    e->pqkv = balloc<__half>(e, M * 3 * E);
+    e->patt = balloc<__half>(e, M * E);
+    e->ph4 = balloc<__half>(e, M * 4 * E);
+    e->plast16 = balloc<__half>(e, B * E);
+    e->ptok = balloc<u64>(e, M);
+  }
+  if (zg_last_error() || !e->k_cache || !e->v_cache || !e->hist) {
+    zg_batch_destroy(e);
+    return nullptr;
+  }
+  zg_memset(e->k_cache, 0, L * e->layer_stride * sizeof(float));
+  zg_memset(e->v_cache, 0, L * e->layer_stride * sizeof(float));
+  zg_memset(e->pos, 0, 4 * sizeof(int));
+  zg_memset(e->tok, 0, B * sizeof(u64));
+  gemm_init_attrs();
+  attn_init_attrs();
+  if (!build_decode_plans(e)) {
+    zg_batch_destroy(e);
+    return nullptr;
+  }
+  zg_sync();
+  return e;
+}
+
+void zg_batch_destroy(zg_batch *e) {
+  if (!e) return;
+  if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+  if (e->graph_sample) cudaGraphExecDestroy(e->graph_sample);
+  if (e->graph_prompt) cudaGraphExecDestroy(e->graph_prompt);
+  for (void *p : e->owned) zg_free(p);
+  delete e;
+}
+
+const float *zg_batch_logits(const zg_batch *e) { return e->logits; }
+size_t zg_batch_logits_pitch(const zg_batch *e) { return (size_t)e->Vp; }
+
+// GPT.forward(seq_len, tokens[b], compute_logits) for every sequence b (HOST tokens); logits -> zg_batch_logits().
+void zg_batch_forward(zg_batch *e, size_t seq_len, const size_t *tokens, int compute_logits) {
+  if (!require_ready("zg_batch_forward")) return;
+  if (seq_len == 0 || seq_len > (size_t)e->cap) {
+    set_error(1, "zg_batch_forward: seq_len outside the cache", __FILE__, __LINE__);
+    return;
+  }
+  cudaStream_t s = ctx().stream;
+  ZG_CUDA(cudaMemcpyAsync(e->tok, tokens, e->B * sizeof(u64), cudaMemcpyHostToDevice, s));
+  set_pos_kernel<<<1, 1, 0, s>>>(e->pos, (int)seq_len - 1, 0);
+  ZG_LAUNCH_CHECK();
+  u64 *hist = e->hist;
+  e->hist = nullptr;  // explicit forwards do not record history
+  enqueue_step(e, false, 0, compute_logits != 0);
+  e->hist = hist;
+  e->host_pos = (int)seq_len;
+}
+
+// The whole prompt of every sequence at once: tokens[b*T + t] (HOST).  Fills cache rows [0, T) of every block and,
+// if asked, the logits of the last position -- what T calls of GPT.forward per sequence leave behind (main.zig:330-334).
+int zg_batch_prefill(zg_batch *e, const size_t *tokens, size_t T, int compute_logits) {
+  if (!require_ready("zg_batch_prefill")) return 1;
+  if (!e->f16_prefill || T == 0 || T > (size_t)e->max_prompt) {
+    set_error(1, "zg_batch_prefill: T must be in [1, max_prompt] given to zg_batch_create", __FILE__, __LINE__);
+    return 1;
+  }
+  if (!build_prefill_plans(e, (int)T)) return 1;
+  cudaStream_t s = ctx().stream;
+  ZG_CUDA(cudaMemcpyAsync(e->ptok, tokens, e->B * T * sizeof(u64), cudaMemcpyHostToDevice, s));
+  enqueue_prefill(e, (int)T, compute_logits != 0);
+  set_pos_kernel<<<1, 1, 0, s>>>(e->pos, (int)T, 0);
+  ZG_LAUNCH_CHECK();
+  e->host_pos = (int)T;
+  return zg_last_error();
+}
+// same, tokens already on the device (timing without the upload)
+int zg_batch_prefill_resident(zg_batch *e, size_t T, int compute_logits) {
+  if (!require_ready("zg_batch_prefill_resident")) return 1;
+  if (!e->f16_prefill || T == 0 || T > (size_t)e->max_prompt || !build_prefill_plans(e, (int)T)) return 1;
+  enqueue_prefill(e, (int)T, compute_logits != 0);
+  return zg_last_error();
+}
+
+// generate() (main.zig:322-342), greedy, for B sequences with prompts[b*n_inputs + s] (HOST) of equal length.
+// Steps s < n_inputs forward the prompt (one token at a time like the reference, or all at once when use_prefill);
+// step n_inputs forwards the last prompt token again (the reference's duplicate, main.zig:329-338); every step's
+// token goes to out_tokens[b*n_total + s] (HOST).  Asynchronous until the final copy.
+int zg_batch_generate_greedy(zg_batch *e, const size_t *prompts, size_t n_inputs, size_t n_total, size_t *out_tokens,
+                             int use_prefill) {
+  if (!require_ready("zg_batch_generate_greedy")) return 1;
+  const int B = e->B;
+  if (n_inputs == 0 || n_inputs > n_total || n_total > (size_t)e->cap || n_total > e->hist_cap) {
+    set_error(1, "zg_batch_generate_greedy: need 1 <= n_inputs <= n_total <= cache rows", __FILE__, __LINE__);
+    return 1;
+  }
+  if (use_prefill && (!e->f16_prefill || n_inputs > (size_t)e->max_prompt)) {
+    set_error(1, "zg_batch_generate_greedy: prompt longer than max_prompt", __FILE__, __LINE__);
+    return 1;
+  }
+  cudaStream_t s = ctx().stream;
+  ZG_CUDA(cudaMemcpyAsync(e->prompts, prompts, (size_t)B * n_inputs * sizeof(u64), cudaMemcpyHostToDevice, s));
+  size_t first = 0;
+  if (use_prefill) {
+    if (!build_prefill_plans(e, (int)n_inputs)) return 1;
+    ZG_CUDA(cudaMemcpyAsync(e->ptok, e->prompts, (size_t)B * n_inputs * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+    enqueue_prefill(e, (int)n_inputs, false);
+    prompts_to_hist_kernel<<<(unsigned)((B * n_inputs + 255) / 256), 256, 0, s>>>(e->prompts, (int)n_inputs, e->tok,
+                                                                                   e->hist, B);
+    ZG_LAUNCH_CHECK();
+    set_pos_kernel<<<1, 1, 0, s>>>(e->pos, (int)n_inputs, 0);
+    ZG_LAUNCH_CHECK();
+    first = n_inputs;
+  } else {
+    set_pos_kernel<<<1, 1, 0, s>>>(e->pos, 0, 0);
+    ZG_LAUNCH_CHECK();
+  }
+  if (e->use_graph) {
+    if (!e->graph_sample && !capture(e, &e->graph_sample, false, 0, true)) e->use_graph = false;
+    if (e->use_graph && first < n_inputs && (e->graph_n_inputs != (int)n_inputs || !e->graph_prompt)) {
+      if (e->graph_prompt) cudaGraphExecDestroy(e->graph_prompt);
+      e->graph_prompt = nullptr;
+      if (capture(e, &e->graph_prompt, true, (int)n_inputs, false)) e->graph_n_inputs = (int)n_inputs;
+      else e->use_graph = false;
+    }
+  }
+  for (size_t st = first; st < n_total; ++st) {
+    const bool prompt_step = st < n_inputs;
+    if (e->use_graph) {
+      ZG_CUDA(cudaGraphLaunch(prompt_step ? e->graph_prompt : e->graph_sample, s));
+      ctx().launches += prompt_step ? 2 + 7 * e->layers.size() + 1 : 1 + 7 * e->layers.size() + 4;
+    } else {
+      enqueue_step(e, prompt_step, (int)n_inputs, !prompt_step);
+    }
+  }
+  e->host_pos = (int)n_total;
+  // history [n_total][B] -> out [B][n_total]
+  std::vector<u64> tmp((size_t)B * n_total);
+  ZG_CUDA(cudaMemcpyAsync(tmp.data(), e->hist, tmp.size() * sizeof(u64), cudaMemcpyDeviceToHost, s));
+  ZG_CUDA(cudaStreamSynchronize(s));
+  for (size_t st = 0; st < n_total; ++st)
+    for (int b = 0; b < B; ++b) out_tokens[(size_t)b * n_total + st] = (size_t)tmp[st * B + b];
+  if (zg_tc_error()) set_error(1, "tensor-core kernel watchdog tripped", __FILE__, __LINE__);
+  return zg_last_error();
+}
+
+// Device-resident stepping for timing: run n_steps sampling steps from the current position (no host copies).
+void zg_batch_run_steps(zg_batch *e, size_t n_steps) {
+  if (!require_ready("zg_batch_run_steps")) return;
+  cudaStream_t s = ctx().stream;
+  if (e->host_pos + n_steps > (size_t)e->cap) {
+    set_error(1, "zg_batch_run_steps: would run past the KV cache", __FILE__, __LINE__);
+    return;
+  }
+  e->host_pos += (int)n_steps;
+  if (e->use_graph && !e->graph_sample && !capture(e, &e->graph_sample, false, 0, true)) e->use_graph = false;
+  for (size_t i = 0; i < n_steps; ++i) {
+    if (e->use_graph) {
+      ZG_CUDA(cudaGraphLaunch(e->graph_sample, s));
+      ctx().launches += 1 + 7 * e->layers.size() + 4;
+    } else {
+      enqueue_step(e, false, 0, true);
+    }
+  }
+}
+// Set the common position (and so the attended length) directly: timing a step at T = 1024 needs no 1023 real steps.
+void zg_batch_set_position(zg_batch *e, size_t pos) {
+  if (!require_ready("zg_batch_set_position")) return;
+  set_pos_kernel<<<1, 1, 0, ctx().stream>>>(e->pos, (int)pos, 0);
+  ZG_LAUNCH_CHECK();
+  e->host_pos = (int)pos;
+}
+const float *zg_batch_k_cache(const zg_batch *e, size_t layer) { return e->k_cache + layer * e->layer_stride; }
+const float *zg_batch_v_cache(const zg_batch *e, size_t layer) { return e->v_cache + layer * e->layer_stride; }
+
+}  // extern "C"

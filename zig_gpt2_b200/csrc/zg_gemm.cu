@@ -8,7 +8,7 @@
 //   warp 1      MMA issuer     one elected thread issues tcgen05.mma (UTC*MMA), accumulators in TMEM, double-buffered
 //   warps 2..9  epilogue       tcgen05.ld (LDTM) -> bias / GELU / residual / K-V cache append -> global
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).  The epilogue of tile i
-// overlaps the main loop of tile i+1.  kind::tf32 reads the fp32 tensors as they are; kind::f16 reads bf16 copies.
+// overlaps the main loop of tile i+1.  kind::tf32 reads the fp32 tensors as they are; kind::f16 reads f16 copies.
 #include <initializer_list>
 
 #include "zg_gemm.cuh"
@@ -24,15 +24,20 @@ constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (2 + EPI_WARPS) * 32;
 constexpr int SMEM_BUDGET = 200 * 1024;
 
-template <int BN>
+enum { MODE_F16 = 0, MODE_TF32 = 1, MODE_TF32X3 = 2 };
+
+template <int MODE, int BN>
 struct Cfg {
+  static constexpr bool SPLIT = MODE == MODE_TF32X3;  // hi/lo operand copies: every stage holds two A and two B tiles
   static constexpr int B_STAGE = BN * ROW_BYTES;
   static constexpr int STAGE = A_STAGE + B_STAGE;
-  static constexpr int STAGES = (SMEM_BUDGET / STAGE) > 10 ? 10 : (SMEM_BUDGET / STAGE);
+  static constexpr int STAGE_ALL = SPLIT ? 2 * STAGE : STAGE;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_ALL) > 10 ? 10 : (SMEM_BUDGET / STAGE_ALL);
   static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;  // two accumulator stages
-  static constexpr int HALVES = BN >= 64 ? 2 : 1;               // epilogue warps e and e+4 split the columns
+  // epilogue warps e and e+4 split the columns; in the 3xTF32 mode warps 6..9 split operands instead
+  static constexpr int HALVES = (SPLIT || BN < 64) ? 1 : 2;
   static constexpr int COLS_PER_HALF = BN / HALVES;
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM = STAGES * STAGE_ALL + 1024 /*alignment slack*/ + 384 /*barriers*/;
 };
 
 __device__ __forceinline__ float gelu_fast(float x) {
@@ -82,14 +87,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float (&v)[32]
         if (col0 + j < g.N) v[j] += rr[j];
     }
   }
-  if (g.out_bf16) {
-    __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(g.out) + (size_t)row * g.ldo + col0;
+  if (g.out_f16) {
+    __half *o = reinterpret_cast<__half *>(g.out) + (size_t)row * g.ldo + col0;
     if (full && (g.ldo & 7) == 0) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         uint4 pk;
-        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]),
-                       t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+        __half2 t0 = __floats2half2_rn(v[j], v[j + 1]), t1 = __floats2half2_rn(v[j + 2], v[j + 3]),
+                       t2 = __floats2half2_rn(v[j + 4], v[j + 5]), t3 = __floats2half2_rn(v[j + 6], v[j + 7]);
         pk.x = *reinterpret_cast<uint32_t *>(&t0); pk.y = *reinterpret_cast<uint32_t *>(&t1);
         pk.z = *reinterpret_cast<uint32_t *>(&t2); pk.w = *reinterpret_cast<uint32_t *>(&t3);
         *reinterpret_cast<uint4 *>(o + j) = pk;
@@ -97,7 +102,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float (&v)[32]
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (col0 + j < g.N) o[j] = __float2bfloat16_rn(v[j]);
+        if (col0 + j < g.N) o[j] = __float2half_rn(v[j]);
     }
   } else {
     float *o = reinterpret_cast<float *>(g.out) + (size_t)row * g.ldo + col0;
@@ -120,18 +125,26 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float (&v)[32]
   }
 }
 
-template <bool TF32, int BN>
+// MODE_F16: fp16 operands, kind::f16.  MODE_TF32: fp32 operands read in place as kind::tf32 (the tensor core drops the
+// low 13 mantissa bits).  MODE_TF32X3: error-compensated fp32 -- warps 6..9 split every landed tile into
+// hi = x & 0xffffe000 (exactly representable in tf32) and lo = x - hi (exact in fp32), and the MMA warp accumulates
+// A_lo B_hi + A_hi B_lo + A_hi B_hi, which restores fp32-class accuracy (~2^-20 relative per product) on the tensor
+// cores.  Used by the batched decode step, which is HBM-bound, so the 3x MMA count is free.
+template <int MODE, int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ GemmArgs g) {
-  using C = Cfg<BN>;
+  using C = Cfg<MODE, BN>;
+  constexpr bool TF32 = MODE != MODE_F16;
+  constexpr bool SPLIT = C::SPLIT;
   constexpr int BK = TF32 ? 32 : 64;  // elements per 128-byte swizzle row
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = tc::smem_addr(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t sA = base, sB = base + C::STAGES * A_STAGE;
-  const uint32_t bars = base + C::STAGES * C::STAGE;
-  const uint32_t full_bar = bars, empty_bar = bars + 8 * C::STAGES;
-  const uint32_t tfull_bar = bars + 16 * C::STAGES, tempty_bar = tfull_bar + 16;
+  const uint32_t sAlo = base + C::STAGES * C::STAGE, sBlo = sAlo + C::STAGES * A_STAGE;  // SPLIT only
+  const uint32_t bars = base + C::STAGES * C::STAGE_ALL;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * C::STAGES, split_bar = bars + 16 * C::STAGES;
+  const uint32_t tfull_bar = bars + 24 * C::STAGES, tempty_bar = tfull_bar + 16;
   const uint32_t slot = tempty_bar + 16, abort_flag = slot + 4;
   uint32_t *slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (slot - raw));
   const tc::Guard guard{g.err, abort_flag};
@@ -141,6 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     for (int s = 0; s < C::STAGES; ++s) {
       tc::mbar_init(full_bar + 8 * s, 1);
       tc::mbar_init(empty_bar + 8 * s, 1);
+      tc::mbar_init(split_bar + 8 * s, 4);
     }
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(tfull_bar + 8 * a, 1);
@@ -177,7 +191,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc = tc::umma_idesc(TF32 ? 2u : 1u, BM, BN, 0, 0);
+      constexpr uint32_t idesc = tc::umma_idesc(TF32 ? 2u : 0u, BM, BN, 0, 0);
+      const uint32_t ready_bar = SPLIT ? split_bar : full_bar;
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < tiles && ok; tile += gridDim.x) {
@@ -185,18 +200,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         tc::fence_after_sync();
         const uint32_t d = tmem + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          if (!tc::mbar_wait(full_bar + 8 * stage, phase, guard)) { ok = false; break; }
+          if (!tc::mbar_wait(ready_bar + 8 * stage, phase, guard)) { ok = false; break; }
           tc::fence_after_sync();
           const uint32_t a = sA + stage * A_STAGE, b = sB + stage * C::B_STAGE;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // 4 x 32 bytes of K per swizzle row: UMMA_K = 8 (tf32) / 16 (bf16)
-            tc::umma<TF32>(d, tc::umma_desc_sw128(a + 32 * k, 16, 1024), tc::umma_desc_sw128(b + 32 * k, 16, 1024),
-                           idesc, (uint32_t)((kb | k) != 0));
+          for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per swizzle row: UMMA_K = 8 (tf32) / 16 (f16)
+            const uint64_t da = tc::umma_desc_sw128(a + 32 * k, 16, 1024), db = tc::umma_desc_sw128(b + 32 * k, 16, 1024);
+            if constexpr (SPLIT) {
+              const uint64_t da_lo = tc::umma_desc_sw128(sAlo + stage * A_STAGE + 32 * k, 16, 1024);
+              const uint64_t db_lo = tc::umma_desc_sw128(sBlo + stage * C::B_STAGE + 32 * k, 16, 1024);
+              tc::umma<true>(d, da_lo, db, idesc, (uint32_t)((kb | k) != 0));
+              tc::umma<true>(d, da, db_lo, idesc, 1u);
+              tc::umma<true>(d, da, db, idesc, 1u);
+            } else {
+              tc::umma<TF32>(d, da, db, idesc, (uint32_t)((kb | k) != 0));
+            }
+          }
           tc::umma_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs have read it
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         if (ok) tc::umma_commit(tfull_bar + 8 * acc);  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (SPLIT && warp >= 6) {  // ---------------- operand splitters (3xTF32) ----------------
+    const int t = threadIdx.x - 6 * 32;  // 0..127
+    uint32_t stage = 0, phase = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < tiles && ok; tile += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if (!tc::mbar_wait(full_bar + 8 * stage, phase, guard)) { ok = false; break; }
+        const uint32_t hi[2] = {sA + stage * A_STAGE, sB + stage * C::B_STAGE};
+        const uint32_t lo[2] = {sAlo + stage * A_STAGE, sBlo + stage * C::B_STAGE};
+        const int chunks[2] = {A_STAGE / 16, C::B_STAGE / 16};
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+#pragma unroll 4
+          for (int i = t; i < chunks[w]; i += 128) {  // elementwise, so the swizzled placement is irrelevant
+            uint32_t x0, x1, x2, x3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(hi[w] + 16 * i));
+            const uint32_t h0 = x0 & 0xffffe000u, h1 = x1 & 0xffffe000u, h2 = x2 & 0xffffe000u, h3 = x3 & 0xffffe000u;
+            const uint32_t l0 = __float_as_uint(__uint_as_float(x0) - __uint_as_float(h0)),
+                           l1 = __float_as_uint(__uint_as_float(x1) - __uint_as_float(h1)),
+                           l2 = __float_as_uint(__uint_as_float(x2) - __uint_as_float(h2)),
+                           l3 = __float_as_uint(__uint_as_float(x3) - __uint_as_float(h3));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi[w] + 16 * i), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo[w] + 16 * i), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
+          }
+        }
+        tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(split_bar + 8 * stage);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {  // ---------------- epilogue warps ----------------
@@ -251,21 +306,46 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-template <bool TF32, int BN>
-void launch_one(const GemmPlan &p) {
-  using C = Cfg<BN>;
+template <int MODE, int BN>
+void set_attr() {
   static bool attr_set = false;
   if (!attr_set) {
-    ZG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TF32, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    ZG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE, BN>::SMEM));
     attr_set = true;
   }
-  gemm_tc_kernel<TF32, BN><<<p.grid, THREADS, C::SMEM, ctx().stream>>>(p.tm_a, p.tm_b, p.args);
+}
+
+template <int MODE, int BN>
+void launch_one(const GemmPlan &p) {
+  set_attr<MODE, BN>();
+  gemm_tc_kernel<MODE, BN><<<p.grid, THREADS, Cfg<MODE, BN>::SMEM, ctx().stream>>>(p.tm_a, p.tm_b, p.args);
   ZG_LAUNCH_CHECK();
+}
+
+template <int MODE>
+void launch_mode(const GemmPlan &p) {
+  switch (p.bn) {
+    case 256: launch_one<MODE, 256>(p); break;
+    case 128: launch_one<MODE, 128>(p); break;
+    case 64: launch_one<MODE, 64>(p); break;
+    default: launch_one<MODE, 32>(p); break;
+  }
+}
+template <int MODE>
+void set_attr_mode() {
+  set_attr<MODE, 256>(); set_attr<MODE, 128>(); set_attr<MODE, 64>(); set_attr<MODE, 32>();
 }
 
 unsigned *g_err_word = nullptr;
 
 }  // namespace
+
+void gemm_init_attrs() {  // outside any stream capture
+  set_attr_mode<MODE_F16>();
+  set_attr_mode<MODE_TF32>();
+  set_attr_mode<MODE_TF32X3>();
+  gemm_error_word();
+}
 
 unsigned *gemm_error_word() {
   if (!g_err_word) {
@@ -290,7 +370,7 @@ bool make_tmap_2d(CUtensorMap *out, const void *base, int dtype, uint64_t rows, 
   const cuuint64_t gstride[1] = {pitch_bytes};
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estride[2] = {1, 1};
-  const CUtensorMapDataType dt = dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt = dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const CUresult r = fn(out, dt, 2, const_cast<void *>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -300,7 +380,8 @@ bool make_tmap_2d(CUtensorMap *out, const void *base, int dtype, uint64_t rows, 
   return true;
 }
 
-bool gemm_plan(GemmPlan *p, int tf32, const void *A, size_t lda, const void *W, const GemmArgs &args, int bn) {
+bool gemm_plan(GemmPlan *p, int mode, const void *A, size_t lda, const void *W, const GemmArgs &args, int bn) {
+  const int tf32 = mode != MODE_F16;
   const int es = tf32 ? 4 : 2, bk = 128 / es;
   if (args.M <= 0 || args.N <= 0 || args.K <= 0) return false;
   if ((args.K * es) % 16 != 0) {
@@ -320,7 +401,7 @@ bool gemm_plan(GemmPlan *p, int tf32, const void *A, size_t lda, const void *W, 
     }
   }
   p->bn = bn;
-  p->tf32 = tf32;
+  p->mode = mode;
   p->args = args;
   if (!p->args.err) p->args.err = gemm_error_word();
   const int tiles = ((args.M + BM - 1) / BM) * ((args.N + bn - 1) / bn);
@@ -331,21 +412,9 @@ bool gemm_plan(GemmPlan *p, int tf32, const void *A, size_t lda, const void *W, 
 }
 
 void gemm_launch(const GemmPlan &p) {
-  if (p.tf32) {
-    switch (p.bn) {
-      case 256: launch_one<true, 256>(p); break;
-      case 128: launch_one<true, 128>(p); break;
-      case 64: launch_one<true, 64>(p); break;
-      default: launch_one<true, 32>(p); break;
-    }
-  } else {
-    switch (p.bn) {
-      case 256: launch_one<false, 256>(p); break;
-      case 128: launch_one<false, 128>(p); break;
-      case 64: launch_one<false, 64>(p); break;
-      default: launch_one<false, 32>(p); break;
-    }
-  }
+  if (p.mode == MODE_TF32X3) launch_mode<MODE_TF32X3>(p);
+  else if (p.mode == MODE_TF32) launch_mode<MODE_TF32>(p);
+  else launch_mode<MODE_F16>(p);
 }
 
 }  // namespace zg
@@ -357,8 +426,9 @@ using namespace zg;
 
 extern "C" {
 
-// Linear.forward on the tensor cores.  precision: 0 = fp32 operands as kind::tf32 (no copies), 1 = bf16 operands
-// (inputs_bf16 / weight_bf16 are device pointers to bf16 copies made by zg_to_bf16).  epi: 0 none, 1 GELU, 2 residual.
+// Linear.forward on the tensor cores.  precision: 0 = fp32 operands as kind::tf32 (no copies), 2 = the same with
+// 3xTF32 error compensation (fp32-class accuracy), 1 = f16 operands
+// (inputs_f16 / weight_f16 are device pointers to f16 copies made by zg_to_f16).  epi: 0 none, 1 GELU, 2 residual.
 void zg_linear_forward_tc(const zg_linear *self, const void *inputs, size_t inputs_len, float *outputs, int precision,
                           const void *weight_lowp, int epi, const float *resid, int tile_n) {
   if (!require_ready("zg_linear_forward_tc")) return;
@@ -373,31 +443,32 @@ void zg_linear_forward_tc(const zg_linear *self, const void *inputs, size_t inpu
   a.resid = resid;
   a.ldr = a.N;
   GemmPlan p;
-  const void *w = precision == 0 ? (const void *)self->weight : weight_lowp;
-  if (!gemm_plan(&p, precision == 0, inputs, self->in_features, w, a, tile_n)) return;
+  const void *w = precision == 1 ? weight_lowp : (const void *)self->weight;
+  const int mode = precision == 1 ? 0 : (precision == 2 ? 2 : 1);
+  if (!gemm_plan(&p, mode, inputs, self->in_features, w, a, tile_n)) return;
   gemm_launch(p);
 }
 
-// fp32 -> bf16 (round to nearest even) copy: start-up conversion of weights for the kind::f16 path.
-__global__ void to_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, size_t n) {
+// fp32 -> f16 (round to nearest even) copy: start-up conversion of weights for the kind::f16 path.
+__global__ void to_f16_kernel(const float *__restrict__ src, __half *__restrict__ dst, size_t n) {
   for (size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4; i < n; i += (size_t)blockDim.x * gridDim.x * 4) {
     if (i + 4 <= n) {
       const float4 v = *reinterpret_cast<const float4 *>(src + i);
-      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+      __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
       uint2 pk;
       pk.x = *reinterpret_cast<uint32_t *>(&a);
       pk.y = *reinterpret_cast<uint32_t *>(&b);
       *reinterpret_cast<uint2 *>(dst + i) = pk;
     } else {
-      for (size_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+      for (size_t j = i; j < n; ++j) dst[j] = __float2half_rn(src[j]);
     }
   }
 }
-void zg_to_bf16(const float *src, void *dst_bf16, size_t n) {
-  if (!require_ready("zg_to_bf16") || n == 0) return;
+void zg_to_f16(const float *src, void *dst_f16, size_t n) {
+  if (!require_ready("zg_to_f16") || n == 0) return;
   const size_t want = (n / 4 + 255) / 256;
-  to_bf16_kernel<<<(unsigned)(want < 2368 ? (want ? want : 1) : 2368), 256, 0, ctx().stream>>>(
-      src, reinterpret_cast<__nv_bfloat16 *>(dst_bf16), n);
+  to_f16_kernel<<<(unsigned)(want < 2368 ? (want ? want : 1) : 2368), 256, 0, ctx().stream>>>(
+      src, reinterpret_cast<__half *>(dst_f16), n);
   ZG_LAUNCH_CHECK();
 }
 

@@ -11,11 +11,11 @@ enum { TC_EPI_NONE = 0, TC_EPI_GELU = 1, TC_EPI_RESIDUAL = 2 };
 struct GemmArgs {
   int M = 0, N = 0, K = 0;
   const float *bias = nullptr;  // [N] or null (lm_head, main.zig:312)
-  void *out = nullptr;          // [M, ldo] fp32 or bf16
+  void *out = nullptr;          // [M, ldo] fp32 or f16
   int ldo = 0;
-  int out_bf16 = 0;
+  int out_f16 = 0;
   int epi = TC_EPI_NONE;
-  int gelu_fast = 0;            // tanh.approx instead of tanhf (bf16 pipelines only)
+  int gelu_fast = 0;            // tanh.approx instead of tanhf (f16 pipelines only)
   const float *resid = nullptr;  // [M, ldr] fp32, added after the bias (main.zig:136-139,142-145); may alias out
   int ldr = 0;
   // c_attn only: columns [E, 2E) / [2E, 3E) are additionally appended, as fp32, to the K / V caches
@@ -33,14 +33,15 @@ struct GemmPlan {
   CUtensorMap tm_a, tm_b;
   GemmArgs args;
   int bn = 256;
-  int tf32 = 1;
+  int mode = 1;  // 0 = fp16 operands, 1 = fp32 operands as tf32, 2 = fp32 operands, 3xTF32 error-compensated
   int grid = 0;
 };
 
 // A: [M, K] row-major with pitch lda elements; W: [N, K] row-major (the reference's Linear.weight layout, ops.zig:9).
-// tf32 != 0: fp32 operands fed to kind::tf32; else bf16 operands fed to kind::f16.  bn = 0 picks the tile width.
-bool gemm_plan(GemmPlan *p, int tf32, const void *A, size_t lda, const void *W, const GemmArgs &args, int bn);
+// mode: see GemmPlan::mode.  bn = 0 picks the tile width.
+bool gemm_plan(GemmPlan *p, int mode, const void *A, size_t lda, const void *W, const GemmArgs &args, int bn);
 void gemm_launch(const GemmPlan &p);
+void gemm_init_attrs();
 unsigned *gemm_error_word();  // device word shared by every tensor-core kernel of this library
 
 }  // namespace zg

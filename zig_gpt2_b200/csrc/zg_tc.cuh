@@ -2,7 +2,7 @@
 // accumulators, tcgen05.ld, UMMA shared-memory / instruction descriptors.  sm_100a only.
 #pragma once
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -39,7 +39,7 @@ struct Guard {
   unsigned *err_global;
   uint32_t abort_smem;  // shared address of a u32
 };
-__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, Guard g) {
+static __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, Guard g) {
   uint32_t aborted;
   asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(aborted) : "r"(g.abort_smem));
   if (aborted) return false;
@@ -174,7 +174,7 @@ __device__ __forceinline__ bool elect_one() {
 
 // ---- host side: tensor maps ---------------------------------------------------------------------------
 // 2-D row-major tensor [rows, cols] of `elem_bytes`-wide elements with row pitch `pitch_bytes`; box = [box_rows,
-// box_cols] with box_cols * elem_bytes == 128 (one swizzle row).  dtype: 0 = fp32 (tf32 operand), 1 = bf16.
+// box_cols] with box_cols * elem_bytes == 128 (one swizzle row).  dtype: 0 = fp32 (tf32 operand), 1 = fp16.
 bool make_tmap_2d(CUtensorMap *out, const void *base, int dtype, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
                   uint32_t box_rows, uint32_t box_cols);
 

@@ -66,7 +66,7 @@ SIGNATURES = {
     "zg_timer_begin": (I, []), "zg_timer_end_ms": (C.c_float, []),
     "zg_linear_forward": (V, [C.POINTER(ZgLinear), P, Z, P]),
     "zg_linear_forward_tc": (V, [C.POINTER(ZgLinear), P, Z, P, I, P, I, P, I]),
-    "zg_to_bf16": (V, [P, P, Z]), "zg_tc_error": (I, []),
+    "zg_to_f16": (V, [P, P, Z]), "zg_tc_error": (I, []),
     "zg_embedding_forward": (V, [C.POINTER(ZgEmbedding), c_size_p, Z, P]),
     "zg_layer_norm_forward": (V, [C.POINTER(ZgLayerNorm), P, Z]),
     "zg_attention_forward": (V, [C.POINTER(ZgAttention), Z] + [P] * 9),
@@ -90,6 +90,14 @@ SIGNATURES = {
     "zg_engine_set_prompt": (I, [P, c_size_p, Z]), "zg_engine_run_steps": (V, [P, Z, Z]),
     "zg_engine_read_tokens": (I, [P, Z, Z, c_size_p]),
     "zg_engine_read_profile": (Z, [P, C.POINTER(C.c_ulonglong), Z]),
+    "zg_batch_create": (P, [C.POINTER(ZgGPT), Z, Z, Z, I]), "zg_batch_destroy": (V, [P]),
+    "zg_batch_forward": (V, [P, Z, c_size_p, I]), "zg_batch_logits": (P, [P]), "zg_batch_logits_pitch": (Z, [P]),
+    "zg_batch_prefill": (I, [P, c_size_p, Z, I]), "zg_batch_prefill_resident": (I, [P, Z, I]),
+    "zg_batch_generate_greedy": (I, [P, c_size_p, Z, Z, c_size_p, I]),
+    "zg_batch_set_position": (V, [P, Z]), "zg_batch_run_steps": (V, [P, Z]),
+    "zg_batch_k_cache": (P, [P, Z]), "zg_batch_v_cache": (P, [P, Z]),
+    "zg_attention_prefill": (V, [P, P, Z, Z, Z, Z]),
+    "zg_attention_decode_batch": (V, [P, P, P, Z, Z, Z, Z, Z, P]),
 }
 
 _lib: Optional[C.CDLL] = None
