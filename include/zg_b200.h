@@ -63,7 +63,8 @@ typedef struct { /* ops.zig:4-19 */
   const float *bias;   /* device or NULL */
 } zg_linear;
 /* Linear.forward, ops.zig:21-46: outputs[M,N] = bias + inputs[M,K] weight[N,K]^T, M = inputs_len / in_features.
- * fp32 SIMT path (warp-per-row GEMV, exact fp32 accumulation). */
+ * M < 16: fp32 SIMT path (warp-per-row GEMV, HBM-bound, fp32 accumulation).  M >= 16: tcgen05 tensor-core GEMM in
+ * the error-compensated 3xTF32 mode (see zg_linear_forward_tc, precision 2). */
 void zg_linear_forward(const zg_linear *self, const float *inputs, size_t inputs_len, float *outputs);
 
 /* Linear.forward on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed shared-memory ring),
@@ -74,7 +75,7 @@ void zg_linear_forward(const zg_linear *self, const float *inputs, size_t inputs
  *   precision 1: f16 operands (`inputs` and `weight_lowp` are f16 copies made with zg_to_f16), fp32 accumulation.
  *   epi: 0 = bias only, 1 = bias + GELU (main.zig:79-80 fused), 2 = bias + residual add of `resid` [M,N] (main.zig:136-145).
  *   tile_n: 0 = automatic, else 32/64/128/256 (N width of the CTA tile).
- * zg_linear_forward itself takes this path (precision 0) when M >= 16. */
+ * zg_linear_forward itself takes this path (precision 2) when M >= 16. */
 void zg_linear_forward_tc(const zg_linear *self, const void *inputs, size_t inputs_len, float *outputs, int precision,
                           const void *weight_lowp, int epi, const float *resid, int tile_n);
 void zg_to_f16(const float *src, void *dst_f16, size_t n); /* fp32 -> f16 round-to-nearest-even copy (start-up) */

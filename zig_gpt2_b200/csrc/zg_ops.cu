@@ -320,6 +320,13 @@ extern "C" {
 
 void zg_linear_forward(const zg_linear *self, const float *inputs, size_t inputs_len, float *outputs) {
   if (!require_ready("zg_linear_forward")) return;
+  const size_t M = self->in_features ? inputs_len / self->in_features : 0;
+  // M >= 16: the dense contraction goes to the tensor cores (tcgen05 GEMM, 3xTF32 error-compensated so the result
+  // keeps fp32-class accuracy); below that the HBM-bound SIMT GEMV streams the weights once.
+  if (M >= 16 && self->in_features % 4 == 0 && ((uintptr_t)inputs & 15) == 0 && ((uintptr_t)self->weight & 15) == 0) {
+    zg_linear_forward_tc(self, inputs, inputs_len, outputs, 2, nullptr, 0, nullptr, 0);
+    return;
+  }
   launch_linear(inputs, self->weight, self->bias, outputs, inputs_len / self->in_features, self->in_features,
                 self->out_features, EPI_NONE, nullptr);
 }
