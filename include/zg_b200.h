@@ -79,6 +79,7 @@ void zg_linear_forward(const zg_linear *self, const float *inputs, size_t inputs
 void zg_linear_forward_tc(const zg_linear *self, const void *inputs, size_t inputs_len, float *outputs, int precision,
                           const void *weight_lowp, int epi, const float *resid, int tile_n);
 void zg_to_f16(const float *src, void *dst_f16, size_t n); /* fp32 -> f16 round-to-nearest-even copy (start-up) */
+void zg_tc_set_direct_epilogue(int on); /* test hook: 1 = per-row direct stores instead of the staged TMA-store epilogue */
 int zg_tc_error(void); /* watchdog word of the tensor-core kernels (0 = clean); synchronises */
 
 typedef struct { size_t emb_dim; const float *weight; } zg_embedding; /* ops.zig:49-57 */

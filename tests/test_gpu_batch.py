@@ -86,24 +86,33 @@ def test_linear_forward_routes_large_m_to_tensor_cores(L):
     assert rel(out.download().reshape(48, 3072), zo.linear(x, w, None)) <= FP32_RTOL
 
 
-@pytest.mark.parametrize("epi", [1, 2])
-def test_linear_fused_epilogues(L, epi):
-    """GELU folded into c_fc (main.zig:79-80) and the residual add folded into c_proj (main.zig:136-145)."""
+@pytest.mark.parametrize("direct", [0, 1])
+@pytest.mark.parametrize("epi,inplace,out_cols", [(1, False, 3072), (2, False, 3072), (2, True, 3072), (0, False, 3001)])
+def test_linear_fused_epilogues(L, epi, inplace, out_cols, direct):
+    """GELU folded into c_fc (main.zig:79-80) and the residual add folded into c_proj (main.zig:136-145), through
+    both epilogues: staged TMA stores (an in-place residual becomes a TMA reduce-add) and per-row direct stores.
+    N = 3001 exercises the clipped last tile."""
     import zg_oracle as zo
     from zig_gpt2_b200 import lib
     from zig_gpt2_b200.lib import DeviceBuffer, ZgLinear
 
     rs = np.random.RandomState(epi)
-    M, N, K = 130, 3072, 768
+    M, N, K = 130, out_cols, 768
     x, w, b = rs.randn(M, K).astype(np.float32), (rs.randn(N, K) * 0.05).astype(np.float32), rs.randn(N).astype(np.float32)
     r = rs.randn(M, N).astype(np.float32)
     want = zo.linear(x, w, b)
-    want = zo.gelu(want) if epi == 1 else want + r
+    want = zo.gelu(want) if epi == 1 else (want + r if epi == 2 else want)
     dx, dw, db, dr, out = (DeviceBuffer.from_numpy(a) for a in (x, w, b, r, np.zeros(M * N, np.float32)))
     lin = ZgLinear(K, N, dw.ptr, db.ptr)
-    L.zg_linear_forward_tc(C.byref(lin), dx.ptr, M * K, out.ptr, 2, None, epi, dr.ptr, 0)
-    lib.check()
-    assert rel(out.download().reshape(M, N), want) <= FP32_RTOL
+    L.zg_tc_set_direct_epilogue(direct)
+    try:
+        dst = dr if inplace else out
+        L.zg_linear_forward_tc(C.byref(lin), dx.ptr, M * K, dst.ptr, 2, None, epi, dr.ptr, 0)
+        lib.check()
+    finally:
+        L.zg_tc_set_direct_epilogue(0)
+    assert L.zg_tc_error() == 0
+    assert rel(dst.download().reshape(M, N), want) <= FP32_RTOL
 
 
 @pytest.mark.parametrize("B,T,H", [(1, 5, 12), (2, 128, 2), (2, 200, 3), (1, 1024, 2)])

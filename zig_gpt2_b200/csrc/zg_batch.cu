@@ -38,28 +38,55 @@ __global__ void embed_rows_kernel(const float *__restrict__ wte, const float *__
   }
 }
 
-// LayerNorm.forward (ops.zig:82-104: single pass, eps inside the square root, division) over rows that may be
-// strided in the input (row r starts at in + r * in_stride); output dense, fp32 or f16.
+// LayerNorm.forward (ops.zig:82-104: single pass sums of x and x^2, eps inside the square root, division) over rows
+// that may be strided in the input (row r starts at in + r * in_stride); output dense, fp32 or fp16.  One warp per
+// row: the row is read once with 128-bit loads and stays in registers between the statistics and the normalisation,
+// reductions are warp shuffles, stores are 128-bit (fp32) / 64-bit (fp16).  HBM-bound: E*4 bytes in, E*(4|2) out.
+constexpr int LN_WARPS = 8, LN_MAXV = 16;  // up to 16 float4 per lane: n_embed <= 2048
 template <bool OUT_F16>
-__global__ void __launch_bounds__(256) ln_rows_kernel(const float *__restrict__ in, size_t in_stride, void *out,
-                                                      const float *__restrict__ g, const float *__restrict__ b, int E,
-                                                      float eps) {
-  __shared__ float red[32];
-  const float *row = in + (size_t)blockIdx.x * in_stride;
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_rows_kernel(const float *__restrict__ in, size_t in_stride, void *out,
+                                                                const float *__restrict__ g, const float *__restrict__ b,
+                                                                int E, float eps, int rows) {
+  const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4 *src = reinterpret_cast<const float4 *>(in + (size_t)row * in_stride);
+  const int nv = E >> 2;
+  float4 v[LN_MAXV];
   float s = 0.0f, ss = 0.0f;
-  for (int i = threadIdx.x; i < E; i += blockDim.x) {
-    const float v = row[i];
-    s += v;
-    ss = fmaf(v, v, ss);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nv) {
+      v[i] = src[c];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      ss = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, fmaf(v[i].w, v[i].w, ss))));
+    }
   }
-  s = block_sum(s, red);
-  ss = block_sum(ss, red);
+  s = warp_sum(s);
+  ss = warp_sum(ss);
   const float n = (float)E, mean = s / n;
   const float std_ = sqrtf(ss / n - mean * mean + eps);
-  for (int i = threadIdx.x; i < E; i += blockDim.x) {
-    const float y = (row[i] - mean) / std_ * g[i] + b[i];
-    if (OUT_F16) reinterpret_cast<__half *>(out)[(size_t)blockIdx.x * E + i] = __float2half_rn(y);
-    else reinterpret_cast<float *>(out)[(size_t)blockIdx.x * E + i] = y;
+  const float4 *g4 = reinterpret_cast<const float4 *>(g), *b4 = reinterpret_cast<const float4 *>(b);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nv) {
+      const float4 gg = __ldg(g4 + c), bb = __ldg(b4 + c);
+      float4 y;
+      y.x = (v[i].x - mean) / std_ * gg.x + bb.x;
+      y.y = (v[i].y - mean) / std_ * gg.y + bb.y;
+      y.z = (v[i].z - mean) / std_ * gg.z + bb.z;
+      y.w = (v[i].w - mean) / std_ * gg.w + bb.w;
+      if (OUT_F16) {
+        __half2 lo = __floats2half2_rn(y.x, y.y), hi = __floats2half2_rn(y.z, y.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t *>(&lo);
+        pk.y = *reinterpret_cast<uint32_t *>(&hi);
+        reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(out) + (size_t)row * E)[c] = pk;
+      } else {
+        reinterpret_cast<float4 *>(reinterpret_cast<float *>(out) + (size_t)row * E)[c] = y;
+      }
+    }
   }
 }
 
@@ -190,7 +217,7 @@ bool build_decode_plans(zg_batch *e) {
     GemmArgs a = base_args(B, 3 * E, E, w.attn_b, e->qkv, 3 * E, 0);
     a.k_cache = e->k_cache + l * e->layer_stride;
     a.v_cache = e->v_cache + l * e->layer_stride;
-    a.E = E; a.rows_per_seq = 1; a.cache_seq_stride = (long long)e->seq_stride; a.pos_dev = e->pos;
+    a.E = E; a.rows_per_seq = 1; a.cache_seq_stride = (long long)e->seq_stride; a.pos_dev = e->pos; a.cache_rows = e->cap;
     if (!gemm_plan(&p.attn, e->dec_mode, e->h, E, w.attn_w, a, 0)) return false;
     a = base_args(B, E, E, w.proj_b, e->x, E, 0);
     a.epi = TC_EPI_RESIDUAL; a.resid = e->x; a.ldr = E;
@@ -217,7 +244,7 @@ bool build_prefill_plans(zg_batch *e, int T) {
     GemmArgs a = base_args(M, 3 * E, E, w.attn_b, e->pqkv, 3 * E, 1);
     a.k_cache = e->k_cache + l * e->layer_stride;
     a.v_cache = e->v_cache + l * e->layer_stride;
-    a.E = E; a.rows_per_seq = T; a.cache_seq_stride = (long long)e->seq_stride; a.pos_dev = nullptr; a.pos_base = 0;
+    a.E = E; a.rows_per_seq = T; a.cache_seq_stride = (long long)e->seq_stride; a.pos_dev = nullptr; a.pos_base = 0; a.cache_rows = e->cap;
     if (!gemm_plan(&p.attn, 0, e->ph, E, w.attn_w16, a, 0)) return false;
     if (!attn_prefill_plan(&e->pre_attn[l], e->pqkv, e->patt, B, T, H, E)) return false;
     a = base_args(M, E, E, w.proj_b, e->px, E, 0);
@@ -249,19 +276,19 @@ void enqueue_step(zg_batch *e, bool from_prompt, int n_inputs, bool with_logits)
   for (size_t l = 0; l < e->layers.size(); ++l) {
     const LayerW &w = e->layers[l];
     const LayerPlans &p = e->dec_plans[l];
-    ln_rows_kernel<false><<<B, 256, 0, s>>>(e->x, E, e->h, w.ln1_g, w.ln1_b, E, 1e-5f);  // main.zig:121-123
+    ln_rows_kernel<false><<<(B + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(e->x, E, e->h, w.ln1_g, w.ln1_b, E, 1e-5f, B);  // main.zig:121-123
     ZG_LAUNCH_CHECK();
     gemm_launch(p.attn);  // c_attn + K/V append at row *pos (ops.zig:143,151-152,156-157)
     attn_decode_batch_launch(e->qkv, 3 * E, e->k_cache + l * e->layer_stride, e->v_cache + l * e->layer_stride,
                              (long long)e->seq_stride, B, H, E, e->att, E, e->pos, 0);  // ops.zig:160-169
     gemm_launch(p.proj);  // c_proj + residual (ops.zig:172, main.zig:136-139)
-    ln_rows_kernel<false><<<B, 256, 0, s>>>(e->x, E, e->h, w.ln2_g, w.ln2_b, E, 1e-5f);  // main.zig:140
+    ln_rows_kernel<false><<<(B + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(e->x, E, e->h, w.ln2_g, w.ln2_b, E, 1e-5f, B);  // main.zig:140
     ZG_LAUNCH_CHECK();
     gemm_launch(p.fc);     // c_fc + GELU (main.zig:79-80)
     gemm_launch(p.proj2);  // c_proj + residual (main.zig:81,142-145)
   }
   if (with_logits) {
-    ln_rows_kernel<false><<<B, 256, 0, s>>>(e->x, E, e->h, e->lnf_g, e->lnf_b, E, 1e-5f);  // main.zig:189
+    ln_rows_kernel<false><<<(B + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(e->x, E, e->h, e->lnf_g, e->lnf_b, E, 1e-5f, B);  // main.zig:189
     ZG_LAUNCH_CHECK();
     gemm_launch(e->dec_head);  // tied lm_head (main.zig:192-194)
     argmax_rows_kernel<<<B, 256, 0, s>>>(e->logits, (size_t)e->Vp, V, e->tok, e->hist, B, e->pos);
@@ -279,18 +306,18 @@ void enqueue_prefill(zg_batch *e, int T, bool with_logits) {
   for (size_t l = 0; l < e->layers.size(); ++l) {
     const LayerW &w = e->layers[l];
     const LayerPlans &p = e->pre_plans[l];
-    ln_rows_kernel<true><<<M, 256, 0, s>>>(e->px, E, e->ph, w.ln1_g, w.ln1_b, E, 1e-5f);
+    ln_rows_kernel<true><<<(M + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(e->px, E, e->ph, w.ln1_g, w.ln1_b, E, 1e-5f, M);
     ZG_LAUNCH_CHECK();
     gemm_launch(p.attn);
     attn_prefill_launch(e->pre_attn[l]);
     gemm_launch(p.proj);
-    ln_rows_kernel<true><<<M, 256, 0, s>>>(e->px, E, e->ph, w.ln2_g, w.ln2_b, E, 1e-5f);
+    ln_rows_kernel<true><<<(M + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(e->px, E, e->ph, w.ln2_g, w.ln2_b, E, 1e-5f, M);
     ZG_LAUNCH_CHECK();
     gemm_launch(p.fc);
     gemm_launch(p.proj2);
   }
   if (with_logits) {  // last position of every prompt only (main.zig:192)
-    ln_rows_kernel<true><<<B, 256, 0, s>>>(e->px + (size_t)(T - 1) * E, (size_t)T * E, e->plast16, e->lnf_g, e->lnf_b, E, 1e-5f);
+    ln_rows_kernel<true><<<(B + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(e->px + (size_t)(T - 1) * E, (size_t)T * E, e->plast16, e->lnf_g, e->lnf_b, E, 1e-5f, B);
     ZG_LAUNCH_CHECK();
     gemm_launch(e->pre_head);
   }
@@ -318,6 +345,10 @@ zg_batch *zg_batch_create(const zg_gpt *gpt, size_t n_seqs, size_t cache_rows, s
   if (!require_ready("zg_batch_create")) return nullptr;
   const zg_config &c = gpt->config;
   const size_t E = c.n_embed, V = c.vocab_size, L = c.n_layer;
+  if (E > 2048 || E % 4 != 0) {
+    set_error(1, "zg_batch_create: n_embed must be a multiple of 4 and <= 2048 (row kernels keep a row in registers)", __FILE__, __LINE__);
+    return nullptr;
+  }
   if (E != c.n_heads * 64 || n_seqs == 0 || cache_rows == 0 || cache_rows > c.context_size || max_prompt > cache_rows) {
     set_error(1, "zg_batch_create: head_dim must be 64, 0 < max_prompt <= cache_rows <= context_size", __FILE__, __LINE__);
     return nullptr;

@@ -22,7 +22,8 @@ constexpr int ROW_BYTES = 128;    // one swizzle row = BLOCK_K elements
 constexpr int A_STAGE = BM * ROW_BYTES;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (2 + EPI_WARPS) * 32;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_BUDGET = 192 * 1024;
+constexpr int STAGING = EPI_WARPS * 4096;  // one swizzled 32-row x 128-byte chunk per epilogue warp
 
 enum { MODE_F16 = 0, MODE_TF32 = 1, MODE_TF32X3 = 2 };
 
@@ -37,7 +38,7 @@ struct Cfg {
   // epilogue warps e and e+4 split the columns; in the 3xTF32 mode warps 6..9 split operands instead
   static constexpr int HALVES = (SPLIT || BN < 64) ? 1 : 2;
   static constexpr int COLS_PER_HALF = BN / HALVES;
-  static constexpr int SMEM = STAGES * STAGE_ALL + 1024 /*alignment slack*/ + 384 /*barriers*/;
+  static constexpr int SMEM = STAGES * STAGE_ALL + STAGING + 1024 /*alignment slack*/ + 384 /*barriers*/;
 };
 
 __device__ __forceinline__ float gelu_fast(float x) {
@@ -48,7 +49,49 @@ __device__ __forceinline__ float gelu_fast(float x) {
 }
 
 // One 32-column chunk of one accumulator row: v[j] is out[row, col0 + j] before the epilogue.
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float (&v)[32], int row, int col0, int pos_now) {
+struct EpiTma {
+  const CUtensorMap *out, *k, *v;
+  uint32_t stage;  // this warp's 4 KB staging chunk (1024-byte aligned)
+  int row0;        // first row of this warp's 32 rows
+};
+
+// Stage one 32-row chunk (this thread's row = `lane`) and hand it to the TMA engine.  fp32: 128-byte rows, 16-byte
+// chunk c of row r lands at c ^ (r % 8) (SWIZZLE_128B); fp16: 64-byte rows, chunk c at c ^ ((r / 2) % 4) (SWIZZLE_64B).
+__device__ __forceinline__ void stage_and_store(const float (&v)[32], bool as_f16, uint32_t stage, int lane,
+                                                const CUtensorMap *tm, int c0, int c1, bool reduce) {
+  if (lane == 0) tc::tma_wait_read0();  // the previous store from this buffer has been read out
+  __syncwarp();
+  if (as_f16) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      __half2 t0 = __floats2half2_rn(v[8 * q], v[8 * q + 1]), t1 = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]),
+              t2 = __floats2half2_rn(v[8 * q + 4], v[8 * q + 5]), t3 = __floats2half2_rn(v[8 * q + 6], v[8 * q + 7]);
+      const uint32_t a = stage + lane * 64 + ((uint32_t)(q ^ ((lane >> 1) & 3)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(*reinterpret_cast<uint32_t *>(&t0)),
+                   "r"(*reinterpret_cast<uint32_t *>(&t1)), "r"(*reinterpret_cast<uint32_t *>(&t2)),
+                   "r"(*reinterpret_cast<uint32_t *>(&t3))
+                   : "memory");
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t a = stage + lane * 128 + ((uint32_t)(q ^ (lane & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(__float_as_uint(v[4 * q])),
+                   "r"(__float_as_uint(v[4 * q + 1])), "r"(__float_as_uint(v[4 * q + 2])), "r"(__float_as_uint(v[4 * q + 3]))
+                   : "memory");
+    }
+  }
+  tc::fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    if (reduce) tc::tma_reduce_add_2d(tm, stage, c0, c1);
+    else tc::tma_store_2d(tm, stage, c0, c1);
+    tc::tma_commit_group();
+  }
+}
+
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float (&v)[32], int row, int col0, int pos_now,
+                                               const EpiTma &t, int lane) {
   const bool full = (col0 + 32 <= g.N);
   if (g.bias) {
     if (full) {
@@ -71,6 +114,23 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float (&v)[32]
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = gelu_ref(v[j]);
     }
+  }
+  if (g.tma_out) {  // TMA clips rows >= M and columns >= N itself
+    stage_and_store(v, g.out_f16 != 0, t.stage, lane, t.out, col0, t.row0, g.tma_reduce != 0);
+    if (g.k_cache && col0 >= g.E) {
+      const int part = col0 / g.E;
+      if (g.tma_kv) {  // 32 consecutive rows of one sequence -> 32 consecutive cache rows
+        const int seq = t.row0 / g.rows_per_seq, tt = pos_now + t.row0 % g.rows_per_seq;
+        stage_and_store(v, false, t.stage, lane, part == 1 ? t.k : t.v, col0 - part * g.E, seq * g.cache_rows + tt, false);
+      } else if (row < g.M) {
+        float *cache = (part == 1) ? g.k_cache : g.v_cache;
+        const int seq = row / g.rows_per_seq, tt = pos_now + row % g.rows_per_seq;
+        float *d = cache + (size_t)seq * g.cache_seq_stride + (size_t)tt * g.E + (col0 - part * g.E);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+    return;
   }
   if (row >= g.M) return;
   if (g.epi == TC_EPI_RESIDUAL) {
@@ -132,7 +192,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float (&v)[32]
 // cores.  Used by the batched decode step, which is HBM-bound, so the 3x MMA count is free.
 template <int MODE, int BN>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ GemmArgs g) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+               const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_k,
+               const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ GemmArgs g) {
   using C = Cfg<MODE, BN>;
   constexpr bool TF32 = MODE != MODE_F16;
   constexpr bool SPLIT = C::SPLIT;
@@ -142,7 +204,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t sA = base, sB = base + C::STAGES * A_STAGE;
   const uint32_t sAlo = base + C::STAGES * C::STAGE, sBlo = sAlo + C::STAGES * A_STAGE;  // SPLIT only
-  const uint32_t bars = base + C::STAGES * C::STAGE_ALL;
+  const uint32_t staging = base + C::STAGES * C::STAGE_ALL;  // 1024-byte aligned: every stage size is a multiple of 1024
+  const uint32_t bars = staging + STAGING;
   const uint32_t full_bar = bars, empty_bar = bars + 8 * C::STAGES, split_bar = bars + 16 * C::STAGES;
   const uint32_t tfull_bar = bars + 24 * C::STAGES, tempty_bar = tfull_bar + 16;
   const uint32_t slot = tempty_bar + 16, abort_flag = slot + 4;
@@ -164,6 +227,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     tc::fence_mbar_init();
     tc::prefetch_tmap(&tm_a);
     tc::prefetch_tmap(&tm_b);
+    if (g.tma_out) tc::prefetch_tmap(&tm_out);
   }
   if (warp == 1) tc::tmem_alloc<C::TMEM_COLS>(slot);
   tc::fence_before_sync();
@@ -179,7 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       uint32_t stage = 0, phase = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < tiles && ok; tile += gridDim.x) {
-        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        const int m_blk = g.n_fastest ? tile / num_n : tile % num_m, n_blk = g.n_fastest ? tile % num_n : tile / num_m;
         for (int kb = 0; kb < num_kb; ++kb) {
           if (!tc::mbar_wait(empty_bar + 8 * stage, phase ^ 1, guard)) { ok = false; break; }
           tc::mbar_expect_tx(full_bar + 8 * stage, C::STAGE);
@@ -259,11 +323,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     if (half < C::HALVES) {
       uint32_t acc = 0, acc_phase = 0;
       const int pos_now = g.pos_base + (g.pos_dev ? *g.pos_dev : 0);
+      EpiTma et{&tm_out, &tm_k, &tm_v, staging + (uint32_t)e * 4096u, 0};
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        const int m_blk = g.n_fastest ? tile / num_n : tile % num_m, n_blk = g.n_fastest ? tile % num_n : tile / num_m;
         if (!tc::mbar_wait(tfull_bar + 8 * acc, acc_phase, guard)) break;
         tc::fence_after_sync();
         const int row = m_blk * BM + quad * 32 + lane;
+        et.row0 = m_blk * BM + quad * 32;
 #pragma unroll 1
         for (int c = 0; c < C::COLS_PER_HALF; c += 32) {
           const int col_in_tile = half * C::COLS_PER_HALF + c;
@@ -275,7 +341,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            epilogue_chunk(g, v, row, col0, pos_now);
+            epilogue_chunk(g, v, row, col0, pos_now, et, lane);
           }
         }
         tc::fence_before_sync();
@@ -283,6 +349,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (lane == 0) tc::mbar_arrive(tempty_bar + 8 * acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (g.tma_out && lane == 0) tc::tma_wait_all0();  // staged chunks fully written before the CTA retires
     }
   }
   tc::fence_before_sync();
@@ -318,7 +385,7 @@ void set_attr() {
 template <int MODE, int BN>
 void launch_one(const GemmPlan &p) {
   set_attr<MODE, BN>();
-  gemm_tc_kernel<MODE, BN><<<p.grid, THREADS, Cfg<MODE, BN>::SMEM, ctx().stream>>>(p.tm_a, p.tm_b, p.args);
+  gemm_tc_kernel<MODE, BN><<<p.grid, THREADS, Cfg<MODE, BN>::SMEM, ctx().stream>>>(p.tm_a, p.tm_b, p.tm_out, p.tm_k, p.tm_v, p.args);
   ZG_LAUNCH_CHECK();
 }
 
@@ -337,6 +404,7 @@ void set_attr_mode() {
 }
 
 unsigned *g_err_word = nullptr;
+bool g_disable_tma_out = false;  // test hook: force the direct-store epilogue
 
 }  // namespace
 
@@ -356,7 +424,7 @@ unsigned *gemm_error_word() {
 }
 
 bool make_tmap_2d(CUtensorMap *out, const void *base, int dtype, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
-                  uint32_t box_rows, uint32_t box_cols) {
+                  uint32_t box_rows, uint32_t box_cols, int swizzle_bytes) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error(1, "cuTensorMapEncodeTiled is not available from this driver", __FILE__, __LINE__);
@@ -371,8 +439,9 @@ bool make_tmap_2d(CUtensorMap *out, const void *base, int dtype, uint64_t rows, 
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estride[2] = {1, 1};
   const CUtensorMapDataType dt = dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   const CUresult r = fn(out, dt, 2, const_cast<void *>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error(1, "cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
     return false;
@@ -408,6 +477,32 @@ bool gemm_plan(GemmPlan *p, int mode, const void *A, size_t lda, const void *W, 
   p->grid = tiles < sms ? tiles : sms;
   if (!make_tmap_2d(&p->tm_a, A, tf32 ? 0 : 1, (uint64_t)args.M, (uint64_t)args.K, lda * es, BM, bk)) return false;
   if (!make_tmap_2d(&p->tm_b, W, tf32 ? 0 : 1, (uint64_t)args.N, (uint64_t)args.K, (uint64_t)args.K * es, bn, bk)) return false;
+  // Epilogue through TMA stores when the output is addressable by a tensor map; a residual that aliases the output
+  // (x += ..., main.zig:136-145) becomes a TMA reduce-add so the kernel never reads it.
+  GemmArgs &g = p->args;
+  // Tile order: concurrently running CTAs should share the smaller operand through L2 and read the larger one from
+  // DRAM exactly once.  A (activations) larger than W -> walk all N tiles of one M tile first.
+  g.n_fastest = ((size_t)g.M >= (size_t)g.N) ? 1 : 0;
+  const int oes = g.out_f16 ? 2 : 4;
+  const bool resid_inplace = g.epi == TC_EPI_RESIDUAL && g.resid == g.out && g.ldr == g.ldo && !g.out_f16;
+  g.tma_out = g.tma_reduce = g.tma_kv = 0;
+  p->tm_out = p->tm_a; p->tm_k = p->tm_a; p->tm_v = p->tm_a;  // valid placeholders
+  if (!g_disable_tma_out && ((uintptr_t)g.out & 15) == 0 && ((size_t)g.ldo * oes) % 16 == 0 &&
+      (g.epi != TC_EPI_RESIDUAL || resid_inplace)) {
+    if (!make_tmap_2d(&p->tm_out, g.out, g.out_f16 ? 1 : 0, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldo * oes, 32, 32,
+                      g.out_f16 ? 64 : 128))
+      return false;
+    g.tma_out = 1;
+    g.tma_reduce = resid_inplace ? 1 : 0;
+    if (g.k_cache && !g.pos_dev && g.rows_per_seq % 32 == 0 && g.pos_base % 32 == 0 && g.cache_rows > 0 &&
+        g.cache_seq_stride == (long long)g.cache_rows * g.E) {
+      const uint64_t n_seq = (uint64_t)((g.M + g.rows_per_seq - 1) / g.rows_per_seq);
+      if (!make_tmap_2d(&p->tm_k, g.k_cache, 0, n_seq * g.cache_rows, (uint64_t)g.E, (uint64_t)g.E * 4, 32, 32) ||
+          !make_tmap_2d(&p->tm_v, g.v_cache, 0, n_seq * g.cache_rows, (uint64_t)g.E, (uint64_t)g.E * 4, 32, 32))
+        return false;
+      g.tma_kv = 1;
+    }
+  }
   return true;
 }
 
@@ -471,6 +566,8 @@ void zg_to_f16(const float *src, void *dst_f16, size_t n) {
       src, reinterpret_cast<__half *>(dst_f16), n);
   ZG_LAUNCH_CHECK();
 }
+
+void zg_tc_set_direct_epilogue(int on) { g_disable_tma_out = on != 0; }  // test hook (per-op parity of both epilogues)
 
 int zg_tc_error(void) {  // watchdog word of the tensor-core kernels; 0 when clean (synchronises)
   if (!require_ready("zg_tc_error")) return 1;

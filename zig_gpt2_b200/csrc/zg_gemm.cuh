@@ -26,11 +26,16 @@ struct GemmArgs {
   const int *pos_dev = nullptr;
   int pos_base = 0;
   unsigned *err = nullptr;  // sticky device error word (watchdog)
+  // set by gemm_plan: the epilogue stages 32x32 chunks in swizzled shared memory and writes them with TMA stores
+  // (full 128-byte lines) instead of one 16-byte store per row; a residual that aliases `out` becomes a TMA reduce-add
+  int tma_out = 0, tma_reduce = 0, tma_kv = 0;
+  int cache_rows = 0;  // rows per sequence in the caches (tma_kv addressing)
+  int n_fastest = 0;   // tile order (set by gemm_plan)
 };
 
 // A prepared launch: tensor maps are encoded once (start-up for the engines, per call for the op-level API).
 struct GemmPlan {
-  CUtensorMap tm_a, tm_b;
+  CUtensorMap tm_a, tm_b, tm_out, tm_k, tm_v;
   GemmArgs args;
   int bn = 256;
   int mode = 1;  // 0 = fp16 operands, 1 = fp32 operands as tf32, 2 = fp32 operands, 3xTF32 error-compensated

@@ -89,6 +89,20 @@ __device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(bar), "l"(pol)
       : "memory");
 }
+// 2-D tiled copy shared -> global (SASS: UTMASTG), bulk-group completion; `reduce_add` makes it out += tile in L2
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(m), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(m), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // generic-proxy writes to shared memory -> visible to the async proxy (UMMA / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -175,7 +189,8 @@ __device__ __forceinline__ bool elect_one() {
 // ---- host side: tensor maps ---------------------------------------------------------------------------
 // 2-D row-major tensor [rows, cols] of `elem_bytes`-wide elements with row pitch `pitch_bytes`; box = [box_rows,
 // box_cols] with box_cols * elem_bytes == 128 (one swizzle row).  dtype: 0 = fp32 (tf32 operand), 1 = fp16.
+// swizzle_bytes: 128 (default) or 64 -- must equal box_cols * elem_bytes.
 bool make_tmap_2d(CUtensorMap *out, const void *base, int dtype, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
-                  uint32_t box_rows, uint32_t box_cols);
+                  uint32_t box_rows, uint32_t box_cols, int swizzle_bytes = 128);
 
 }  // namespace zg

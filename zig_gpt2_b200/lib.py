@@ -66,7 +66,7 @@ SIGNATURES = {
     "zg_timer_begin": (I, []), "zg_timer_end_ms": (C.c_float, []),
     "zg_linear_forward": (V, [C.POINTER(ZgLinear), P, Z, P]),
     "zg_linear_forward_tc": (V, [C.POINTER(ZgLinear), P, Z, P, I, P, I, P, I]),
-    "zg_to_f16": (V, [P, P, Z]), "zg_tc_error": (I, []),
+    "zg_to_f16": (V, [P, P, Z]), "zg_tc_error": (I, []), "zg_tc_set_direct_epilogue": (V, [I]),
     "zg_embedding_forward": (V, [C.POINTER(ZgEmbedding), c_size_p, Z, P]),
     "zg_layer_norm_forward": (V, [C.POINTER(ZgLayerNorm), P, Z]),
     "zg_attention_forward": (V, [C.POINTER(ZgAttention), Z] + [P] * 9),
