@@ -41,10 +41,9 @@ typedef unsigned long long u64;
 constexpr int NTHREADS = NCT + 32;  // + producer warp
 constexpr int MAXSLOTS = 32;
 constexpr int MAX_LAYERS = 64;
-constexpr int ATT_CHUNK = 128;  // KV rows per attention work item before splitting
+constexpr int ATT_CHUNK = 16 * NCW;  // KV rows per attention work item before splitting (one register round)
 constexpr int PROF_MAX = 16384;
-constexpr int LNR = 7;          // LayerNorm elements per thread: E <= 7 * 256
-constexpr int GB = 6;           // flagged pairs a thread keeps in flight while gathering
+constexpr int GB = 7;           // flagged pairs a thread keeps in flight while gathering (7 x 224 threads >= 4 x 768 / 2)
 
 struct LayerDesc {
   const float *ln1_g, *ln1_b, *w_attn, *b_attn, *w_proj, *b_proj, *ln2_g, *ln2_b, *w_fc, *b_fc, *w_proj2, *b_proj2;
@@ -119,9 +118,13 @@ __device__ __forceinline__ u64 ld_word(const u64 *p) {
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+#ifdef ZG_NOWAIT  // timing experiment only: never wait for another CTA (results are garbage)
+__device__ __forceinline__ bool pair_ok(const ulonglong2 &, unsigned) { return true; }
+#else
 __device__ __forceinline__ bool pair_ok(const ulonglong2 &v, unsigned ep) {
   return (unsigned)(v.x >> 32) == ep && (unsigned)(v.y >> 32) == ep;
 }
+#endif
 __device__ __forceinline__ float lo_f(u64 w) { return __uint_as_float((unsigned)w); }
 
 __device__ __forceinline__ bool wd_tripped(const Watchdog &wd) {
@@ -164,7 +167,7 @@ __device__ __noinline__ u64 spin_word(const u64 *p, unsigned ep, Watchdog wd) {
 }
 // gather n floats (n even) whose words must carry epoch `ep` into shared memory; all loads of a thread are
 // issued before the first check, so the common case costs one L2 round trip
-__device__ __noinline__ void gather_flagged(float *dst_smem, const u64 *src, int n, unsigned ep, Watchdog wd) {
+__device__ __forceinline__ void gather_flagged(float *dst_smem, const u64 *src, int n, unsigned ep, Watchdog wd) {
   const int npairs = n >> 1;
 #pragma unroll 1
   for (int base = 0; base < npairs; base += GB * NCT) {
@@ -184,7 +187,6 @@ __device__ __noinline__ void gather_flagged(float *dst_smem, const u64 *src, int
     }
   }
 }
-
 // rows [r0, r1) of an N-row matrix owned by this CTA in a phase; `rot` rotates which CTAs get the remainder rows
 __device__ __forceinline__ void row_range(int cta, int G, int rot, int N, int &r0, int &r1) {
   int c = cta + rot;
@@ -230,64 +232,44 @@ struct Smem {
   float *vec;    // 2 x 4E: activation vector the GEMV phases read, double-buffered: with no CTA-wide sync at the
                  // end of a phase, a fast warp may already be gathering the next vector while a slow one still reads
                  // the current one (a gather into buffer b is two CTA syncs after the last read of buffer b)
-  float *xv;     // E: staging for LayerNorm input
+  float *lnp;    // 2E: LayerNorm gain then shift of the current phase (cp.async at the top of the phase)
   float *part;   // NCW * hd attention partial outputs
   float *red;    // 64
   uint32_t full0, empty0;  // shared addresses of mbarrier arrays
   Watchdog wd;             // sticky global error word + CTA-local tripped flag
 };
 
-// LayerNorm of the E-vector in smem `src` into smem `dst`; reference formula ops.zig:86-101 (single pass E[x],
-// E[x^2]; std = sqrt(var + eps)).  The affine parameters are fetched first so that their latency overlaps the
-// two block reductions.  One copy of this code serves every call site (instruction-cache footprint matters:
-// each phase executes its code exactly once).
-__device__ __noinline__ void layer_norm_to_smem(const float *src_smem, float *dst, const float *__restrict__ g,
-                                                const float *__restrict__ b, int E, float eps, float *red) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float xr[LNR], lg[LNR], lb[LNR];
-  float s = 0.0f, ss = 0.0f;
+// Packed butterfly: every lane holds N partial sums v[0..N); afterwards (N = 2^k <= 16) the lane whose bits
+// 4, 3, ... (k bits, most significant first) spell index i holds the warp total of v[i] in v[0].  N + log2(32/N)
+// shuffles instead of 5 N.
+template <int N>
+__device__ __forceinline__ float packed_reduce(float (&v)[N], int lane) {
+  static_assert(N == 1 || N == 2 || N == 4 || N == 8 || N == 16, "power of two");
+  int off = 16;
 #pragma unroll
-  for (int j = 0; j < LNR; ++j) {
-    const int i = tid + j * NCT;
-    lg[j] = (i < E) ? __ldg(g + i) : 0.0f;
-    lb[j] = (i < E) ? __ldg(b + i) : 0.0f;
-  }
+  for (int n = N; n > 1; n >>= 1, off >>= 1) {
+    const bool hi = (lane & off) != 0;
 #pragma unroll
-  for (int j = 0; j < LNR; ++j) {
-    const int i = tid + j * NCT;
-    xr[j] = (i < E) ? src_smem[i] : 0.0f;
-    s += xr[j];
-    ss = fmaf(xr[j], xr[j], ss);
+    for (int i = 0; i < n / 2; ++i) {
+      const float keep = hi ? v[i + n / 2] : v[i];
+      const float send = hi ? v[i] : v[i + n / 2];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
   }
-  s = warp_sum(s);
-  ss = warp_sum(ss);
-  if (lane == 0) {
-    red[warp] = s;
-    red[NCW + warp] = ss;
-  }
-  consumer_sync();
-  float ts = 0.0f, tss = 0.0f;
-#pragma unroll
-  for (int w = 0; w < NCW; ++w) {
-    ts += red[w];
-    tss += red[NCW + w];
-  }
-  const float n = (float)E;
-  const float mean = ts / n;
-  const float rstd = 1.0f / sqrtf(tss / n - mean * mean + eps);
-#pragma unroll
-  for (int j = 0; j < LNR; ++j) {
-    const int i = tid + j * NCT;
-    if (i < E) dst[i] = (xr[j] - mean) * rstd * lg[j] + lb[j];
-  }
-  consumer_sync();
+  float r = v[0];
+  for (; off > 0; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+  return r;
 }
 
 // Attention work item (head h, split s of S) over cache rows [t0,t1) -- ops.zig:249-307 without the
 // whole-cache transposes: K/V of earlier tokens are read in place from the time-major cache (head stride hd = 64,
 // time stride E); q and the current token's K/V row arrive through the flagged exchange (epoch `ep_in`).
-// One pass with an online softmax per warp, merged across warps in shared memory.
-__device__ __noinline__ void attention_item(const DecodeParams &p, const Smem &sm, int l, int h, int s, int S, int T,
+// A warp owns rows t0 + warp + 8u; a round covers 16 rows per warp (128 per CTA), all of them in registers
+// BEFORE q is waited for (cache rows do not depend on this step), so a context of up to 128 rows per split costs
+// no exposed L2 latency after q lands.  Scores: per-lane partial dot over the lane's 2 dims, packed butterfly
+// (16 shuffles for 16 rows), one exp per lane, p broadcast by shuffle for the PV accumulation.
+constexpr int AR = 16;  // rows per warp per round
+__device__ __forceinline__ void attention_item(const DecodeParams &p, const Smem &sm, int l, int h, int s, int S, int T,
                                             unsigned ep_in, unsigned ep_out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int hd = 64;
@@ -299,12 +281,11 @@ __device__ __noinline__ void attention_item(const DecodeParams &p, const Smem &s
   const float *vh = c_layers[l].v_cache + h * hd;
   float *po = sm.part;  // [NCW][hd] per-warp partial outputs
 
-  // cache rows do not depend on this step: put the first batch in flight before waiting for q
   const bool has_new = (pos >= t0 && pos < t1);
-  float2 kv[4], vv[4];
+  float2 kv[AR], vv[AR];
   const int tfirst = t0 + warp;
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
+  for (int u = 0; u < AR; ++u) {
     const int tt = tfirst + u * NCW;
     kv[u] = make_float2(0.0f, 0.0f);
     vv[u] = make_float2(0.0f, 0.0f);
@@ -326,14 +307,16 @@ __device__ __noinline__ void attention_item(const DecodeParams &p, const Smem &s
   }
   const float2 qv = make_float2(lo_f(qw.x), lo_f(qw.y));
   const float2 knew = make_float2(lo_f(kw.x), lo_f(kw.y)), vnew = make_float2(lo_f(vw.x), lo_f(vw.y));
+  // row index (within a round) whose score this lane holds after the packed butterfly
+  const int myu = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 
-  float mw = -INFINITY, lw = 0.0f;
+  float mw = -INFINITY, lw = 0.0f;  // lw: this lane's share of the softmax denominator (even lanes only)
   float2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll 1
-  for (int t = tfirst; t < t1; t += 4 * NCW) {
+  for (int t = tfirst; t < t1; t += AR * NCW) {
     if (t != tfirst) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < AR; ++u) {
         const int tt = t + u * NCW;
         if (tt < t1 && tt != pos) {
           kv[u] = __ldcg(reinterpret_cast<const float2 *>(kh + (size_t)tt * E) + lane);
@@ -341,37 +324,33 @@ __device__ __noinline__ void attention_item(const DecodeParams &p, const Smem &s
         }
       }
     }
+    float a[AR];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < AR; ++u) {
       if (t + u * NCW == pos) {
         kv[u] = knew;
         vv[u] = vnew;
       }
+      a[u] = fmaf(qv.x, kv[u].x, qv.y * kv[u].y);
     }
-    float a[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) a[u] = fmaf(qv.x, kv[u].x, qv.y * kv[u].y);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) a[u] = warp_sum(a[u]) * scale;
-    float mnew = mw;
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (t + u * NCW < t1) mnew = fmaxf(mnew, a[u]);
+    const float sc = packed_reduce<AR>(a, lane) * scale;  // score of row t + myu * NCW
+    const bool valid = (t + myu * NCW) < t1;
+    const float mnew = fmaxf(mw, warp_max(valid ? sc : -INFINITY));
     const float corr = (mw == -INFINITY) ? 0.0f : expf(mw - mnew);
-    lw *= corr;
+    const float pt = valid ? expf(sc - mnew) : 0.0f;
+    lw = fmaf(lw, corr, (lane & 1) ? 0.0f : pt);
     acc.x *= corr;
     acc.y *= corr;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (t + u * NCW < t1) {
-        const float pt = expf(a[u] - mnew);
-        lw += pt;
-        acc.x = fmaf(pt, vv[u].x, acc.x);
-        acc.y = fmaf(pt, vv[u].y, acc.y);
-      }
+    for (int u = 0; u < AR; ++u) {
+      const int src_lane = ((u >> 3) & 1) * 16 + ((u >> 2) & 1) * 8 + ((u >> 1) & 1) * 4 + (u & 1) * 2;
+      const float pu = __shfl_sync(0xffffffffu, pt, src_lane);
+      acc.x = fmaf(pu, vv[u].x, acc.x);  // rows past t1 carry pu == 0 (their stale vv is finite)
+      acc.y = fmaf(pu, vv[u].y, acc.y);
     }
     mw = mnew;
   }
+  lw = warp_sum(lw);
   po[warp * hd + 2 * lane] = acc.x;
   po[warp * hd + 2 * lane + 1] = acc.y;
   if (lane == 0) {
@@ -441,58 +420,78 @@ struct PhaseEnt {
   const u64 *src;
   int r0, nrows;  // rows of W this CTA owns in this phase
   int K, mode;
-  int n_units, rps;
+  int rb, rps;    // rows per batch (one mbarrier wait), rows per ring unit (4 when K = E, 1 when K = 4E)
 };
 
-// up to 8 ring units at once: issue every try_wait before looking at any result, so their latencies overlap
-__device__ __forceinline__ bool mbar_try8(const uint32_t (&bar)[8], uint32_t parity_bits) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p0, p1, p2, p3, p4, p5, p6, p7;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p0, [%1], %9;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p1, [%2], %10;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p2, [%3], %11;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p3, [%4], %12;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p4, [%5], %13;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p5, [%6], %14;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p6, [%7], %15;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p7, [%8], %16;\n\t"
-      "and.pred p0, p0, p1;\n\tand.pred p2, p2, p3;\n\tand.pred p4, p4, p5;\n\tand.pred p6, p6, p7;\n\t"
-      "and.pred p0, p0, p2;\n\tand.pred p4, p4, p6;\n\tand.pred p0, p0, p4;\n\t"
-      "selp.u32 %0, 1, 0, p0;\n\t}"
-      : "=r"(ok)
-      : "r"(bar[0]), "r"(bar[1]), "r"(bar[2]), "r"(bar[3]), "r"(bar[4]), "r"(bar[5]), "r"(bar[6]), "r"(bar[7]),
-        "r"(parity_bits & 1u), "r"((parity_bits >> 1) & 1u), "r"((parity_bits >> 2) & 1u), "r"((parity_bits >> 3) & 1u),
-        "r"((parity_bits >> 4) & 1u), "r"((parity_bits >> 5) & 1u), "r"((parity_bits >> 6) & 1u), "r"((parity_bits >> 7) & 1u)
-      : "memory");
-  return ok != 0;
+// LayerNorm on a warp's register copy of the E-vector (lane holds float4 number lane + 32 j); reference formula
+// ops.zig:86-101: single pass E[x], E[x^2]; std = sqrt(var + eps); divide.  Every warp computes the statistics
+// redundantly from its own registers: no shared-memory round trip and no CTA sync.
+template <int NJ>
+__device__ __forceinline__ void ln_regs(float4 (&xs)[NJ], const float4 *__restrict__ g4, const float4 *__restrict__ b4,
+                                        int E, int lane) {
+  float s0 = 0.0f, s1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {  // lanes past the vector hold zeros
+    s0 += xs[j].x + xs[j].y;
+    s1 += xs[j].z + xs[j].w;
+    q0 = fmaf(xs[j].x, xs[j].x, q0); q1 = fmaf(xs[j].y, xs[j].y, q1);
+    q0 = fmaf(xs[j].z, xs[j].z, q0); q1 = fmaf(xs[j].w, xs[j].w, q1);
+  }
+  float s = s0 + s1, ss = q0 + q1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  const float nE = (float)E;
+  const float mean = s / nE;
+  const float rstd = 1.0f / sqrtf(ss / nE - mean * mean + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int i4 = lane + 32 * j;
+    if (i4 < (E >> 2)) {  // padding lanes keep their zeros
+      const float4 g = g4[i4], b = b4[i4];
+      xs[j].x = (xs[j].x - mean) * rstd * g.x + b.x;
+      xs[j].y = (xs[j].y - mean) * rstd * g.y + b.y;
+      xs[j].z = (xs[j].z - mean) * rstd * g.z + b.z;
+      xs[j].w = (xs[j].w - mean) * rstd * g.w + b.w;
+    }
+  }
 }
 
+// NJ = float4 per lane that cover one E-vector: E <= 128 NJ.
+template <int NJ>
 __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const DecodeParams p) {
+#ifndef ZG_XREG_MAXNJ
+#define ZG_XREG_MAXNJ 6
+#endif
+  constexpr bool XREG4 = (NJ <= ZG_XREG_MAXNJ);  // the 4E-vector of the mlp c_proj phase also fits in registers
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) u64 mbar_store[2 * MAXSLOTS];
   __shared__ unsigned wd_flag;
   const int G = gridDim.x, cta = blockIdx.x;
-  const int E = p.E, E4 = 4 * p.E;
+  const int E = p.E, E4 = 4 * p.E, Eq = p.E >> 2;  // Eq: float4 per E-vector
   const int nslot = p.nslot, slotf = p.slotf;
   const int L5 = 5 * p.L;
   Smem sm;
   sm.ring = reinterpret_cast<float *>(smem_raw);
   sm.vec = sm.ring + (size_t)nslot * slotf;
-  sm.xv = sm.vec + 2 * E4;
-  sm.part = sm.xv + E;
+  sm.lnp = sm.vec + 2 * E4;
+  sm.part = sm.lnp + 2 * E;
   sm.red = sm.part + NCW * p.hd;
   PhaseEnt *table = reinterpret_cast<PhaseEnt *>(sm.red + 64);
   sm.full0 = smem_u32(mbar_store);
   sm.empty0 = smem_u32(mbar_store + MAXSLOTS);
   sm.wd.err_global = p.err;
   sm.wd.tripped_smem = smem_u32(&wd_flag);
+  const int bsz = min(NCW, nslot >> 1);  // ring units per batch: two batches always fit in the ring, and a
+                                         // batch of K = 4E rows gives every warp at most one row
 
   if (threadIdx.x == 0) {
     wd_flag = 0u;
     for (int i = 0; i < nslot; ++i) {
-      mbar_init(sm.full0 + 8u * i, 1);
-      mbar_init(sm.empty0 + 8u * i, NCW);  // every consumer warp reads its slice of a unit, then releases it
+      mbar_init(sm.full0 + 8u * i, 1);      // one arrive.expect_tx per batch, on the batch's first slot
+      mbar_init(sm.empty0 + 8u * i, NCW);   // every consumer warp releases every slot of a batch
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -502,7 +501,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
     const bool is_head = (g == L5);
     PhaseEnt e;
     e.W = nullptr; e.bias = nullptr; e.ln_g = nullptr; e.ln_b = nullptr; e.src = nullptr;
-    e.r0 = 0; e.nrows = 0; e.K = E; e.mode = -1; e.n_units = 0; e.rps = 4;
+    e.r0 = 0; e.nrows = 0; e.K = E; e.mode = -1; e.rb = 4; e.rps = 4;
     if (is_head || ph != 1) {
       const PhaseDesc d = phase_desc(p, l, ph, is_head, G);
       int r0, r1;
@@ -510,19 +509,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
       e.W = d.W; e.bias = d.bias; e.ln_g = d.ln_g; e.ln_b = d.ln_b; e.src = d.src;
       e.r0 = r0; e.nrows = r1 - r0; e.K = d.K; e.mode = d.mode;
       e.rps = (d.K == E) ? 4 : 1;
-      e.n_units = (e.nrows + e.rps - 1) / e.rps;
+      e.rb = bsz * e.rps;
     }
     table[g] = e;
   }
   __syncthreads();
 
   const int last_step = p.first_step + p.n_steps - 1;
-  const int bsz = nslot < 8 ? nslot : 8;  // ring units handled per GEMV batch (all on distinct slots)
 
   if (threadIdx.x >= NCT) {
     // =============================== producer warp ===============================
     // Streams, in consumption order, the rows this CTA owns in every GEMV phase.  Unit = up to slotf floats
-    // (4 rows of K = E, or 1 row of K = 4E) = one cp.async.bulk into one ring slot.
+    // (4 rows of K = E, or 1 row of K = 4E) = one cp.async.bulk into one ring slot; the units of a batch all
+    // complete on the full-barrier of the batch's first slot, so a consumer waits once per batch.
     const int lane = threadIdx.x - NCT;
     const uint64_t pol = policy_evict_first();
     int slot = 0;
@@ -544,17 +543,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           for (int i = cta; i < nlines; i += G) prefetch_l2(reinterpret_cast<const char *>(arr) + (size_t)i * 128);
         }
         if (lane == 0) {
-          const int rps = e.rps, K = e.K;
+          const int rps = e.rps, K = e.K, rb = e.rb;
           const float *W = e.W + (size_t)e.r0 * K;
 #pragma unroll 1
-          for (int r = 0; r < e.nrows; r += rps) {
-            const int nr = min(rps, e.nrows - r);
-            const uint32_t bytes = (uint32_t)nr * (uint32_t)K * 4u;
-            mbar_wait(sm.empty0 + 8u * slot, parity ^ 1u, sm.wd);
+          for (int b0 = 0; b0 < e.nrows; b0 += rb) {
+            const int nbr = min(rb, e.nrows - b0);
             const uint32_t fb = sm.full0 + 8u * slot;
-            mbar_expect_tx(fb, bytes);
-            bulk_g2s(smem_u32(sm.ring + (size_t)slot * slotf), W + (size_t)r * K, bytes, fb, pol);
-            if (++slot == nslot) { slot = 0; parity ^= 1u; }
+            mbar_wait(sm.empty0 + 8u * slot, parity ^ 1u, sm.wd);  // first slot free => its full barrier is idle too
+            mbar_expect_tx(fb, (uint32_t)nbr * (uint32_t)K * 4u);
+#pragma unroll 1
+            for (int r = 0; r < nbr; r += rps) {
+              const int nr = min(rps, nbr - r);
+              if (r) mbar_wait(sm.empty0 + 8u * slot, parity ^ 1u, sm.wd);
+              bulk_g2s(smem_u32(sm.ring + (size_t)slot * slotf), W + (size_t)(b0 + r) * K, (uint32_t)nr * (uint32_t)K * 4u,
+                       fb, pol);
+              if (++slot == nslot) { slot = 0; parity ^= 1u; }
+            }
           }
         }
         __syncwarp();
@@ -568,13 +572,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
   Prof pf{(p.prof && cta == 0 && tid == 0) ? p.prof : nullptr, 0, (p.dbg & 8) != 0};
   pf.mark(0);
   u64 prev_token = 0;
-  int bslot = 0;               // ring slot / parity of the first unit of the current GEMV batch
-  uint32_t bpar = 0;
+  int bslot = 0;               // ring slot of the first unit of the next batch
+  uint32_t fpar = 0;           // bit s: parity the next wait on full barrier s expects
   unsigned ep = p.epoch_base;  // epoch of the phase being executed; its inputs carry ep - 1
   int vsel = 0;                // which half of sm.vec the current GEMV phase reads
-  // each warp reduces one eighth of every ring unit: floats [warp * slice, (warp + 1) * slice) of the slot
-  const int slice4 = slotf >> 5;           // float4 per warp slice (slotf / 8 / 4)
-  const bool small_slice = slice4 <= 96;   // E <= 768: the warp's x-slice fits 3 float4 per lane (registers)
+  // after packed_reduce<4> lane L holds the total of the warp's row number (L >> 3); lanes 0, 8, 16, 24 finish rows
+  const int eidx = lane >> 3;
+  const bool elane = (lane & 7) == 0;
 
 #pragma unroll 1
   for (int step = p.first_step; step <= last_step; ++step) {
@@ -608,221 +612,157 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
 
       vsel ^= 1;
       float *vec = sm.vec + vsel * E4;
-      const int rps = ent.rps, K = ent.K, mode = ent.mode;
+      const float4 *vec4 = reinterpret_cast<const float4 *>(vec);
+      const int rps = ent.rps, K = ent.K, mode = ent.mode, rb = ent.rb;
+      const bool k4 = (rps == 1);
+      const bool has_ln = ent.ln_g != nullptr;
       // ---------------- phase top: issue every load whose address is known before the activation arrives ----
-      // thread t finishes row r0 + t of the first batch: bias and residual operand.  The residual is the
-      // embedding itself in the first block (main.zig:181-183), otherwise the stream word written two (P5) or
-      // three (P3) phases ago.
+      // lanes 0/8/16/24 of warp w finish rows w, w + NCW, w + 2 NCW, w + 3 NCW of a batch: bias and residual operand.
+      // The residual is the embedding itself in the first block (main.zig:181-183), otherwise the stream word
+      // written two (P5) or three (P3) phases ago.
       const bool resid_from_emb = (g == 2);
-      const unsigned ep_resid = ep - (K == E ? 3u : 2u);
+      const unsigned ep_resid = ep - (k4 ? 2u : 3u);
+      const int iloc = warp + NCW * eidx;  // row of a batch this lane finishes
       float bias_v = 0.0f, resid_v = 0.0f;
       u64 resid_w = 0;
-      const bool own_row = tid < min(ent.nrows, bsz * rps);
-      if (own_row) {
-        const int r = ent.r0 + tid;
+      if (elane && iloc < min(rb, ent.nrows)) {
+        const int r = ent.r0 + iloc;
         if (ent.bias) bias_v = __ldg(ent.bias + r);
         if (mode == M_RESID) {
           if (resid_from_emb) resid_v = __ldg(te + r) + __ldg(pe + r);
           else resid_w = ld_word(p.xres_f + r);
         }
       }
-      float lg[LNR], lb[LNR];
-      if (ent.ln_g != nullptr) {
+      if (has_ln) {  // LayerNorm affine parameters: global -> shared without passing through registers
+#pragma unroll 1
+        for (int i4 = tid; i4 < 2 * Eq; i4 += NCT) {
+          const float *src = (i4 < Eq) ? ent.ln_g + 4 * i4 : ent.ln_b + 4 * (i4 - Eq);
+          cp_async16(smem_u32(sm.lnp + 4 * i4), src);
+        }
+        cp_async_commit();
+      }
+
+      // ---------------- activation vector -> shared memory -> registers ----------------
+      if (g == 0) {  // wte[token] + wpe[pos] (main.zig:179-183), recomputed by every CTA
+#pragma unroll 1
+        for (int i = tid; i < E; i += NCT) vec[i] = __ldg(te + i) + __ldg(pe + i);
+      } else {
+        gather_flagged(vec, ent.src, K, ep - 1, sm.wd);
+      }
+      if (has_ln) cp_async_wait_all();
+      pf.fmark(256 + 5);
+      consumer_sync();
+      float4 xs[NJ];
+      float4 xl[XREG4 ? 4 * NJ : 1];
+      if (!k4) {
 #pragma unroll
-        for (int j = 0; j < LNR; ++j) {
-          lg[j] = lb[j] = 0.0f;
-          if (j * NCT < E) {  // uniform: skips the iterations a narrow model does not need
-            const int i = tid + j * NCT;
-            if (i < E) {
-              lg[j] = __ldg(ent.ln_g + i);
-              lb[j] = __ldg(ent.ln_b + i);
+        for (int j = 0; j < NJ; ++j) {
+          const int i4 = lane + 32 * j;
+          xs[j] = (i4 < Eq) ? vec4[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (has_ln) {
+          ln_regs<NJ>(xs, reinterpret_cast<const float4 *>(sm.lnp), reinterpret_cast<const float4 *>(sm.lnp) + Eq, E, lane);
+          if (is_head && p.write_xout && step == last_step && cta == 0 && warp == 0) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+              const int i4 = lane + 32 * j;
+              if (i4 < Eq) {
+                reinterpret_cast<float4 *>(p.xout)[i4] = xs[j];
+                reinterpret_cast<float4 *>(p.xres_out)[i4] = vec4[i4];
+              }
             }
           }
         }
-      }
-      pf.fmark(256 + 4);
-
-      // ---------------- activation vector -> shared memory ----------------
-      if (ent.ln_g != nullptr) {
-        if (g == 0) {  // wte[token] + wpe[pos] (main.zig:179-183), recomputed by every CTA
-#pragma unroll 1
-          for (int i = tid; i < E; i += NCT) sm.xv[i] = __ldg(te + i) + __ldg(pe + i);
-        } else {
-          gather_flagged(sm.xv, ent.src, E, ep - 1, sm.wd);
-        }
-        pf.fmark(256 + 5);
-        consumer_sync();
-        pf.fmark(256 + 6);
-        // LayerNorm, reference formula ops.zig:86-101 (single pass E[x], E[x^2]; std = sqrt(var + eps))
-        float xr[LNR];
-        float s = 0.0f, ss = 0.0f;
+      } else if (XREG4) {
 #pragma unroll
-        for (int j = 0; j < LNR; ++j) {
-          xr[j] = 0.0f;
-          if (j * NCT < E) {
-            const int i = tid + j * NCT;
-            if (i < E) xr[j] = sm.xv[i];
-            s += xr[j];
-            ss = fmaf(xr[j], xr[j], ss);
-          }
+        for (int j = 0; j < 4 * NJ; ++j) {
+          const int i4 = lane + 32 * j;
+          xl[XREG4 ? j : 0] = (i4 < E) ? vec4[i4] : make_float4(0.f, 0.f, 0.f, 0.f);  // E = float4 per 4E-vector
         }
-        s = warp_sum(s);
-        ss = warp_sum(ss);
-        if (lane == 0) {
-          sm.red[warp] = s;
-          sm.red[NCW + warp] = ss;
-        }
-        consumer_sync();
-        float ts = 0.0f, tss = 0.0f;
-#pragma unroll
-        for (int w = 0; w < NCW; ++w) {
-          ts += sm.red[w];
-          tss += sm.red[NCW + w];
-        }
-        const float nE = (float)E;
-        const float mean = ts / nE;
-        const float rstd = 1.0f / sqrtf(tss / nE - mean * mean + 1e-5f);
-#pragma unroll
-        for (int j = 0; j < LNR; ++j) {
-          if (j * NCT < E) {
-            const int i = tid + j * NCT;
-            if (i < E) vec[i] = (xr[j] - mean) * rstd * lg[j] + lb[j];
-          }
-        }
-        consumer_sync();
-        if (is_head && p.write_xout && step == last_step && cta == 0) {
-#pragma unroll 1
-          for (int i = tid; i < E; i += NCT) {
-            p.xout[i] = vec[i];
-            p.xres_out[i] = sm.xv[i];
-          }
-        }
-      } else {
-        gather_flagged(vec, ent.src, K, ep - 1, sm.wd);
-        pf.fmark(256 + 5);
-        consumer_sync();
       }
       pf.mark(tag + 1);
 
-      // ---------------- GEMV: every warp reduces its eighth of every ring unit ----------------
-      // A unit is slotf floats: 4 rows of K = E (warp w covers half of row w / 2) or one row of K = 4E (warp w
-      // covers an eighth of it).  Either way the warp's activation slice is the same for every unit of the
-      // phase, so it is read once.  Per-unit partial sums stay in registers until the whole batch is consumed;
-      // then 8 interleaved shuffle reductions, one CTA sync, and the first threads finish one row each.
+      // ---------------- GEMV: warp w takes rows w, w + 8, ... of every batch ----------------
       float *kc = nullptr, *vc = nullptr;
       if (mode == M_QKV) {
         kc = c_layers[g / 5].k_cache + (size_t)pos * E;
         vc = c_layers[g / 5].v_cache + (size_t)pos * E;
       }
       float *logits = (is_head && p.store_logits && step == last_step) ? p.logits : nullptr;
-      const int xoff4 = (rps == 4) ? (warp & 1) * slice4 : warp * slice4;  // the warp's slice of the activation vector
-      const int row_in_unit = (rps == 4) ? (warp >> 1) : 0;
-      const float4 *vec4 = reinterpret_cast<const float4 *>(vec) + xoff4;
-      float4 xs0 = make_float4(0.f, 0.f, 0.f, 0.f), xs1 = xs0, xs2 = xs0;
-      if (small_slice) {
-        if (lane < slice4) xs0 = vec4[lane];
-        if (lane + 32 < slice4) xs1 = vec4[lane + 32];
-        if (lane + 64 < slice4) xs2 = vec4[lane + 64];
-      }
-      float best = -INFINITY;  // running argmax of the rows this thread finishes (lm_head only)
+      float best = -INFINITY;  // running argmax of the rows this lane finishes (lm_head only)
       unsigned best_i = 0xffffffffu;
-      const int spr = NCW / rps;  // warp slices per row
 
 #pragma unroll 1
-      for (int ub = 0; ub < ent.n_units; ub += bsz) {
-        const int nb = min(bsz, ent.n_units - ub);
-        uint32_t fbar[8];
-        int slotj[8];
-        uint32_t pbits = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          int sj = bslot + (j < nb ? j : 0);
-          uint32_t pj = bpar;
-          if (sj >= nslot) { sj -= nslot; pj ^= 1u; }
-          slotj[j] = sj;
-          fbar[j] = sm.full0 + 8u * sj;
-          pbits |= pj << j;
-        }
-        if (!mbar_try8(fbar, pbits)) {
-#pragma unroll 1
-          for (int j = 0; j < nb; ++j) mbar_wait(fbar[j], (pbits >> j) & 1u, sm.wd);
-        }
-        pf.fmark(256 + 7);
-        float acc[8];
-        if (small_slice) {
-          // branch-free: every load is unconditional (slots past nb alias slot 0, lanes past the slice are clamped and
-          // meet a zero activation), so the compiler can put all 24 LDS.128 in flight before the first FMA
-          const int i0 = min(lane, slice4 - 1), i1 = min(lane + 32, slice4 - 1), i2 = min(lane + 64, slice4 - 1);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)slotj[j] * slotf) + warp * slice4;
-            const float4 wa = w4[i0], wb = w4[i1], wc = w4[i2];
-            float a0 = wa.x * xs0.x, a1 = wa.y * xs0.y;
-            a0 = fmaf(wa.z, xs0.z, a0); a1 = fmaf(wa.w, xs0.w, a1);
-            a0 = fmaf(wb.x, xs1.x, a0); a1 = fmaf(wb.y, xs1.y, a1); a0 = fmaf(wb.z, xs1.z, a0); a1 = fmaf(wb.w, xs1.w, a1);
-            a0 = fmaf(wc.x, xs2.x, a0); a1 = fmaf(wc.y, xs2.y, a1); a0 = fmaf(wc.z, xs2.z, a0); a1 = fmaf(wc.w, xs2.w, a1);
-            const bool valid = (j < nb) && (row_in_unit < min(rps, ent.nrows - (ub + j) * rps));
-            acc[j] = valid ? a0 + a1 : 0.0f;
+      for (int b0 = 0; b0 < ent.nrows; b0 += rb) {
+        const int nbr = min(rb, ent.nrows - b0);
+        const int nun = k4 ? nbr : ((nbr + 3) >> 2);
+        const bool own = elane && iloc < nbr;
+        const int r = ent.r0 + b0 + iloc;
+        if (b0 > 0 && own) {  // operands of later batches (the first batch's were fetched at the top of the phase)
+          bias_v = ent.bias ? __ldg(ent.bias + r) : 0.0f;
+          if (mode == M_RESID) {
+            if (resid_from_emb) resid_v = __ldg(te + r) + __ldg(pe + r);
+            else resid_w = ld_word(p.xres_f + r);
           }
-        } else {
+        }
+        mbar_wait(sm.full0 + 8u * bslot, (fpar >> bslot) & 1u, sm.wd);
+        fpar ^= 1u << bslot;
+        pf.fmark(256 + 7);
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (!k4) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            acc[j] = 0.0f;
-            if (j < nb && row_in_unit < min(rps, ent.nrows - (ub + j) * rps)) {
-              const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)slotj[j] * slotf) + warp * slice4;
-              float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll 1
-              for (int i = lane; i < slice4; i += 32) {
-                const float4 w = w4[i];
-                const float4 x = vec4[i];
-                a0 = fmaf(w.x, x.x, a0); a1 = fmaf(w.y, x.y, a1); a0 = fmaf(w.z, x.z, a0); a1 = fmaf(w.w, x.w, a1);
+          for (int u = 0; u < 4; ++u) {
+            const int i = warp + NCW * u;
+            if (i < nbr) {  // warp-uniform
+              int sl = bslot + (i >> 2);
+              if (sl >= nslot) sl -= nslot;
+              const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)sl * slotf + (size_t)(i & 3) * E);
+              float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+              for (int j = 0; j < NJ; ++j) {
+                const int i4 = min(lane + 32 * j, Eq - 1);  // clamped lanes meet a zero activation
+                const float4 w = w4[i4];
+                a0 = fmaf(w.x, xs[j].x, a0); a1 = fmaf(w.y, xs[j].y, a1);
+                a2 = fmaf(w.z, xs[j].z, a2); a3 = fmaf(w.w, xs[j].w, a3);
               }
-              acc[j] = a0 + a1;
+              acc[u] = (a0 + a1) + (a2 + a3);
             }
           }
+        } else if (warp < nbr) {
+          int sl = bslot + warp;
+          if (sl >= nslot) sl -= nslot;
+          const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)sl * slotf);
+          float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+          if (XREG4) {
+#pragma unroll
+            for (int j = 0; j < 4 * NJ; ++j) {
+              const int i4 = min(lane + 32 * j, E - 1);
+              const float4 w = w4[i4];
+              const float4 x = xl[XREG4 ? j : 0];
+              a0 = fmaf(w.x, x.x, a0); a1 = fmaf(w.y, x.y, a1); a2 = fmaf(w.z, x.z, a2); a3 = fmaf(w.w, x.w, a3);
+            }
+          } else {
+#pragma unroll 4
+            for (int i4 = lane; i4 < E; i4 += 32) {
+              const float4 w = w4[i4];
+              const float4 x = vec4[i4];
+              a0 = fmaf(w.x, x.x, a0); a1 = fmaf(w.y, x.y, a1); a2 = fmaf(w.z, x.z, a2); a3 = fmaf(w.w, x.w, a3);
+            }
+          }
+          acc[0] = (a0 + a1) + (a2 + a3);
         }
         __syncwarp();
-        if (lane < nb) mbar_arrive(sm.empty0 + 8u * (uint32_t)((bslot + lane >= nslot) ? bslot + lane - nslot : bslot + lane));
-        pf.fmark(256 + 8);
-        // packed reduction of the 8 per-unit sums: exchange halves (xor 16, 8, 4), then two plain steps;
-        // afterwards lane L (L % 4 == 0) holds the warp total of unit ((L >> 4) & 1) * 4 + ((L >> 3) & 1) * 2 + ((L >> 2) & 1)
-        {
-          const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-          float b0 = h16 ? acc[4] : acc[0], b1 = h16 ? acc[5] : acc[1], b2 = h16 ? acc[6] : acc[2], b3 = h16 ? acc[7] : acc[3];
-          const float s0 = h16 ? acc[0] : acc[4], s1 = h16 ? acc[1] : acc[5], s2 = h16 ? acc[2] : acc[6], s3 = h16 ? acc[3] : acc[7];
-          b0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-          b1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-          b2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-          b3 += __shfl_xor_sync(0xffffffffu, s3, 16);
-          float c0 = h8 ? b2 : b0, c1 = h8 ? b3 : b1;
-          const float t0 = h8 ? b0 : b2, t1 = h8 ? b1 : b3;
-          c0 += __shfl_xor_sync(0xffffffffu, t0, 8);
-          c1 += __shfl_xor_sync(0xffffffffu, t1, 8);
-          float d0 = h4 ? c1 : c0;
-          const float u0 = h4 ? c0 : c1;
-          d0 += __shfl_xor_sync(0xffffffffu, u0, 4);
-          d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
-          d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
-          if ((lane & 3) == 0) sm.part[(lane >> 2) * NCW + warp] = d0;
+        if (lane < nun) {
+          int sl = bslot + lane;
+          if (sl >= nslot) sl -= nslot;
+          mbar_arrive(sm.empty0 + 8u * (uint32_t)sl);
         }
-        bslot += nb;
-        if (bslot >= nslot) { bslot -= nslot; bpar ^= 1u; }
-        consumer_sync();
-        pf.fmark(256 + 9);
-        // ---------------- epilogue: thread t finishes row (ub * rps + t) of this phase ----------------
-        const int rr = ub * rps + tid;
-        if (tid < nb * rps && rr < ent.nrows) {
-          const int j = (rps == 4) ? (tid >> 2) : tid, ri = tid - j * rps;
-          const int r = ent.r0 + rr;
-          float v = 0.0f;
-          for (int sgm = 0; sgm < spr; ++sgm) v += sm.part[j * NCW + ri * spr + sgm];
-          if (ub > 0) {  // operands of later batches were not prefetched at the top of the phase
-            bias_v = ent.bias ? __ldg(ent.bias + r) : 0.0f;
-            if (mode == M_RESID) {
-              if (resid_from_emb) resid_v = __ldg(te + r) + __ldg(pe + r);
-              else resid_w = ld_word(p.xres_f + r);
-            }
-          }
+        pf.fmark(256 + 8);
+        float v = packed_reduce<4>(acc, lane);  // lane L: total of the warp's row number L >> 3
+        bslot += nun;
+        if (bslot >= nslot) bslot -= nslot;
+        // ---------------- epilogue: lanes 0/8/16/24 finish one row each ----------------
+        if (own) {
           v += bias_v;
           if (mode == M_QKV) {  // q to the exchange, k/v to cache row `pos` (ops.zig:146-158) and to the exchange
             if (r < E) {
@@ -836,28 +776,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
             }
           } else if (mode == M_RESID) {  // main.zig:136-139,142-145
             if (!resid_from_emb) {
+#ifndef ZG_NOWAIT
               if ((unsigned)(resid_w >> 32) != ep_resid) resid_w = spin_word(p.xres_f + r, ep_resid, sm.wd);
+#endif
               resid_v = lo_f(resid_w);
             }
             st_flag(p.xres_f + r, v + resid_v, ep);
           } else if (mode == M_GELU) {  // main.zig:80
             st_flag(p.f_f + r, gelu_ref(v), ep);
-          } else {  // tied lm_head (main.zig:193) + running argmax; this thread sees increasing r, so strict >
+          } else {  // tied lm_head (main.zig:193) + running argmax; this lane sees increasing r, so strict >
             if (logits) logits[r] = v;
             if (v > best) { best = v; best_i = (unsigned)r; }
           }
         }
-        if (ub + bsz < ent.n_units) consumer_sync();  // sm.part is rewritten by the next batch
       }
       pf.mark(tag + 3);
 
       if (is_head) {
-        // CTA-level argmax (value desc, index asc): the finishing threads all live in warp 0.  One flagged
-        // partial per CTA, then every CTA reduces the G partials itself: the next step's embedding needs the
-        // token everywhere.
-        if (tid < 32) {
+        // argmax (value desc, index asc): warp -> CTA -> one flagged partial per CTA, then every CTA reduces the
+        // G partials itself: the next step's embedding needs the token everywhere.
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+          const unsigned oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+          if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+        }
+        if (lane == 0) {
+          sm.red[44 + warp] = best;
+          sm.red[52 + warp] = __uint_as_float(best_i);
+        }
+        consumer_sync();
+        if (tid < 32) {
+          best = (lane < NCW) ? sm.red[44 + lane] : -INFINITY;
+          best_i = (lane < NCW) ? __float_as_uint(sm.red[52 + lane]) : 0xffffffffu;
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, best, o);
             const unsigned oi = __shfl_xor_sync(0xffffffffu, best_i, o);
             if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
@@ -894,13 +847,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
 
     if (!want_logits && p.write_xout && step == last_step && cta == 0) {
       // GPT.forward(compute_logits = false) still leaves ln_f(x) in state.x (main.zig:189)
-      gather_flagged(sm.xv, p.xres_f, E, ep, sm.wd);
-      consumer_sync();  // also: every warp is past the last GEMV's reads of sm.vec
-      layer_norm_to_smem(sm.xv, sm.vec, p.lnf_g, p.lnf_b, E, 1e-5f, sm.red);
-#pragma unroll 1
-      for (int i = tid; i < E; i += NCT) {
-        p.xout[i] = sm.vec[i];
-        p.xres_out[i] = sm.xv[i];
+      vsel ^= 1;
+      float *vec = sm.vec + vsel * E4;
+      gather_flagged(vec, p.xres_f, E, ep, sm.wd);
+      consumer_sync();
+      if (warp == 0) {
+        float4 xs[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int i4 = lane + 32 * j;
+          xs[j] = (i4 < Eq) ? reinterpret_cast<const float4 *>(vec)[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        ln_regs<NJ>(xs, reinterpret_cast<const float4 *>(p.lnf_g), reinterpret_cast<const float4 *>(p.lnf_b), E, lane);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int i4 = lane + 32 * j;
+          if (i4 < Eq) {
+            reinterpret_cast<float4 *>(p.xout)[i4] = xs[j];
+            reinterpret_cast<float4 *>(p.xres_out)[i4] = reinterpret_cast<const float4 *>(vec)[i4];
+          }
+        }
       }
     }
     if (cta == 0 && tid == 0) {
@@ -911,6 +877,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
   }
   pf.mark(1);
   if (pf.buf) pf.buf[2 * PROF_MAX] = (u64)pf.i;
+}
+
+typedef void (*decode_kernel_t)(const DecodeParams);
+// smallest instantiation whose register copy covers E (E <= 128 NJ)
+static decode_kernel_t decode_kernel_for(int E) {
+  if (E <= 256) return decode_persistent_kernel<2>;
+  if (E <= 768) return decode_persistent_kernel<6>;
+  if (E <= 1024) return decode_persistent_kernel<8>;
+  if (E <= 1280) return decode_persistent_kernel<10>;
+  return decode_persistent_kernel<13>;
 }
 
 }  // namespace zg
@@ -944,7 +920,7 @@ static zg_engine *g_table_owner = nullptr;  // whose layer table currently sits 
 
 static size_t engine_smem_bytes(const zg_config &c, int nslot) {
   const size_t E = c.n_embed, hd = E / c.n_heads;
-  const size_t floats = (size_t)nslot * 4 * E + 2 * 4 * E + E + NCW * hd + 64;
+  const size_t floats = (size_t)nslot * 4 * E + 2 * 4 * E + 2 * E + NCW * hd + 64;
   return floats * sizeof(float) + (5 * c.n_layer + 1) * sizeof(PhaseEnt);
 }
 
@@ -955,8 +931,8 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
   Context &c = ctx();
   const zg_config &cfg = gpt->config;
   const size_t E = cfg.n_embed;
-  if (E % 8 != 0 || cfg.n_heads * 64 != E || E > (size_t)LNR * NCT || cfg.n_layer > (size_t)MAX_LAYERS) {
-    set_error(1, "zg_engine_create: needs head_dim 64, n_embed % 8 == 0, n_embed <= 1792, n_layer <= 64", __FILE__, __LINE__);
+  if (E % 8 != 0 || cfg.n_heads * 64 != E || E > 1664 || cfg.n_layer > (size_t)MAX_LAYERS) {
+    set_error(1, "zg_engine_create: needs head_dim 64, n_embed % 8 == 0, n_embed <= 1664, n_layer <= 64", __FILE__, __LINE__);
     return nullptr;
   }
   zg_engine *e = (zg_engine *)calloc(1, sizeof(zg_engine));
@@ -980,10 +956,10 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
     return nullptr;
   }
   e->smem_bytes = engine_smem_bytes(cfg, nslot);
-  ZG_CUDA(cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)e->smem_bytes));
+  const decode_kernel_t kern = decode_kernel_for((int)E);
+  ZG_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
   int per_sm = 0;
-  ZG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persistent_kernel, NTHREADS, e->smem_bytes));
+  ZG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)kern, NTHREADS, e->smem_bytes));
   if (per_sm < 1) {
     set_error(1, "zg_engine_create: persistent kernel does not fit on an SM", __FILE__, __LINE__);
     free(e);
@@ -1081,8 +1057,8 @@ static void engine_launch(zg_engine *e, DecodeParams &p) {
   p.prof = e->prof_enabled ? e->prof_dev : nullptr;
   e->epoch_count += phases_for(e, p);
   void *args[] = {(void *)&p};
-  ZG_CUDA(cudaLaunchCooperativeKernel((const void *)decode_persistent_kernel, dim3(e->grid), dim3(NTHREADS), args,
-                                      e->smem_bytes, ctx().stream));
+  ZG_CUDA(cudaLaunchCooperativeKernel((const void *)decode_kernel_for((int)e->cfg.n_embed), dim3(e->grid), dim3(NTHREADS),
+                                      args, e->smem_bytes, ctx().stream));
   ctx().launches++;
 }
 

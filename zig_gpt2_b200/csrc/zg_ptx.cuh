@@ -5,7 +5,8 @@
 
 namespace zg {
 
-constexpr int NCW = 8;             // consumer warps of the persistent decode kernel
+constexpr int NCW = 7;             // consumer warps of the persistent decode kernel (+ 1 producer warp = 8 warps:
+                                   // two per scheduler, so a thread may use up to 255 registers)
 constexpr int NCT = NCW * 32;      // consumer threads
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -81,6 +82,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
       ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol)
       : "memory");
 }
+// 16-byte asynchronous global -> shared copy (SASS: LDGSTS), L2 only; completion via commit/wait groups
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
 __device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {

@@ -9,7 +9,7 @@ from typing import Optional
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libzg_b200.so")
+SO = os.environ.get("ZG_B200_LIB") or os.path.join(HERE, "libzg_b200.so")  # override: kernel experiments only
 
 c_float_p = C.POINTER(C.c_float)
 c_size_p = C.POINTER(C.c_size_t)
