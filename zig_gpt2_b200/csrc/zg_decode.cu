@@ -2,26 +2,34 @@
 // (src/main.zig:178-207, 322-342) as ONE persistent cooperative kernel.
 //
 // Design (B200, 148 SMs, HBM-bound: 495 MB of fp32 weights per token at 124M):
-//   * one CTA per SM, 8 consumer warps + 1 producer warp;
+//   * one CTA per SM, 7 consumer warps + 1 producer warp (two warps per scheduler: 255 registers per thread);
 //   * the producer warp streams this CTA's share of every weight matrix, in execution order, through a
 //     shared-memory ring with cp.async.bulk (UBLKCP) + mbarrier complete_tx, L2 evict-first.  The stream does
-//     not depend on activations, so it runs ahead across layer phases and tokens;
-//   * consumers take weight rows from the ring (one warp per ring unit, conflict-free 128-bit LDS), dot them
-//     with the activation vector held in shared memory, reduce with warp shuffles, and apply the fused
-//     epilogue (bias, GELU, residual add, KV-cache append, running argmax);
-//   * five phases per layer
+//     not depend on activations, so it runs ahead across layer phases and tokens.  All units of a batch (up to
+//     28 rows) complete on ONE mbarrier, so a consumer waits once per batch;
+//   * consumers: warp w owns rows w, w + 7, ... of a batch; the activation vector sits in the warp's registers;
+//     a packed butterfly reduces the warp's (up to 4) row sums in 6 shuffles; lanes 0/8/16/24 apply the fused
+//     epilogue.  No shared-memory partials and no CTA sync after the dot;
+//   * phases of a layer (every phase boundary is a cross-SM exchange, the dominant cost at this size)
 //        P1 LN1 + c_attn (+ K/V append)   ops.zig:143-158, main.zig:121-123
 //        P2 attention over the time-major cache (flash-decoding splits when T is long)  ops.zig:160-171
 //        P3 attn c_proj + residual         ops.zig:172, main.zig:136-139
-//        P4 LN2 + c_fc + GELU              main.zig:140, :79-80
-//        P5 mlp c_proj + residual          main.zig:81, :142-145
+//        P4 LN2 + c_fc + GELU + mlp c_proj main.zig:140, :79-81 -- the CTA that owns hidden units [j0, j1)
+//           computes them AND multiplies them into its rows of c_proj^T, so the 4E-wide GELU vector never leaves
+//           the SM; every CTA publishes an E-wide partial result
+//        P5 reduce-scatter: CTA c sums its 5-6 elements over the 148 partial vectors in a fixed order
+//           (deterministic; same-address atomics were measured at ~45 ns each, 7 us per layer), adds the bias and
+//           the residual (main.zig:142-145) and publishes its slice of the new stream; no weights, no GEMV
 //     then ln_f + tied lm_head + argmax (main.zig:189-194);
+//   * FOUR phases per layer carry weights; the fifth is a pure exchange step;
+//   * LayerNorm is folded into the matrix that follows it (start-up copies W' = W diag(g), c1 = W' 1,
+//     c2 = W b + bias): y = rstd (W' x - mean c1) + c2 -- algebraically ops.zig:86-101 followed by ops.zig:21-46.
+//     The statistics (single pass E[x], E[x^2], ops.zig:86-95) are computed by every warp from its register copy
+//     while the dot products are already running; nothing waits for them until the epilogue;
 //   * NO grid barrier and NO memory fence between phases.  Every activation word crosses SMs as one 64-bit
 //     store {epoch : 32 | fp32 bits : 32}; a consumer gathers the vector it needs with 128-bit relaxed loads
 //     and spins until every word carries the epoch of the phase that produces it (the NCCL "LL" idea: the
-//     flag travels inside the datum, so there is nothing to fence).  A measured grid barrier costs ~2.6 us per
-//     phase inside this kernel (0.9 us release fence + 0.7 us poll + 0.5 us acquire fence + skew); the
-//     flagged gather costs one L2 round trip;
+//     flag travels inside the datum, so there is nothing to fence);
 //   * the layer table lives in __constant__ memory, so no phase starts with a dependent global load;
 //   * the token loop of generate() runs inside the kernel; each token is written to device memory and to a
 //     pinned host ring, so the host only waits once per call.
@@ -43,10 +51,14 @@ constexpr int MAXSLOTS = 32;
 constexpr int MAX_LAYERS = 64;
 constexpr int ATT_CHUNK = 16 * NCW;  // KV rows per attention work item before splitting (one register round)
 constexpr int PROF_MAX = 16384;
-constexpr int GB = 7;           // flagged pairs a thread keeps in flight while gathering (7 x 224 threads >= 4 x 768 / 2)
+constexpr int GB = 4;            // flagged pairs a thread keeps in flight while gathering an E-vector (E <= 8 * 224)
+constexpr int MAXNE = 16;        // elements of the stream a CTA owns in the reduce phase: ceil(E / SMs) <= 16
 
 struct LayerDesc {
-  const float *ln1_g, *ln1_b, *w_attn, *b_attn, *w_proj, *b_proj, *ln2_g, *ln2_b, *w_fc, *b_fc, *w_proj2, *b_proj2;
+  const float *wq, *c1q, *c2q;    // LN1-folded c_attn: W diag(g) [3E,E], its row sums, W b + bias
+  const float *w_proj, *b_proj;   // attention c_proj (reference layout)
+  const float *wfc, *c1f, *c2f;   // LN2-folded c_fc [4E,E]
+  const float *w2t, *b_proj2;     // mlp c_proj TRANSPOSED [4E,E]; its bias
   float *k_cache, *v_cache;
 };
 __constant__ LayerDesc c_layers[MAX_LAYERS];
@@ -55,13 +67,15 @@ struct DecodeParams {
   int E, H, hd, L, V, C;
   int nslot, slotf;  // ring geometry: slotf = 4E floats per slot
   const float *wte, *wpe, *lnf_g, *lnf_b;
+  const float *wte_f, *c1h, *c2h;  // ln_f-folded tied lm_head
   // flagged exchange buffers: word = {epoch << 32 | fp32 bits}
-  u64 *xres_f;  // [E]   residual stream
+  u64 *xres_f;  // [E]   residual stream after the attention half (P3 output)
   u64 *q_f;     // [E]   query of the current token
   u64 *kvn_f;   // [2E]  K row then V row of the current token (the cache gets the same values, unflagged)
   u64 *att_f;   // [E]   attention output
-  u64 *f_f;     // [4E]  GELU(c_fc)
   u64 *amax_f;  // [2G]  per-CTA argmax partial: value word, index word
+  u64 *part_f;  // [G][E] partial mlp c_proj outputs, one vector per CTA
+  u64 *xnew_f;  // [E]   residual stream after the MLP half (P5 output)
   unsigned epoch_base;
   float *xres_out;  // [E] state.o: the reference leaves the pre-ln_f stream there (main.zig:116-118)
   float *xout;      // [E] state.x: ln_f output
@@ -83,7 +97,9 @@ struct DecodeParams {
   int dbg;
 };
 
-// optional timeline of CTA 0 / thread 0: (tag, %globaltimer) pairs
+// optional timeline of CTA 0 / thread 0: (tag, %globaltimer) pairs.  Compiled in only with -DZG_PROF (the profiling
+// variant scripts/phase_profile.py loads): even a not-taken mark costs a local-memory load per call site.
+#ifdef ZG_PROF
 struct Prof {
   u64 *buf;
   int i;
@@ -101,7 +117,20 @@ struct Prof {
     }
     ++i;
   }
+  __device__ __forceinline__ void finish() {
+    if (buf) buf[2 * PROF_MAX] = (u64)i;
+  }
 };
+#else
+struct Prof {
+  u64 *buf;
+  int i;
+  bool fine;
+  __device__ __forceinline__ void fmark(int) {}
+  __device__ __forceinline__ void mark(int) {}
+  __device__ __forceinline__ void finish() {}
+};
+#endif
 
 // ---- flag-in-data exchange ------------------------------------------------------------------------
 __device__ __forceinline__ void st_flag(u64 *p, float v, unsigned ep) {
@@ -166,12 +195,13 @@ __device__ __noinline__ u64 spin_word(const u64 *p, unsigned ep, Watchdog wd) {
   return v;
 }
 // gather n floats (n even) whose words must carry epoch `ep` into shared memory; all loads of a thread are
-// issued before the first check, so the common case costs one L2 round trip
+// issued before the first check, so the common case costs one L2 round trip; late pairs are re-polled together
 __device__ __forceinline__ void gather_flagged(float *dst_smem, const u64 *src, int n, unsigned ep, Watchdog wd) {
   const int npairs = n >> 1;
 #pragma unroll 1
   for (int base = 0; base < npairs; base += GB * NCT) {
     ulonglong2 v[GB];
+    bool all_ok = true;
 #pragma unroll
     for (int j = 0; j < GB; ++j) {
       const int idx = base + j * NCT + (int)threadIdx.x;
@@ -180,13 +210,40 @@ __device__ __forceinline__ void gather_flagged(float *dst_smem, const u64 *src, 
 #pragma unroll
     for (int j = 0; j < GB; ++j) {
       const int idx = base + j * NCT + (int)threadIdx.x;
-      if (idx < npairs) {
-        if (!pair_ok(v[j], ep)) v[j] = spin_pair(src + 2 * idx, ep, wd);
-        reinterpret_cast<float2 *>(dst_smem)[idx] = make_float2(lo_f(v[j].x), lo_f(v[j].y));
-      }
+      if (idx < npairs) all_ok = all_ok && pair_ok(v[j], ep);
+    }
+    if (!all_ok && !wd_tripped(wd)) {
+      const long long t0 = clock64();
+      do {
+        all_ok = true;
+#pragma unroll
+        for (int j = 0; j < GB; ++j) {
+          const int idx = base + j * NCT + (int)threadIdx.x;
+          if (idx < npairs && !pair_ok(v[j], ep)) v[j] = ld_pair(src + 2 * idx);
+        }
+#pragma unroll
+        for (int j = 0; j < GB; ++j) {
+          const int idx = base + j * NCT + (int)threadIdx.x;
+          if (idx < npairs) all_ok = all_ok && pair_ok(v[j], ep);
+        }
+        if (!all_ok && clock64() - t0 > WATCHDOG_CYCLES) {
+          wd_trip(wd, 3u);
+          break;
+        }
+      } while (!all_ok);
+    }
+#pragma unroll
+    for (int j = 0; j < GB; ++j) {
+      const int idx = base + j * NCT + (int)threadIdx.x;
+      if (idx < npairs) reinterpret_cast<float2 *>(dst_smem)[idx] = make_float2(lo_f(v[j].x), lo_f(v[j].y));
     }
   }
 }
+__device__ __forceinline__ void st_flag2(u64 *p, float v0, float v1, unsigned ep) {  // two adjacent flagged words
+  const u64 w0 = ((u64)ep << 32) | (u64)__float_as_uint(v0), w1 = ((u64)ep << 32) | (u64)__float_as_uint(v1);
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
+}
+
 // rows [r0, r1) of an N-row matrix owned by this CTA in a phase; `rot` rotates which CTAs get the remainder rows
 __device__ __forceinline__ void row_range(int cta, int G, int rot, int N, int &r0, int &r1) {
   int c = cta + rot;
@@ -196,43 +253,17 @@ __device__ __forceinline__ void row_range(int cta, int G, int rot, int N, int &r
 }
 __device__ __forceinline__ int phase_rot(int layer, int ph, int G) { return ((layer * 5 + ph) * 29) % G; }
 
-// GEMV phases.  ph numbering inside a layer: 0 = c_attn, 1 = attention (no weights), 2 = attn c_proj,
-// 3 = c_fc, 4 = mlp c_proj; the tied lm_head is phase index 5L of a step.
-enum { M_QKV = 0, M_RESID = 1, M_GELU = 2, M_LMHEAD = 3 };
-struct PhaseDesc {
-  const float *W, *bias, *ln_g, *ln_b;
-  const u64 *src;
-  int N, K, mode, rot;
-};
-__device__ __forceinline__ PhaseDesc phase_desc(const DecodeParams &p, int l, int ph, bool is_head, int G) {
-  PhaseDesc d;
-  const int E = p.E;
-  if (is_head) {
-    d = PhaseDesc{p.wte, nullptr, p.lnf_g, p.lnf_b, p.xres_f, p.V, E, M_LMHEAD, 0};
-    return d;
-  }
-  const LayerDesc &ld = c_layers[l];
-  d.rot = phase_rot(l, ph, G);
-  d.K = E;
-  d.ln_g = d.ln_b = nullptr;
-  if (ph == 0) {
-    d.W = ld.w_attn; d.bias = ld.b_attn; d.ln_g = ld.ln1_g; d.ln_b = ld.ln1_b; d.src = p.xres_f; d.N = 3 * E; d.mode = M_QKV;
-  } else if (ph == 2) {
-    d.W = ld.w_proj; d.bias = ld.b_proj; d.src = p.att_f; d.N = E; d.mode = M_RESID;
-  } else if (ph == 3) {
-    d.W = ld.w_fc; d.bias = ld.b_fc; d.ln_g = ld.ln2_g; d.ln_b = ld.ln2_b; d.src = p.xres_f; d.N = 4 * E; d.mode = M_GELU;
-  } else {
-    d.W = ld.w_proj2; d.bias = ld.b_proj2; d.src = p.f_f; d.N = E; d.K = 4 * E; d.mode = M_RESID;
-  }
-  return d;
-}
+// Phases of a layer: 0 = LN1 + c_attn, 1 = attention (no weights), 2 = attn c_proj + residual,
+// 3 = LN2 + c_fc + GELU + mlp c_proj (partial sums), 4 = reduce-scatter of the partial sums (no weights); the tied
+// lm_head is phase index 5L of a step.
+enum { M_REDUCE = -2, M_ATTN = -1, M_QKV = 0, M_RESID = 1, M_MLP = 2, M_LMHEAD = 3 };
 
 struct Smem {
   float *ring;   // nslot * slotf
-  float *vec;    // 2 x 4E: activation vector the GEMV phases read, double-buffered: with no CTA-wide sync at the
-                 // end of a phase, a fast warp may already be gathering the next vector while a slow one still reads
-                 // the current one (a gather into buffer b is two CTA syncs after the last read of buffer b)
-  float *lnp;    // 2E: LayerNorm gain then shift of the current phase (cp.async at the top of the phase)
+  float *vec;    // 2 x E: activation vector of the current GEMV phase, double-buffered: the previous phase's vector
+                 // stays readable (residual operands), and with no CTA-wide sync at the end of a phase a fast warp
+                 // may already be gathering the next vector while a slow one still reads the current one
+  float *fbuf;   // 64: GELU outputs of the hidden units this CTA owns
   float *part;   // NCW * hd attention partial outputs
   float *red;    // 64
   uint32_t full0, empty0;  // shared addresses of mbarrier arrays
@@ -264,15 +295,16 @@ __device__ __forceinline__ float packed_reduce(float (&v)[N], int lane) {
 // Attention work item (head h, split s of S) over cache rows [t0,t1) -- ops.zig:249-307 without the
 // whole-cache transposes: K/V of earlier tokens are read in place from the time-major cache (head stride hd = 64,
 // time stride E); q and the current token's K/V row arrive through the flagged exchange (epoch `ep_in`).
-// A warp owns rows t0 + warp + 8u; a round covers 16 rows per warp (128 per CTA), all of them in registers
-// BEFORE q is waited for (cache rows do not depend on this step), so a context of up to 128 rows per split costs
-// no exposed L2 latency after q lands.  Scores: per-lane partial dot over the lane's 2 dims, packed butterfly
-// (16 shuffles for 16 rows), one exp per lane, p broadcast by shuffle for the PV accumulation.
-constexpr int AR = 16;  // rows per warp per round
+// A warp owns rows t0 + warp + NCW u; a round covers AR rows per warp, all of them in registers BEFORE q is
+// waited for (cache rows do not depend on this step), so a split that fits one round costs no exposed L2 latency
+// after q lands.  Scores: per-lane partial dot over the lane's 2 dims, packed butterfly (AR + 5 - log2 AR shuffles
+// for AR rows), one exp per lane, p broadcast by shuffle for the PV accumulation.
+template <int AR>
 __device__ __forceinline__ void attention_item(const DecodeParams &p, const Smem &sm, int l, int h, int s, int S, int T,
-                                            unsigned ep_in, unsigned ep_out) {
+                                               unsigned ep_in, unsigned ep_out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int hd = 64;
+  constexpr int LG = AR == 16 ? 4 : AR == 8 ? 3 : 2;  // log2 AR
   const int E = p.E, pos = T - 1;
   const int chunk = (T + S - 1) / S;
   const int t0 = s * chunk, t1 = min(T, t0 + chunk);
@@ -307,10 +339,11 @@ __device__ __forceinline__ void attention_item(const DecodeParams &p, const Smem
   }
   const float2 qv = make_float2(lo_f(qw.x), lo_f(qw.y));
   const float2 knew = make_float2(lo_f(kw.x), lo_f(kw.y)), vnew = make_float2(lo_f(vw.x), lo_f(vw.y));
-  // row index (within a round) whose score this lane holds after the packed butterfly
-  const int myu = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+  // row index (within a round) whose score this lane holds after the packed butterfly: the top LG lane bits
+  const int myu = lane >> (5 - LG);
+  const bool first_copy = (lane & ((1 << (5 - LG)) - 1)) == 0;  // one lane per row feeds the softmax denominator
 
-  float mw = -INFINITY, lw = 0.0f;  // lw: this lane's share of the softmax denominator (even lanes only)
+  float mw = -INFINITY, lw = 0.0f;
   float2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll 1
   for (int t = tfirst; t < t1; t += AR * NCW) {
@@ -338,13 +371,12 @@ __device__ __forceinline__ void attention_item(const DecodeParams &p, const Smem
     const float mnew = fmaxf(mw, warp_max(valid ? sc : -INFINITY));
     const float corr = (mw == -INFINITY) ? 0.0f : expf(mw - mnew);
     const float pt = valid ? expf(sc - mnew) : 0.0f;
-    lw = fmaf(lw, corr, (lane & 1) ? 0.0f : pt);
+    lw = fmaf(lw, corr, first_copy ? pt : 0.0f);
     acc.x *= corr;
     acc.y *= corr;
 #pragma unroll
     for (int u = 0; u < AR; ++u) {
-      const int src_lane = ((u >> 3) & 1) * 16 + ((u >> 2) & 1) * 8 + ((u >> 1) & 1) * 4 + (u & 1) * 2;
-      const float pu = __shfl_sync(0xffffffffu, pt, src_lane);
+      const float pu = __shfl_sync(0xffffffffu, pt, u << (5 - LG));
       acc.x = fmaf(pu, vv[u].x, acc.x);  // rows past t1 carry pu == 0 (their stale vv is finite)
       acc.y = fmaf(pu, vv[u].y, acc.y);
     }
@@ -416,22 +448,22 @@ __device__ __forceinline__ bool step_needs_logits(const DecodeParams &p, int ste
 // shared memory, so that the top of a phase is a handful of LDS instead of integer divisions and branches
 // (each phase executes its code exactly once: every instruction on its critical path is latency).
 struct PhaseEnt {
-  const float *W, *bias, *ln_g, *ln_b;
-  const u64 *src;
-  int r0, nrows;  // rows of W this CTA owns in this phase
-  int K, mode;
-  int rb, rps;    // rows per batch (one mbarrier wait), rows per ring unit (4 when K = E, 1 when K = 4E)
+  const float *W;     // rows of the (folded) matrix, K = E
+  const float *W2;    // M_MLP: rows of c_proj^T for the same hidden units
+  const float *bias;  // c2 (folded phases) or the plain bias
+  const float *c1;    // row sums of the folded matrix; null when no LayerNorm precedes
+  const u64 *src;     // flagged input vector
+  int r0, nrows;      // rows this CTA owns
+  int mode;
 };
 
-// LayerNorm on a warp's register copy of the E-vector (lane holds float4 number lane + 32 j); reference formula
-// ops.zig:86-101: single pass E[x], E[x^2]; std = sqrt(var + eps); divide.  Every warp computes the statistics
-// redundantly from its own registers: no shared-memory round trip and no CTA sync.
+// mean and 1/std of a warp's register copy of the E-vector (lane holds float4 number lane + 32 j, zeros past the
+// end); reference formula ops.zig:86-95: single pass E[x], E[x^2]; std = sqrt(var + eps)
 template <int NJ>
-__device__ __forceinline__ void ln_regs(float4 (&xs)[NJ], const float4 *__restrict__ g4, const float4 *__restrict__ b4,
-                                        int E, int lane) {
+__device__ __forceinline__ void ln_stats(const float4 (&xs)[NJ], int E, float &mean, float &rstd) {
   float s0 = 0.0f, s1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) {  // lanes past the vector hold zeros
+  for (int j = 0; j < NJ; ++j) {
     s0 += xs[j].x + xs[j].y;
     s1 += xs[j].z + xs[j].w;
     q0 = fmaf(xs[j].x, xs[j].x, q0); q1 = fmaf(xs[j].y, xs[j].y, q1);
@@ -444,17 +476,25 @@ __device__ __forceinline__ void ln_regs(float4 (&xs)[NJ], const float4 *__restri
     ss += __shfl_xor_sync(0xffffffffu, ss, o);
   }
   const float nE = (float)E;
-  const float mean = s / nE;
-  const float rstd = 1.0f / sqrtf(ss / nE - mean * mean + 1e-5f);
+  mean = s / nE;
+  rstd = 1.0f / sqrtf(ss / nE - mean * mean + 1e-5f);
+}
+// explicit LayerNorm output (only needed when GPT.forward has to leave ln_f(x) in state.x, main.zig:189)
+template <int NJ>
+__device__ __forceinline__ void ln_write(const float4 (&xs)[NJ], float mean, float rstd, const float *__restrict__ g,
+                                         const float *__restrict__ b, float *out, float *raw_out, int E, int lane) {
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
     const int i4 = lane + 32 * j;
-    if (i4 < (E >> 2)) {  // padding lanes keep their zeros
-      const float4 g = g4[i4], b = b4[i4];
-      xs[j].x = (xs[j].x - mean) * rstd * g.x + b.x;
-      xs[j].y = (xs[j].y - mean) * rstd * g.y + b.y;
-      xs[j].z = (xs[j].z - mean) * rstd * g.z + b.z;
-      xs[j].w = (xs[j].w - mean) * rstd * g.w + b.w;
+    if (i4 < (E >> 2)) {
+      const float4 gg = __ldg(reinterpret_cast<const float4 *>(g) + i4), bb = __ldg(reinterpret_cast<const float4 *>(b) + i4);
+      float4 y;
+      y.x = (xs[j].x - mean) * rstd * gg.x + bb.x;
+      y.y = (xs[j].y - mean) * rstd * gg.y + bb.y;
+      y.z = (xs[j].z - mean) * rstd * gg.z + bb.z;
+      y.w = (xs[j].w - mean) * rstd * gg.w + bb.w;
+      reinterpret_cast<float4 *>(out)[i4] = y;
+      reinterpret_cast<float4 *>(raw_out)[i4] = xs[j];
     }
   }
 }
@@ -462,30 +502,26 @@ __device__ __forceinline__ void ln_regs(float4 (&xs)[NJ], const float4 *__restri
 // NJ = float4 per lane that cover one E-vector: E <= 128 NJ.
 template <int NJ>
 __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const DecodeParams p) {
-#ifndef ZG_XREG_MAXNJ
-#define ZG_XREG_MAXNJ 6
-#endif
-  constexpr bool XREG4 = (NJ <= ZG_XREG_MAXNJ);  // the 4E-vector of the mlp c_proj phase also fits in registers
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) u64 mbar_store[2 * MAXSLOTS];
   __shared__ unsigned wd_flag;
   const int G = gridDim.x, cta = blockIdx.x;
-  const int E = p.E, E4 = 4 * p.E, Eq = p.E >> 2;  // Eq: float4 per E-vector
+  const int E = p.E, Eq = p.E >> 2;  // Eq: float4 per E-vector
   const int nslot = p.nslot, slotf = p.slotf;
   const int L5 = 5 * p.L;
   Smem sm;
   sm.ring = reinterpret_cast<float *>(smem_raw);
   sm.vec = sm.ring + (size_t)nslot * slotf;
-  sm.lnp = sm.vec + 2 * E4;
-  sm.part = sm.lnp + 2 * E;
+  sm.fbuf = sm.vec + 2 * E;
+  sm.part = sm.fbuf + 64;
   sm.red = sm.part + NCW * p.hd;
   PhaseEnt *table = reinterpret_cast<PhaseEnt *>(sm.red + 64);
   sm.full0 = smem_u32(mbar_store);
   sm.empty0 = smem_u32(mbar_store + MAXSLOTS);
   sm.wd.err_global = p.err;
   sm.wd.tripped_smem = smem_u32(&wd_flag);
-  const int bsz = min(NCW, nslot >> 1);  // ring units per batch: two batches always fit in the ring, and a
-                                         // batch of K = 4E rows gives every warp at most one row
+  const int bsz = min(NCW, nslot >> 1);  // ring units per batch: two batches always fit in the ring
+  const int rb = 4 * bsz;                // rows per batch: at most 4 per warp
 
   if (threadIdx.x == 0) {
     wd_flag = 0u;
@@ -498,18 +534,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
   }
   for (int g = threadIdx.x; g <= L5; g += blockDim.x) {
     const int l = g / 5, ph = g - 5 * l;
-    const bool is_head = (g == L5);
     PhaseEnt e;
-    e.W = nullptr; e.bias = nullptr; e.ln_g = nullptr; e.ln_b = nullptr; e.src = nullptr;
-    e.r0 = 0; e.nrows = 0; e.K = E; e.mode = -1; e.rb = 4; e.rps = 4;
-    if (is_head || ph != 1) {
-      const PhaseDesc d = phase_desc(p, l, ph, is_head, G);
+    e.W = e.W2 = e.bias = e.c1 = nullptr;
+    e.src = nullptr;
+    e.r0 = 0; e.nrows = 0; e.mode = M_ATTN;
+    int N = 0, rot = 0;
+    if (g == L5) {
+      e.W = p.wte_f; e.bias = p.c2h; e.c1 = p.c1h; e.src = p.xnew_f; e.mode = M_LMHEAD; N = p.V;
+    } else {
+      const LayerDesc &ld = c_layers[l];
+      rot = phase_rot(l, ph, G);
+      if (ph == 0) {
+        e.W = ld.wq; e.bias = ld.c2q; e.c1 = ld.c1q; e.src = p.xnew_f; e.mode = M_QKV; N = 3 * E;
+      } else if (ph == 2) {
+        e.W = ld.w_proj; e.bias = ld.b_proj; e.src = p.att_f; e.mode = M_RESID; N = E;
+      } else if (ph == 3) {
+        e.W = ld.wfc; e.W2 = ld.w2t; e.bias = ld.c2f; e.c1 = ld.c1f; e.src = p.xres_f; e.mode = M_MLP; N = 4 * E;
+      } else if (ph == 4) {
+        e.bias = ld.b_proj2; e.mode = M_REDUCE; N = E;
+      }
+    }
+    if (e.mode != M_ATTN) {
       int r0, r1;
-      row_range(cta, G, d.rot, d.N, r0, r1);
-      e.W = d.W; e.bias = d.bias; e.ln_g = d.ln_g; e.ln_b = d.ln_b; e.src = d.src;
-      e.r0 = r0; e.nrows = r1 - r0; e.K = d.K; e.mode = d.mode;
-      e.rps = (d.K == E) ? 4 : 1;
-      e.rb = bsz * e.rps;
+      row_range(cta, G, rot, N, r0, r1);
+      e.r0 = r0; e.nrows = r1 - r0;
     }
     table[g] = e;
   }
@@ -519,9 +567,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
 
   if (threadIdx.x >= NCT) {
     // =============================== producer warp ===============================
-    // Streams, in consumption order, the rows this CTA owns in every GEMV phase.  Unit = up to slotf floats
-    // (4 rows of K = E, or 1 row of K = 4E) = one cp.async.bulk into one ring slot; the units of a batch all
-    // complete on the full-barrier of the batch's first slot, so a consumer waits once per batch.
+    // Streams, in consumption order, the rows this CTA owns in every GEMV phase.  Unit = up to 4 rows of E floats
+    // = one cp.async.bulk into one ring slot; the units of a batch all complete on the full-barrier of the batch's
+    // first slot, so a consumer waits once per batch.  The MLP phase streams its c_fc rows, then its c_proj^T rows.
     const int lane = threadIdx.x - NCT;
     const uint64_t pol = policy_evict_first();
     int slot = 0;
@@ -533,31 +581,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
       for (int g = 0; g < nph; ++g) {
         const PhaseEnt &e = table[g];
         if (e.mode < 0) continue;
-        if (e.mode == M_QKV && lane < 8) {
-          // pull the layer's small vectors (LayerNorm affine + biases, 13E floats) into L2 ahead of the consumers
+        if (e.mode == M_QKV && lane < 6) {
+          // pull the layer's small vectors (folded constants + biases, 10E floats) into L2 ahead of the consumers
           const LayerDesc &ld = c_layers[g / 5];
-          const float *arr = lane == 0 ? ld.ln1_g : lane == 1 ? ld.ln1_b : lane == 2 ? ld.b_attn : lane == 3 ? ld.b_proj
-                           : lane == 4 ? ld.ln2_g : lane == 5 ? ld.ln2_b : lane == 6 ? ld.b_fc : ld.b_proj2;
-          const int len = lane == 2 ? 3 * E : lane == 6 ? E4 : E;
+          const float *arr = lane == 0 ? ld.c1q : lane == 1 ? ld.c2q : lane == 2 ? ld.b_proj : lane == 3 ? ld.c1f
+                           : lane == 4 ? ld.c2f : ld.b_proj2;
+          const int len = lane < 2 ? 3 * E : (lane == 3 || lane == 4) ? 4 * E : E;
           const int nlines = (len * 4 + 127) / 128;
           for (int i = cta; i < nlines; i += G) prefetch_l2(reinterpret_cast<const char *>(arr) + (size_t)i * 128);
         }
         if (lane == 0) {
-          const int rps = e.rps, K = e.K, rb = e.rb;
-          const float *W = e.W + (size_t)e.r0 * K;
 #pragma unroll 1
-          for (int b0 = 0; b0 < e.nrows; b0 += rb) {
-            const int nbr = min(rb, e.nrows - b0);
-            const uint32_t fb = sm.full0 + 8u * slot;
-            mbar_wait(sm.empty0 + 8u * slot, parity ^ 1u, sm.wd);  // first slot free => its full barrier is idle too
-            mbar_expect_tx(fb, (uint32_t)nbr * (uint32_t)K * 4u);
+          for (int pass = 0; pass < 2; ++pass) {
+            const float *Wm = pass ? e.W2 : e.W;
+            if (Wm == nullptr) break;
+            const float *W = Wm + (size_t)e.r0 * E;
 #pragma unroll 1
-            for (int r = 0; r < nbr; r += rps) {
-              const int nr = min(rps, nbr - r);
-              if (r) mbar_wait(sm.empty0 + 8u * slot, parity ^ 1u, sm.wd);
-              bulk_g2s(smem_u32(sm.ring + (size_t)slot * slotf), W + (size_t)(b0 + r) * K, (uint32_t)nr * (uint32_t)K * 4u,
-                       fb, pol);
-              if (++slot == nslot) { slot = 0; parity ^= 1u; }
+            for (int b0 = 0; b0 < e.nrows; b0 += rb) {
+              const int nbr = min(rb, e.nrows - b0);
+              const uint32_t fb = sm.full0 + 8u * slot;
+              mbar_wait(sm.empty0 + 8u * slot, parity ^ 1u, sm.wd);  // first slot free => its full barrier is idle too
+              mbar_expect_tx(fb, (uint32_t)nbr * (uint32_t)E * 4u);
+#pragma unroll 1
+              for (int r = 0; r < nbr; r += 4) {
+                const int nr = min(4, nbr - r);
+                if (r) mbar_wait(sm.empty0 + 8u * slot, parity ^ 1u, sm.wd);
+                bulk_g2s(smem_u32(sm.ring + (size_t)slot * slotf), W + (size_t)(b0 + r) * E, (uint32_t)nr * (uint32_t)E * 4u,
+                         fb, pol);
+                if (++slot == nslot) { slot = 0; parity ^= 1u; }
+              }
             }
           }
         }
@@ -579,6 +631,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
   // after packed_reduce<4> lane L holds the total of the warp's row number (L >> 3); lanes 0, 8, 16, 24 finish rows
   const int eidx = lane >> 3;
   const bool elane = (lane & 7) == 0;
+  const int iloc = warp + NCW * eidx;  // row of a batch this lane finishes
 
 #pragma unroll 1
   for (int step = p.first_step; step <= last_step; ++step) {
@@ -591,7 +644,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
     const bool want_logits = step_needs_logits(p, step);
     const int nph = L5 + (want_logits ? 1 : 0);
     u64 out_tok = tok;
-    const float *te = p.wte + (size_t)tok * E, *pe = p.wpe + (size_t)pos * E;  // main.zig:179-180
 
 #pragma unroll 1
     for (int g = 0; g < nph; ++g) {
@@ -599,90 +651,123 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
       const PhaseEnt ent = table[g];
       const bool is_head = (g == L5);
       const int tag = is_head ? 96 : 16 * (g % 5 + 1);
+      const int mode = ent.mode;
 
-      if (ent.mode < 0) {
+      if (mode == M_ATTN) {
         // ---------------- attention over the cache (ops.zig:160-171) ----------------
         int S = (T + ATT_CHUNK - 1) / ATT_CHUNK;
         const int smax = G / p.H;
         if (S > smax) S = smax;
-        if (cta < p.H * S) attention_item(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep);
+        if (cta < p.H * S) {
+          const int chunk = (T + S - 1) / S;
+          if (chunk <= 4 * NCW) attention_item<4>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep);
+          else if (chunk <= 8 * NCW) attention_item<8>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep);
+          else attention_item<16>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep);
+        }
+        pf.mark(tag + 3);
+        continue;
+      }
+      if (mode == M_REDUCE) {
+        // ---------------- residual 2, main.zig:142-145: x = x_mid + bias + sum over the G partial c_proj outputs,
+        // for the elements [r0, r0 + ne) this CTA owns.  8 (or 16) adjacent threads read the ne adjacent words of
+        // one source CTA (coalesced), a thread sums its element over its sources in a fixed order, then two
+        // shuffles and a fixed-order sum over the warps: deterministic. ----------------
+        const int ne = ent.nrows;
+        const float *xmid = sm.vec + vsel * E;  // the MLP phase's input vector: this CTA's copy of the stream
+        float bmine = 0.0f;
+        if (tid < ne) bmine = __ldg(ent.bias + ent.r0 + tid);
+        const int lg = ne <= 8 ? 3 : 4;              // log2(threads per source)
+        const int k = tid & ((1 << lg) - 1);         // element this thread sums
+        const int sgrp = tid >> lg, nsg = NCT >> lg;  // sources advance by nsg per pass
+        constexpr int NP = 12;                        // passes: ceil(G / (NCT / 16)) <= 12 for G <= 168
+        const u64 *col = p.part_f + ent.r0 + k;
+        u64 w[NP];
+        bool all_ok = true;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          const int src = sgrp + q * nsg;
+          w[q] = (u64)(ep - 1) << 32;  // a source that does not exist contributes +0.0f
+          if (src < G && k < ne) w[q] = ld_word(col + (size_t)src * E);
+        }
+#ifndef ZG_NOWAIT
+#pragma unroll
+        for (int q = 0; q < NP; ++q) all_ok = all_ok && (unsigned)(w[q] >> 32) == ep - 1;
+        if (!all_ok && !wd_tripped(sm.wd)) {
+          const long long t0 = clock64();
+          do {
+            all_ok = true;
+#pragma unroll
+            for (int q = 0; q < NP; ++q)
+              if ((unsigned)(w[q] >> 32) != ep - 1) w[q] = ld_word(col + (size_t)(sgrp + q * nsg) * E);
+#pragma unroll
+            for (int q = 0; q < NP; ++q) all_ok = all_ok && (unsigned)(w[q] >> 32) == ep - 1;
+            if (!all_ok && clock64() - t0 > WATCHDOG_CYCLES) {
+              wd_trip(sm.wd, 4u);
+              break;
+            }
+          } while (!all_ok);
+        }
+#endif
+        float tot = 0.0f;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) tot += lo_f(w[q]);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 16);
+        if (lg == 3) tot += __shfl_xor_sync(0xffffffffu, tot, 8);
+        if (lane < (1 << lg)) sm.part[lane * 8 + warp] = tot;
+        consumer_sync();
+        if (tid < ne) {
+          float v = 0.0f;
+#pragma unroll
+          for (int w2 = 0; w2 < NCW; ++w2) v += sm.part[tid * 8 + w2];
+          st_flag(p.xnew_f + ent.r0 + tid, xmid[ent.r0 + tid] + bmine + v, ep);
+        }
         pf.mark(tag + 3);
         continue;
       }
 
       vsel ^= 1;
-      float *vec = sm.vec + vsel * E4;
+      float *vec = sm.vec + vsel * E;              // this phase's input vector
+      const float *vprev = sm.vec + (vsel ^ 1) * E;  // the previous GEMV phase's input vector
       const float4 *vec4 = reinterpret_cast<const float4 *>(vec);
-      const int rps = ent.rps, K = ent.K, mode = ent.mode, rb = ent.rb;
-      const bool k4 = (rps == 1);
-      const bool has_ln = ent.ln_g != nullptr;
+      const bool has_ln = ent.c1 != nullptr;
       // ---------------- phase top: issue every load whose address is known before the activation arrives ----
-      // lanes 0/8/16/24 of warp w finish rows w, w + NCW, w + 2 NCW, w + 3 NCW of a batch: bias and residual operand.
-      // The residual is the embedding itself in the first block (main.zig:181-183), otherwise the stream word
-      // written two (P5) or three (P3) phases ago.
-      const bool resid_from_emb = (g == 2);
-      const unsigned ep_resid = ep - (k4 ? 2u : 3u);
-      const int iloc = warp + NCW * eidx;  // row of a batch this lane finishes
-      float bias_v = 0.0f, resid_v = 0.0f;
-      u64 resid_w = 0;
+      // lanes 0/8/16/24 of warp w finish rows w, w + NCW, w + 2 NCW, w + 3 NCW of a batch
+      float bias_v = 0.0f, c1_v = 0.0f;
       if (elane && iloc < min(rb, ent.nrows)) {
         const int r = ent.r0 + iloc;
         if (ent.bias) bias_v = __ldg(ent.bias + r);
-        if (mode == M_RESID) {
-          if (resid_from_emb) resid_v = __ldg(te + r) + __ldg(pe + r);
-          else resid_w = ld_word(p.xres_f + r);
-        }
-      }
-      if (has_ln) {  // LayerNorm affine parameters: global -> shared without passing through registers
-#pragma unroll 1
-        for (int i4 = tid; i4 < 2 * Eq; i4 += NCT) {
-          const float *src = (i4 < Eq) ? ent.ln_g + 4 * i4 : ent.ln_b + 4 * (i4 - Eq);
-          cp_async16(smem_u32(sm.lnp + 4 * i4), src);
-        }
-        cp_async_commit();
+        if (has_ln) c1_v = __ldg(ent.c1 + r);
       }
 
       // ---------------- activation vector -> shared memory -> registers ----------------
       if (g == 0) {  // wte[token] + wpe[pos] (main.zig:179-183), recomputed by every CTA
+        const float4 *te = reinterpret_cast<const float4 *>(p.wte + (size_t)tok * E);
+        const float4 *pe = reinterpret_cast<const float4 *>(p.wpe + (size_t)pos * E);
 #pragma unroll 1
-        for (int i = tid; i < E; i += NCT) vec[i] = __ldg(te + i) + __ldg(pe + i);
+        for (int i4 = tid; i4 < Eq; i4 += NCT) {
+          const float4 a = __ldg(te + i4), b = __ldg(pe + i4);
+          reinterpret_cast<float4 *>(vec)[i4] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        }
       } else {
-        gather_flagged(vec, ent.src, K, ep - 1, sm.wd);
+        gather_flagged(vec, ent.src, E, ep - 1, sm.wd);
       }
-      if (has_ln) cp_async_wait_all();
       pf.fmark(256 + 5);
       consumer_sync();
       float4 xs[NJ];
-      float4 xl[XREG4 ? 4 * NJ : 1];
-      if (!k4) {
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          const int i4 = lane + 32 * j;
-          xs[j] = (i4 < Eq) ? vec4[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (has_ln) {
-          ln_regs<NJ>(xs, reinterpret_cast<const float4 *>(sm.lnp), reinterpret_cast<const float4 *>(sm.lnp) + Eq, E, lane);
-          if (is_head && p.write_xout && step == last_step && cta == 0 && warp == 0) {
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-              const int i4 = lane + 32 * j;
-              if (i4 < Eq) {
-                reinterpret_cast<float4 *>(p.xout)[i4] = xs[j];
-                reinterpret_cast<float4 *>(p.xres_out)[i4] = vec4[i4];
-              }
-            }
-          }
-        }
-      } else if (XREG4) {
-#pragma unroll
-        for (int j = 0; j < 4 * NJ; ++j) {
-          const int i4 = lane + 32 * j;
-          xl[XREG4 ? j : 0] = (i4 < E) ? vec4[i4] : make_float4(0.f, 0.f, 0.f, 0.f);  // E = float4 per 4E-vector
-        }
+      for (int j = 0; j < NJ; ++j) {
+        const int i4 = lane + 32 * j;
+        xs[j] = (i4 < Eq) ? vec4[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float mean = 0.0f, rstd = 1.0f;
+      if (has_ln) {
+        ln_stats<NJ>(xs, E, mean, rstd);
+        if (is_head && p.write_xout && step == last_step && cta == 0 && warp == 0)
+          ln_write<NJ>(xs, mean, rstd, p.lnf_g, p.lnf_b, p.xout, p.xres_out, E, lane);
       }
       pf.mark(tag + 1);
 
-      // ---------------- GEMV: warp w takes rows w, w + 8, ... of every batch ----------------
+      // ---------------- GEMV: warp w takes rows w, w + NCW, ... of every batch ----------------
       float *kc = nullptr, *vc = nullptr;
       if (mode == M_QKV) {
         kc = c_layers[g / 5].k_cache + (size_t)pos * E;
@@ -695,61 +780,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
 #pragma unroll 1
       for (int b0 = 0; b0 < ent.nrows; b0 += rb) {
         const int nbr = min(rb, ent.nrows - b0);
-        const int nun = k4 ? nbr : ((nbr + 3) >> 2);
+        const int nun = (nbr + 3) >> 2;
         const bool own = elane && iloc < nbr;
         const int r = ent.r0 + b0 + iloc;
         if (b0 > 0 && own) {  // operands of later batches (the first batch's were fetched at the top of the phase)
           bias_v = ent.bias ? __ldg(ent.bias + r) : 0.0f;
-          if (mode == M_RESID) {
-            if (resid_from_emb) resid_v = __ldg(te + r) + __ldg(pe + r);
-            else resid_w = ld_word(p.xres_f + r);
-          }
+          if (has_ln) c1_v = __ldg(ent.c1 + r);
         }
         mbar_wait(sm.full0 + 8u * bslot, (fpar >> bslot) & 1u, sm.wd);
         fpar ^= 1u << bslot;
         pf.fmark(256 + 7);
         float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        if (!k4) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = warp + NCW * u;
-            if (i < nbr) {  // warp-uniform
-              int sl = bslot + (i >> 2);
-              if (sl >= nslot) sl -= nslot;
-              const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)sl * slotf + (size_t)(i & 3) * E);
-              float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        for (int u = 0; u < 4; ++u) {
+          const int i = warp + NCW * u;
+          if (i < nbr) {  // warp-uniform
+            int sl = bslot + (i >> 2);
+            if (sl >= nslot) sl -= nslot;
+            const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)sl * slotf + (size_t)(i & 3) * E);
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll
-              for (int j = 0; j < NJ; ++j) {
-                const int i4 = min(lane + 32 * j, Eq - 1);  // clamped lanes meet a zero activation
-                const float4 w = w4[i4];
-                a0 = fmaf(w.x, xs[j].x, a0); a1 = fmaf(w.y, xs[j].y, a1);
-                a2 = fmaf(w.z, xs[j].z, a2); a3 = fmaf(w.w, xs[j].w, a3);
-              }
-              acc[u] = (a0 + a1) + (a2 + a3);
-            }
-          }
-        } else if (warp < nbr) {
-          int sl = bslot + warp;
-          if (sl >= nslot) sl -= nslot;
-          const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)sl * slotf);
-          float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-          if (XREG4) {
-#pragma unroll
-            for (int j = 0; j < 4 * NJ; ++j) {
-              const int i4 = min(lane + 32 * j, E - 1);
+            for (int j = 0; j < NJ; ++j) {
+              const int i4 = min(lane + 32 * j, Eq - 1);  // clamped lanes meet a zero activation
               const float4 w = w4[i4];
-              const float4 x = xl[XREG4 ? j : 0];
-              a0 = fmaf(w.x, x.x, a0); a1 = fmaf(w.y, x.y, a1); a2 = fmaf(w.z, x.z, a2); a3 = fmaf(w.w, x.w, a3);
+              a0 = fmaf(w.x, xs[j].x, a0); a1 = fmaf(w.y, xs[j].y, a1);
+              a2 = fmaf(w.z, xs[j].z, a2); a3 = fmaf(w.w, xs[j].w, a3);
             }
-          } else {
-#pragma unroll 4
-            for (int i4 = lane; i4 < E; i4 += 32) {
-              const float4 w = w4[i4];
-              const float4 x = vec4[i4];
-              a0 = fmaf(w.x, x.x, a0); a1 = fmaf(w.y, x.y, a1); a2 = fmaf(w.z, x.z, a2); a3 = fmaf(w.w, x.w, a3);
-            }
+            acc[u] = (a0 + a1) + (a2 + a3);
           }
-          acc[0] = (a0 + a1) + (a2 + a3);
         }
         __syncwarp();
         if (lane < nun) {
@@ -763,7 +821,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         if (bslot >= nslot) bslot -= nslot;
         // ---------------- epilogue: lanes 0/8/16/24 finish one row each ----------------
         if (own) {
-          v += bias_v;
+          // folded LayerNorm: W (g (x - mean) rstd + b) + bias = rstd (W' x - mean c1) + c2
+          v = has_ln ? fmaf(rstd, v - mean * c1_v, bias_v) : v + bias_v;
           if (mode == M_QKV) {  // q to the exchange, k/v to cache row `pos` (ops.zig:146-158) and to the exchange
             if (r < E) {
               st_flag(p.q_f + r, v, ep);
@@ -774,19 +833,69 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
               vc[r - 2 * E] = v;
               st_flag(p.kvn_f + E + (r - 2 * E), v, ep);
             }
-          } else if (mode == M_RESID) {  // main.zig:136-139,142-145
-            if (!resid_from_emb) {
-#ifndef ZG_NOWAIT
-              if ((unsigned)(resid_w >> 32) != ep_resid) resid_w = spin_word(p.xres_f + r, ep_resid, sm.wd);
-#endif
-              resid_v = lo_f(resid_w);
-            }
-            st_flag(p.xres_f + r, v + resid_v, ep);
-          } else if (mode == M_GELU) {  // main.zig:80
-            st_flag(p.f_f + r, gelu_ref(v), ep);
+          } else if (mode == M_RESID) {  // residual 1, main.zig:136-139: the stream is this CTA's own copy
+            st_flag(p.xres_f + r, v + vprev[r], ep);
+          } else if (mode == M_MLP) {  // main.zig:79-80
+            sm.fbuf[b0 + iloc] = gelu_ref(v);
           } else {  // tied lm_head (main.zig:193) + running argmax; this lane sees increasing r, so strict >
             if (logits) logits[r] = v;
             if (v > best) { best = v; best_i = (unsigned)r; }
+          }
+        }
+      }
+
+      if (mode == M_MLP) {
+        // ---------------- mlp c_proj, main.zig:81: out += f_j * c_proj^T[j, :] over the hidden units j this CTA owns.
+        // Thread t accumulates output float4 t (and t + 224 for wide models); no shuffles. ----------------
+        consumer_sync();  // fbuf complete
+        float4 o4[2];
+        o4[0] = o4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int b0 = 0; b0 < ent.nrows; b0 += rb) {
+          const int nbr = min(rb, ent.nrows - b0);
+          const int nun = (nbr + 3) >> 2;
+          mbar_wait(sm.full0 + 8u * bslot, (fpar >> bslot) & 1u, sm.wd);
+          fpar ^= 1u << bslot;
+#pragma unroll
+          for (int q = 0; q < NCW; ++q) {  // ring unit q of the batch: 4 hidden units (bsz <= NCW units per batch)
+            if (q < nun) {
+              int sl = bslot + q;
+              if (sl >= nslot) sl -= nslot;
+              const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)sl * slotf);
+              const float4 f4 = *reinterpret_cast<const float4 *>(sm.fbuf + b0 + 4 * q);  // zero past the last unit
+              const float fj[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (4 * q + j < nbr) {  // warp-uniform: rows past the batch are stale ring contents
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) {
+                    const int i4 = tid + k * NCT;
+                    if (i4 < Eq) {
+                      const float4 w = w4[j * Eq + i4];
+                      o4[k].x = fmaf(fj[j], w.x, o4[k].x); o4[k].y = fmaf(fj[j], w.y, o4[k].y);
+                      o4[k].z = fmaf(fj[j], w.z, o4[k].z); o4[k].w = fmaf(fj[j], w.w, o4[k].w);
+                    }
+                  }
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (lane < nun) {
+            int sl = bslot + lane;
+            if (sl >= nslot) sl -= nslot;
+            mbar_arrive(sm.empty0 + 8u * (uint32_t)sl);
+          }
+          bslot += nun;
+          if (bslot >= nslot) bslot -= nslot;
+        }
+        u64 *mine = p.part_f + (size_t)cta * E;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int i4 = tid + k * NCT;
+          if (i4 < Eq) {
+            st_flag2(mine + 4 * i4, o4[k].x, o4[k].y, ep);
+            st_flag2(mine + 4 * i4 + 2, o4[k].z, o4[k].w, ep);
           }
         }
       }
@@ -848,8 +957,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
     if (!want_logits && p.write_xout && step == last_step && cta == 0) {
       // GPT.forward(compute_logits = false) still leaves ln_f(x) in state.x (main.zig:189)
       vsel ^= 1;
-      float *vec = sm.vec + vsel * E4;
-      gather_flagged(vec, p.xres_f, E, ep, sm.wd);
+      float *vec = sm.vec + vsel * E;
+      gather_flagged(vec, p.xnew_f, E, ep, sm.wd);
       consumer_sync();
       if (warp == 0) {
         float4 xs[NJ];
@@ -858,15 +967,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           const int i4 = lane + 32 * j;
           xs[j] = (i4 < Eq) ? reinterpret_cast<const float4 *>(vec)[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        ln_regs<NJ>(xs, reinterpret_cast<const float4 *>(p.lnf_g), reinterpret_cast<const float4 *>(p.lnf_b), E, lane);
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          const int i4 = lane + 32 * j;
-          if (i4 < Eq) {
-            reinterpret_cast<float4 *>(p.xout)[i4] = xs[j];
-            reinterpret_cast<float4 *>(p.xres_out)[i4] = reinterpret_cast<const float4 *>(vec)[i4];
-          }
-        }
+        float mean, rstd;
+        ln_stats<NJ>(xs, E, mean, rstd);
+        ln_write<NJ>(xs, mean, rstd, p.lnf_g, p.lnf_b, p.xout, p.xres_out, E, lane);
       }
     }
     if (cta == 0 && tid == 0) {
@@ -876,7 +979,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
     prev_token = out_tok;
   }
   pf.mark(1);
-  if (pf.buf) pf.buf[2 * PROF_MAX] = (u64)pf.i;
+  pf.finish();
 }
 
 typedef void (*decode_kernel_t)(const DecodeParams);
@@ -887,6 +990,44 @@ static decode_kernel_t decode_kernel_for(int E) {
   if (E <= 1024) return decode_persistent_kernel<8>;
   if (E <= 1280) return decode_persistent_kernel<10>;
   return decode_persistent_kernel<13>;
+}
+
+// ---- start-up kernels: derived weight copies --------------------------------------------------------
+// W'[r,k] = W[r,k] g[k];  c1[r] = sum_k W'[r,k];  c2[r] = sum_k W[r,k] b[k] + bias[r].  One warp per row.
+__global__ void fold_ln_kernel(const float *__restrict__ W, const float *__restrict__ g, const float *__restrict__ b,
+                               const float *__restrict__ bias, size_t N, int K, float *__restrict__ Wf,
+                               float *__restrict__ c1, float *__restrict__ c2) {
+  const size_t r = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= N) return;
+  float s1 = 0.0f, s2 = 0.0f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[r * K + k];
+    const float wf = w * g[k];
+    Wf[r * K + k] = wf;
+    s1 += wf;
+    s2 = fmaf(w, b[k], s2);
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) {
+    c1[r] = s1;
+    c2[r] = s2 + (bias ? bias[r] : 0.0f);
+  }
+}
+// out[k, n] = in[n, k] for in [N, K]
+__global__ void transpose_weight_kernel(const float *__restrict__ in, int N, int K, float *__restrict__ out) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    tile[i][threadIdx.x] = (n < N && k < K) ? in[(size_t)n * K + k] : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    if (k < K && n < N) out[(size_t)k * N + n] = tile[threadIdx.x][i];
+  }
 }
 
 }  // namespace zg
@@ -902,6 +1043,7 @@ struct zg_engine {
   DecodeParams base;
   LayerDesc *layers_host;
   u64 *exchange_dev;  // all flagged buffers, one allocation
+  float *derived_dev;  // folded / transposed weight copies, one allocation
   u64 *prompt_dev;
   u64 *tokens_dev;
   u64 *tokens_host;  // pinned, mapped
@@ -920,7 +1062,7 @@ static zg_engine *g_table_owner = nullptr;  // whose layer table currently sits 
 
 static size_t engine_smem_bytes(const zg_config &c, int nslot) {
   const size_t E = c.n_embed, hd = E / c.n_heads;
-  const size_t floats = (size_t)nslot * 4 * E + 2 * 4 * E + 2 * E + NCW * hd + 64;
+  const size_t floats = (size_t)nslot * 4 * E + 2 * E + 64 + NCW * hd + 64;
   return floats * sizeof(float) + (5 * c.n_layer + 1) * sizeof(PhaseEnt);
 }
 
@@ -930,8 +1072,8 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
   if (!require_ready("zg_engine_create")) return nullptr;
   Context &c = ctx();
   const zg_config &cfg = gpt->config;
-  const size_t E = cfg.n_embed;
-  if (E % 8 != 0 || cfg.n_heads * 64 != E || E > 1664 || cfg.n_layer > (size_t)MAX_LAYERS) {
+  const size_t E = cfg.n_embed, V = cfg.vocab_size, L = cfg.n_layer;
+  if (E % 8 != 0 || cfg.n_heads * 64 != E || E > 1664 || L > (size_t)MAX_LAYERS) {
     set_error(1, "zg_engine_create: needs head_dim 64, n_embed % 8 == 0, n_embed <= 1664, n_layer <= 64", __FILE__, __LINE__);
     return nullptr;
   }
@@ -940,8 +1082,10 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
   e->cfg = cfg;
   e->state = *state;
   e->grid = c.sm_count;
-  if ((size_t)e->grid < cfg.n_heads) {
-    set_error(1, "zg_engine_create: fewer SMs than attention heads", __FILE__, __LINE__);
+  if ((size_t)e->grid < cfg.n_heads || e->grid > 168 || (size_t)e->grid > E ||
+      (4 * E + (size_t)e->grid - 1) / (size_t)e->grid > 64 || (E + (size_t)e->grid - 1) / (size_t)e->grid > MAXNE) {
+    set_error(1, "zg_engine_create: needs n_heads <= SMs <= min(168, n_embed), <= 64 hidden units and <= 16 stream elements per SM",
+              __FILE__, __LINE__);
     free(e);
     return nullptr;
   }
@@ -966,19 +1110,46 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
     return nullptr;
   }
 
-  // layer table (start-up only); copied into __constant__ memory before a launch when another engine owned it
-  e->layers_host = (LayerDesc *)calloc(MAX_LAYERS, sizeof(LayerDesc));
-  for (size_t l = 0; l < cfg.n_layer; ++l) {
-    const zg_block &b = gpt->h[l];
-    e->layers_host[l] = LayerDesc{b.ln_1.weight, b.ln_1.bias, b.attn.c_attn.weight, b.attn.c_attn.bias,
-                                  b.attn.c_proj.weight, b.attn.c_proj.bias, b.ln_2.weight, b.ln_2.bias,
-                                  b.mlp.c_fc.weight, b.mlp.c_fc.bias, b.mlp.c_proj.weight, b.mlp.c_proj.bias,
-                                  b.k_cache, b.v_cache};
+  // derived weight copies (start-up only): LayerNorm-folded c_attn / c_fc / lm_head, transposed mlp c_proj
+  const size_t per_layer = 3 * E * E + 2 * 3 * E + 4 * E * E + 2 * 4 * E + 4 * E * E;
+  const size_t n_derived = L * per_layer + V * E + 2 * V;
+  e->derived_dev = (float *)zg_alloc(n_derived * sizeof(float));
+  if (!e->derived_dev) {
+    free(e);
+    return nullptr;
   }
+  e->layers_host = (LayerDesc *)calloc(MAX_LAYERS, sizeof(LayerDesc));
+  float *d = e->derived_dev;
+  const int fold_threads = 256, rows_per_block = fold_threads / 32;
+  for (size_t l = 0; l < L; ++l) {
+    const zg_block &b = gpt->h[l];
+    float *wq = d; d += 3 * E * E;
+    float *c1q = d; d += 3 * E;
+    float *c2q = d; d += 3 * E;
+    float *wfc = d; d += 4 * E * E;
+    float *c1f = d; d += 4 * E;
+    float *c2f = d; d += 4 * E;
+    float *w2t = d; d += 4 * E * E;
+    fold_ln_kernel<<<(unsigned)((3 * E + rows_per_block - 1) / rows_per_block), fold_threads, 0, c.stream>>>(
+        b.attn.c_attn.weight, b.ln_1.weight, b.ln_1.bias, b.attn.c_attn.bias, 3 * E, (int)E, wq, c1q, c2q);
+    fold_ln_kernel<<<(unsigned)((4 * E + rows_per_block - 1) / rows_per_block), fold_threads, 0, c.stream>>>(
+        b.mlp.c_fc.weight, b.ln_2.weight, b.ln_2.bias, b.mlp.c_fc.bias, 4 * E, (int)E, wfc, c1f, c2f);
+    // mlp c_proj.weight is [E, 4E] (out, in); the fused MLP phase walks it by hidden unit: [4E, E]
+    transpose_weight_kernel<<<dim3((unsigned)((4 * E + 31) / 32), (unsigned)((E + 31) / 32)), dim3(32, 8), 0, c.stream>>>(
+        b.mlp.c_proj.weight, (int)E, (int)(4 * E), w2t);
+    e->layers_host[l] = LayerDesc{wq, c1q, c2q, b.attn.c_proj.weight, b.attn.c_proj.bias, wfc, c1f, c2f, w2t,
+                                  b.mlp.c_proj.bias, b.k_cache, b.v_cache};
+  }
+  float *wte_f = d; d += V * E;
+  float *c1h = d; d += V;
+  float *c2h = d; d += V;
+  fold_ln_kernel<<<(unsigned)((V + rows_per_block - 1) / rows_per_block), fold_threads, 0, c.stream>>>(
+      gpt->lm_head.weight, gpt->ln_f.weight, gpt->ln_f.bias, gpt->lm_head.bias, V, (int)E, wte_f, c1h, c2h);
+  ZG_CUDA(cudaGetLastError());
 
   const size_t C = cfg.context_size, hd = 64;
   const int smax = e->grid / (int)cfg.n_heads > 0 ? e->grid / (int)cfg.n_heads : 1;
-  const size_t n_exchange = E + E + 2 * E + E + 4 * E + 2 * (size_t)e->grid;
+  const size_t n_exchange = E + E + 2 * E + E + 2 * (size_t)e->grid + E + (size_t)e->grid * E;
   e->exchange_dev = (u64 *)zg_alloc(n_exchange * 8);
   e->prompt_dev = (u64 *)zg_alloc(C * 8);
   e->tokens_dev = (u64 *)zg_alloc(C * 8);
@@ -1003,16 +1174,18 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
 
   DecodeParams &p = e->base;
   memset(&p, 0, sizeof(p));
-  p.E = (int)E; p.H = (int)cfg.n_heads; p.hd = (int)hd; p.L = (int)cfg.n_layer; p.V = (int)cfg.vocab_size; p.C = (int)C;
+  p.E = (int)E; p.H = (int)cfg.n_heads; p.hd = (int)hd; p.L = (int)L; p.V = (int)V; p.C = (int)C;
   p.nslot = nslot; p.slotf = 4 * (int)E;
   p.wte = gpt->wte.weight; p.wpe = gpt->wpe.weight; p.lnf_g = gpt->ln_f.weight; p.lnf_b = gpt->ln_f.bias;
+  p.wte_f = wte_f; p.c1h = c1h; p.c2h = c2h;
   u64 *x = e->exchange_dev;
   p.xres_f = x; x += E;
   p.q_f = x; x += E;
   p.kvn_f = x; x += 2 * E;
   p.att_f = x; x += E;
-  p.f_f = x; x += 4 * E;
-  p.amax_f = x;
+  p.amax_f = x; x += 2 * (size_t)e->grid;
+  p.xnew_f = x; x += E;
+  p.part_f = x;
   p.xres_out = state->o; p.xout = state->x; p.logits = state->logits;
   p.att_part = att_part; p.head_count = head_count; p.err = e->err_dev;
   p.tokens = e->tokens_dev; p.tokens_host = e->tokens_host_devptr; p.last_token = e->last_token_dev;
@@ -1025,7 +1198,7 @@ void zg_engine_destroy(zg_engine *e) {
   if (!e) return;
   zg_sync();
   if (g_table_owner == e) g_table_owner = nullptr;
-  zg_free(e->exchange_dev); zg_free(e->prompt_dev); zg_free(e->tokens_dev); zg_free(e->last_token_dev);
+  zg_free(e->exchange_dev); zg_free(e->derived_dev); zg_free(e->prompt_dev); zg_free(e->tokens_dev); zg_free(e->last_token_dev);
   zg_free(e->prof_dev); zg_free(e->err_dev); zg_free(e->base.att_part); zg_free(e->base.head_count);
   cudaFreeHost(e->tokens_host);
   free(e->layers_host);
