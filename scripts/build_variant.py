@@ -21,8 +21,9 @@ for f in sorted(os.listdir(CSRC)):
         continue
     src = os.path.join(CSRC, f)
     if f == "zg_decode.cu":
+        src = os.environ.get("ZG_DECODE_SRC", src)  # e.g. an older revision, for A/B runs on the same box
         obj = os.path.join(VDIR, f"zg_decode_{name}.o")
-        subprocess.check_call(BASE + flags + ["-c", src, "-o", obj])
+        subprocess.check_call(BASE + flags + ["-I", CSRC, "-c", src, "-o", obj])
     else:
         obj = os.path.join(VDIR, f[:-3] + ".o")
         if not os.path.exists(obj) or os.path.getmtime(obj) < os.path.getmtime(src):
