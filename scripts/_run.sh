@@ -1,1 +1,2 @@
-for i in 1 2; do for v in prev cur branchy noredux both; do echo "== $v"; ZG_B200_LIB=$PWD/zig_gpt2_b200/variants/libzg_$v.so timeout 300 python scripts/phase_profile.py 124M 32 2>&1 | grep -E "unprofiled"; done; done
+timeout 900 python -m pytest tests/test_gpu_model.py -m gpu -x -q 2>&1 | tail -4
+timeout 300 python scripts/pos_sweep.py 124M

@@ -50,6 +50,7 @@ constexpr int NTHREADS = NCT + 32;  // + producer warp
 constexpr int MAXSLOTS = 32;
 constexpr int MAX_LAYERS = 64;
 constexpr int ATT_CHUNK = 16 * NCW;  // KV rows per attention work item before splitting (one register round)
+constexpr int ATT_SMAX = 8;          // at most this many splits per head; longer contexts loop over rounds inside a split
 constexpr int PROF_MAX = 16384;
 constexpr int GB = 4;            // flagged pairs a thread keeps in flight while gathering an E-vector (E <= 8 * 224)
 constexpr int MAXNE = 16;        // elements of the stream a CTA owns in the reduce phase: ceil(E / SMs) <= 16
@@ -80,8 +81,7 @@ struct DecodeParams {
   float *xres_out;  // [E] state.o: the reference leaves the pre-ln_f stream there (main.zig:116-118)
   float *xout;      // [E] state.x: ln_f output
   float *logits;    // [V] state.logits
-  float *att_part;       // [H][S][hd+2] flash-decoding partials
-  unsigned *head_count;  // [H] arrival counters for the split combine
+  u64 *attp_f;           // [H][ATT_SMAX][hd+2] flagged flash-decoding partials: m, l, unnormalised o[hd]
   unsigned *err;         // sticky watchdog word
   const u64 *prompt;     // device, n_prompt entries; null => `single_token` is the forced token
   u64 single_token;
@@ -410,39 +410,77 @@ __device__ __forceinline__ void attention_item(const DecodeParams &p, const Smem
     }
     if (S == 1) {
       st_flag(p.att_f + h * hd + tid, o / lsum, ep_out);
-    } else {  // flash-decoding partial: (m, l, unnormalised o)
-      float *mine = p.att_part + ((size_t)h * S + s) * (hd + 2);
-      mine[2 + tid] = o;
-      if (tid == 0) {
-        mine[0] = m;
-        mine[1] = lsum;
+    } else {  // flash-decoding partial (m, l, unnormalised o): every consumer of the attention output combines the S
+              // partials of a head itself while it gathers the vector (gather_att_partials), so no fence, no counter
+      u64 *mine = p.attp_f + ((size_t)h * ATT_SMAX + s) * (hd + 2);
+      st_flag(mine + 2 + tid, o, ep_out);
+      if (tid == 0) st_flag2(mine, m, lsum, ep_out);
+    }
+  }
+}
+
+// Attention output vector from S (2..ATT_SMAX) flagged partials per head: out = sum_s o_s e^(m_s - M) / sum_s l_s e^(m_s - M).
+// A thread handles pairs of adjacent elements; all 2 S loads of a pair are in flight before the first check.
+__device__ __forceinline__ void gather_att_partials(float *dst_smem, const u64 *attp, int E, int S, unsigned ep, Watchdog wd) {
+  constexpr int hd = 64;
+  const int npairs = E >> 1;
+#pragma unroll 1
+  for (int idx = (int)threadIdx.x; idx < npairs; idx += NCT) {
+    const int h = idx >> 5, d = (idx & 31) * 2;
+    const u64 *base = attp + (size_t)h * ATT_SMAX * (hd + 2);
+    ulonglong2 ml[ATT_SMAX], ov[ATT_SMAX];
+    bool all_ok = true;
+#pragma unroll
+    for (int q = 0; q < ATT_SMAX; ++q) {
+      if (q < S) {
+        ml[q] = ld_pair(base + (size_t)q * (hd + 2));
+        ov[q] = ld_pair(base + (size_t)q * (hd + 2) + 2 + d);
       }
     }
-  }
-  if (S == 1) return;
-  // the last split of this head to arrive combines the partials (the only fence left: long contexts only)
-  __threadfence();
-  consumer_sync();
-  if (tid == 0) {
-    const unsigned old = atomicAdd(p.head_count + h, 1u);
-    const bool last = (old == (unsigned)(S - 1));
-    if (last) p.head_count[h] = 0u;
-    sm.red[32] = last ? 1.0f : 0.0f;
-    __threadfence();
-  }
-  consumer_sync();
-  if (sm.red[32] != 0.0f && tid < hd) {
-    const float *base = p.att_part + (size_t)h * S * (hd + 2);
-    float M = -INFINITY;
-    for (int i = 0; i < S; ++i) M = fmaxf(M, __ldcg(base + (size_t)i * (hd + 2)));
-    float Lsum = 0.0f, a = 0.0f;
-    for (int i = 0; i < S; ++i) {
-      const float sc = expf(__ldcg(base + (size_t)i * (hd + 2)) - M);
-      Lsum = fmaf(__ldcg(base + (size_t)i * (hd + 2) + 1), sc, Lsum);
-      a = fmaf(__ldcg(base + (size_t)i * (hd + 2) + 2 + tid), sc, a);
+#pragma unroll
+    for (int q = 0; q < ATT_SMAX; ++q)
+      if (q < S) all_ok = all_ok && pair_ok(ml[q], ep) && pair_ok(ov[q], ep);
+    if (!all_ok && !wd_tripped(wd)) {
+      const long long t0 = clock64();
+      do {
+        all_ok = true;
+#pragma unroll
+        for (int q = 0; q < ATT_SMAX; ++q) {
+          if (q < S) {
+            if (!pair_ok(ml[q], ep)) ml[q] = ld_pair(base + (size_t)q * (hd + 2));
+            if (!pair_ok(ov[q], ep)) ov[q] = ld_pair(base + (size_t)q * (hd + 2) + 2 + d);
+            all_ok = all_ok && pair_ok(ml[q], ep) && pair_ok(ov[q], ep);
+          }
+        }
+        if (!all_ok && clock64() - t0 > WATCHDOG_CYCLES) {
+          wd_trip(wd, 6u);
+          break;
+        }
+      } while (!all_ok);
     }
-    st_flag(p.att_f + h * hd + tid, a / Lsum, ep_out);
+    float M = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < ATT_SMAX; ++q)
+      if (q < S) M = fmaxf(M, lo_f(ml[q].x));
+    float lsum = 0.0f, o0 = 0.0f, o1 = 0.0f;
+#pragma unroll
+    for (int q = 0; q < ATT_SMAX; ++q) {
+      if (q < S) {
+        const float sc = expf(lo_f(ml[q].x) - M);
+        lsum = fmaf(lo_f(ml[q].y), sc, lsum);
+        o0 = fmaf(lo_f(ov[q].x), sc, o0);
+        o1 = fmaf(lo_f(ov[q].y), sc, o1);
+      }
+    }
+    reinterpret_cast<float2 *>(dst_smem)[idx] = make_float2(o0 / lsum, o1 / lsum);
   }
+}
+
+// splits per head of the attention phase at context length T
+__device__ __forceinline__ int att_splits(int T, int G, int H) {
+  int S = (T + ATT_CHUNK - 1) / ATT_CHUNK;
+  S = min(S, min(ATT_SMAX, G / H));
+  return S;
 }
 
 __device__ __forceinline__ bool step_needs_logits(const DecodeParams &p, int step) {
@@ -661,9 +699,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
 
       if (mode == M_ATTN) {
         // ---------------- attention over the cache (ops.zig:160-171) ----------------
-        int S = (T + ATT_CHUNK - 1) / ATT_CHUNK;
-        const int smax = G / p.H;
-        if (S > smax) S = smax;
+        const int S = att_splits(T, G, p.H);
         if (cta < p.H * S) {
           const int chunk = (T + S - 1) / S;
           if (chunk <= 4 * NCW) attention_item<4>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep);
@@ -754,6 +790,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           const float4 a = __ldg(te + i4), b = __ldg(pe + i4);
           reinterpret_cast<float4 *>(vec)[i4] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
         }
+      } else if (mode == M_RESID && att_splits(T, G, p.H) > 1) {
+        gather_att_partials(vec, p.attp_f, E, att_splits(T, G, p.H), ep - 1, sm.wd);
       } else {
         gather_flagged(vec, ent.src, E, ep - 1, sm.wd);
       }
@@ -1159,16 +1197,14 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
   ZG_CUDA(cudaGetLastError());
 
   const size_t C = cfg.context_size, hd = 64;
-  const int smax = e->grid / (int)cfg.n_heads > 0 ? e->grid / (int)cfg.n_heads : 1;
-  const size_t n_exchange = E + E + 2 * E + E + 2 * (size_t)e->grid + E + (size_t)e->grid * E;
+  const size_t n_attp = cfg.n_heads * (size_t)ATT_SMAX * (hd + 2);
+  const size_t n_exchange = E + E + 2 * E + E + 2 * (size_t)e->grid + E + n_attp + (size_t)e->grid * E;
   e->exchange_dev = (u64 *)zg_alloc(n_exchange * 8);
   e->prompt_dev = (u64 *)zg_alloc(C * 8);
   e->tokens_dev = (u64 *)zg_alloc(C * 8);
   e->last_token_dev = (u64 *)zg_alloc(8);
   e->prof_dev = (u64 *)zg_alloc((2 * PROF_MAX + 4) * 8);
   e->err_dev = (unsigned *)zg_alloc(256);
-  float *att_part = (float *)zg_alloc(cfg.n_heads * (size_t)smax * (hd + 2) * sizeof(float));
-  unsigned *head_count = (unsigned *)zg_alloc(cfg.n_heads * sizeof(unsigned));
   ZG_CUDA(cudaHostAlloc(&e->tokens_host, C * 8, cudaHostAllocMapped));
   ZG_CUDA(cudaHostGetDevicePointer((void **)&e->tokens_host_devptr, e->tokens_host, 0));
   if (zg_last_error()) {
@@ -1178,7 +1214,6 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
   memset(e->tokens_host, 0xff, C * 8);
   zg_memset(e->exchange_dev, 0, n_exchange * 8);  // epoch 0 everywhere; the first phase of the first launch is epoch 1
   zg_memset(e->err_dev, 0, 256);
-  zg_memset(head_count, 0, cfg.n_heads * sizeof(unsigned));
   zg_memset(e->tokens_dev, 0, C * 8);
   zg_memset(e->prof_dev, 0, (2 * PROF_MAX + 4) * 8);
   e->epoch_count = 0;
@@ -1196,9 +1231,10 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
   p.att_f = x; x += E;
   p.amax_f = x; x += 2 * (size_t)e->grid;
   p.xnew_f = x; x += E;
+  p.attp_f = x; x += n_attp;
   p.part_f = x;
   p.xres_out = state->o; p.xout = state->x; p.logits = state->logits;
-  p.att_part = att_part; p.head_count = head_count; p.err = e->err_dev;
+  p.err = e->err_dev;
   p.tokens = e->tokens_dev; p.tokens_host = e->tokens_host_devptr; p.last_token = e->last_token_dev;
   p.dbg = getenv("ZG_DEBUG") ? atoi(getenv("ZG_DEBUG")) : 0;
   zg_sync();
@@ -1210,7 +1246,7 @@ void zg_engine_destroy(zg_engine *e) {
   zg_sync();
   if (g_table_owner == e) g_table_owner = nullptr;
   zg_free(e->exchange_dev); zg_free(e->derived_dev); zg_free(e->prompt_dev); zg_free(e->tokens_dev); zg_free(e->last_token_dev);
-  zg_free(e->prof_dev); zg_free(e->err_dev); zg_free(e->base.att_part); zg_free(e->base.head_count);
+  zg_free(e->prof_dev); zg_free(e->err_dev);
   cudaFreeHost(e->tokens_host);
   free(e->layers_host);
   free(e);
