@@ -182,7 +182,9 @@ int zg_engine_generate_greedy(zg_engine *e, const size_t *inputs, size_t n_input
 int zg_engine_set_prompt(zg_engine *e, const size_t *inputs, size_t n_inputs);
 void zg_engine_run_steps(zg_engine *e, size_t first_step, size_t n_steps);
 int zg_engine_read_tokens(zg_engine *e, size_t first_step, size_t n_steps, size_t *out_tokens);
-/* Per-phase device timestamps of the last launch (ns, CTA 0), for profiling; returns entries written. */
+/* Cycle timeline of the last launch, for profiling.  zg_engine_read_profile(e, NULL, n): n != 0 makes thread 0 of CTA
+ * n - 1 record (tag = 512 + 16 * phase kind + point, SM clock cycles) pairs in later launches, n == 0 switches it off.
+ * With a buffer: copies up to max_entries / 2 pairs into `out`, returns the number of pairs.  scripts/clock_profile.py */
 size_t zg_engine_read_profile(zg_engine *e, unsigned long long *out, size_t max_entries);
 
 /* ---------------------------------------------------------------------------------------------

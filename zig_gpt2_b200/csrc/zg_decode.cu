@@ -94,43 +94,53 @@ struct DecodeParams {
   int store_logits;  // also write the logits vector to global memory
   int write_xout;    // write ln_f(x) to xout (state.x) and the stream to xres_out on the last step
   u64 *prof;
-  int dbg;
+  int prof_cta;  // CTA whose thread 0 records the cycle timeline
 };
 
-// optional timeline of CTA 0 / thread 0: (tag, %globaltimer) pairs.  Compiled in only with -DZG_PROF (the profiling
-// variant scripts/phase_profile.py loads): even a not-taken mark costs a local-memory load per call site.
-#ifdef ZG_PROF
-struct Prof {
+// Cycle-level breakdown of a phase (zg_engine_read_profile): thread 0 of one chosen CTA keeps up to 12 %clock readings
+// in registers and dumps them as (tag = 512 + 16 * phase kind + point, cycles) pairs when the phase ends.  Compiled
+// in by default: with profiling off every hook is one not-taken uniform branch.  (Measured on B200: the build WITH
+// the hooks decodes ~5% faster than -DZG_NO_PROF -- a ptxas scheduling artefact, recorded in DESIGN.md, not relied on.)
+#ifndef ZG_NO_PROF
+struct Clk {
+  unsigned t[12];
   u64 *buf;
   int i;
-  bool fine;
-  __device__ __forceinline__ void fmark(int tag) {
-    if (fine) mark(tag);
-  }
-  __device__ __forceinline__ void mark(int tag) {
-    if (buf != nullptr) record(tag);
-  }
-  __device__ __noinline__ void record(int tag) {
-    if (i < PROF_MAX) {
-      buf[2 * i] = (u64)tag;
-      buf[2 * i + 1] = globaltimer();
+  __device__ __forceinline__ void at(int k) {
+    if (buf) {
+      if (k == 0) {
+#pragma unroll
+        for (int q = 1; q < 12; ++q) t[q] = 0u;
+      }
+      t[k] = (unsigned)clock64();
     }
-    ++i;
   }
-  __device__ __forceinline__ void finish() {
-    if (buf) buf[2 * PROF_MAX] = (u64)i;
+  __device__ __forceinline__ void dump(int kind) {
+    if (buf && i + 12 < PROF_MAX) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        buf[2 * (i + k)] = (u64)(512 + 16 * kind + k);
+        buf[2 * (i + k) + 1] = (u64)t[k];
+      }
+      i += 12;
+      buf[2 * PROF_MAX] = (u64)i;
+    }
   }
 };
 #else
-struct Prof {
+struct Clk {
   u64 *buf;
-  int i;
-  bool fine;
-  __device__ __forceinline__ void fmark(int) {}
-  __device__ __forceinline__ void mark(int) {}
-  __device__ __forceinline__ void finish() {}
+  __device__ __forceinline__ void at(int) {}
+  __device__ __forceinline__ void dump(int) {}
 };
 #endif
+
+// optional back-off between polls of the flagged exchange (experiment: -DZG_POLL_NS=n)
+__device__ __forceinline__ void poll_backoff() {
+#ifdef ZG_POLL_NS
+  __nanosleep(ZG_POLL_NS);
+#endif
+}
 
 // ---- flag-in-data exchange ------------------------------------------------------------------------
 __device__ __forceinline__ void st_flag(u64 *p, float v, unsigned ep) {
@@ -172,6 +182,7 @@ __device__ __noinline__ ulonglong2 spin_pair(const u64 *p, unsigned ep, Watchdog
   const long long t0 = clock64();
   unsigned spins = 0;
   while (!pair_ok(v, ep)) {
+    poll_backoff();
     v = ld_pair(p);
     if ((++spins & 255u) == 0 && clock64() - t0 > WATCHDOG_CYCLES) {
       wd_trip(wd, 3u);
@@ -215,6 +226,7 @@ __device__ __forceinline__ void gather_flagged(float *dst_smem, const u64 *src, 
     if (!all_ok && !wd_tripped(wd)) {
       const long long t0 = clock64();
       do {
+        poll_backoff();
         all_ok = true;
 #pragma unroll
         for (int j = 0; j < GB; ++j) {
@@ -306,8 +318,11 @@ __device__ __forceinline__ float packed_reduce(float (&v)[N], int lane) {
 // waited for (cache rows do not depend on this step), so a split that fits one round costs no exposed L2 latency
 // after q lands.  Scores: per-lane partial dot over the lane's 2 dims, packed butterfly (AR + 5 - log2 AR shuffles
 // for AR rows), one exp per lane, p broadcast by shuffle for the PV accumulation.
+#ifndef ZG_ATT_INLINE
+#define ZG_ATT_INLINE __forceinline__
+#endif
 template <int AR>
-__device__ __forceinline__ void attention_item(const DecodeParams &p, const Smem &sm, int l, int h, int s, int S, int T,
+__device__ ZG_ATT_INLINE void attention_item(const DecodeParams &p, const Smem &sm, int l, int h, int s, int S, int T,
                                                unsigned ep_in, unsigned ep_out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int hd = 64;
@@ -421,7 +436,10 @@ __device__ __forceinline__ void attention_item(const DecodeParams &p, const Smem
 
 // Attention output vector from S (2..ATT_SMAX) flagged partials per head: out = sum_s o_s e^(m_s - M) / sum_s l_s e^(m_s - M).
 // A thread handles pairs of adjacent elements; all 2 S loads of a pair are in flight before the first check.
-__device__ __forceinline__ void gather_att_partials(float *dst_smem, const u64 *attp, int E, int S, unsigned ep, Watchdog wd) {
+#ifndef ZG_GAP_INLINE
+#define ZG_GAP_INLINE __forceinline__
+#endif
+__device__ ZG_GAP_INLINE void gather_att_partials(float *dst_smem, const u64 *attp, int E, int S, unsigned ep, Watchdog wd) {
   constexpr int hd = 64;
   const int npairs = E >> 1;
 #pragma unroll 1
@@ -501,10 +519,11 @@ struct PhaseEnt {
   int mode;
 };
 
-// mean and 1/std of a warp's register copy of the E-vector (lane holds float4 number lane + 32 j, zeros past the
-// end); reference formula ops.zig:86-95: single pass E[x], E[x^2]; std = sqrt(var + eps)
+// LayerNorm statistics of a warp's register copy of the E-vector (lane holds float4 number lane + 32 j, zeros past
+// the end); reference formula ops.zig:86-95: single pass E[x], E[x^2]; std = sqrt(var + eps).  Two steps so that the
+// shuffle reduction can be scheduled after the dot products (nothing needs mean / rstd before the epilogue).
 template <int NJ>
-__device__ __forceinline__ void ln_stats(const float4 (&xs)[NJ], int E, float &mean, float &rstd) {
+__device__ __forceinline__ void ln_partial(const float4 (&xs)[NJ], float &s, float &ss) {
   float s0 = 0.0f, s1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
@@ -513,15 +532,21 @@ __device__ __forceinline__ void ln_stats(const float4 (&xs)[NJ], int E, float &m
     q0 = fmaf(xs[j].x, xs[j].x, q0); q1 = fmaf(xs[j].y, xs[j].y, q1);
     q0 = fmaf(xs[j].z, xs[j].z, q0); q1 = fmaf(xs[j].w, xs[j].w, q1);
   }
-  float s = s0 + s1, ss = q0 + q1;
+  s = s0 + s1;
+  ss = q0 + q1;
+}
+__device__ __forceinline__ void ln_finish(float s, float ss, float inv_E, float &mean, float &rstd) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
     ss += __shfl_xor_sync(0xffffffffu, ss, o);
   }
-  const float nE = (float)E;
-  mean = s / nE;
-  rstd = 1.0f / sqrtf(ss / nE - mean * mean + 1e-5f);
+  mean = s * inv_E;
+#ifdef ZG_SLOW_RSTD
+  rstd = 1.0f / sqrtf(ss * inv_E - mean * mean + 1e-5f);
+#else
+  rstd = rsqrtf(fmaf(ss, inv_E, -mean * mean) + 1e-5f);
+#endif
 }
 // explicit LayerNorm output (only needed when GPT.forward has to leave ln_f(x) in state.x, main.zig:189)
 template <int NJ>
@@ -565,6 +590,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
   sm.wd.err_global = p.err;
   sm.wd.tripped_smem = smem_u32(&wd_flag);
   const int bsz = min(NCW, nslot >> 1);  // ring units per batch: two batches always fit in the ring
+  const float inv_E = 1.0f / (float)p.E;
   const int rb = 4 * bsz;                // rows per batch: at most 4 per warp
 
   if (threadIdx.x == 0) {
@@ -665,8 +691,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
 
   // ================================= consumer warps =================================
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  Prof pf{(p.prof && cta == 0 && tid == 0) ? p.prof : nullptr, 0, (p.dbg & 8) != 0};
-  pf.mark(0);
+#ifndef ZG_NO_PROF
+  Clk ck;
+  ck.buf = (p.prof && cta == p.prof_cta && tid == 0) ? p.prof : nullptr;
+  ck.i = 0;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) ck.t[k] = 0u;
+#else
+  Clk ck{nullptr};
+#endif
   u64 prev_token = 0;
   int bslot = 0;               // ring slot of the first unit of the next batch
   uint32_t fpar = 0;           // bit s: parity the next wait on full barrier s expects
@@ -696,6 +729,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
       const bool is_head = (g == L5);
       const int tag = is_head ? 96 : 16 * (g % 5 + 1);
       const int mode = ent.mode;
+      ck.at(0);
 
       if (mode == M_ATTN) {
         // ---------------- attention over the cache (ops.zig:160-171) ----------------
@@ -706,7 +740,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           else if (chunk <= 8 * NCW) attention_item<8>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep);
           else attention_item<16>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep);
         }
-        pf.mark(tag + 3);
+        ck.at(11);
+        ck.dump(1);
         continue;
       }
       if (mode == M_REDUCE) {
@@ -737,6 +772,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         if (!all_ok && !wd_tripped(sm.wd)) {
           const long long t0 = clock64();
           do {
+            poll_backoff();
             all_ok = true;
 #pragma unroll
             for (int q = 0; q < NP; ++q)
@@ -750,20 +786,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           } while (!all_ok);
         }
 #endif
+        ck.at(2);
         float tot = 0.0f;
 #pragma unroll
         for (int q = 0; q < NP; ++q) tot += lo_f(w[q]);
         tot += __shfl_xor_sync(0xffffffffu, tot, 16);
         if (lg == 3) tot += __shfl_xor_sync(0xffffffffu, tot, 8);
         if (lane < (1 << lg)) sm.part[lane * 8 + warp] = tot;
+        ck.at(3);
         consumer_sync();
+        ck.at(4);
         if (tid < ne) {
           float v = 0.0f;
 #pragma unroll
           for (int w2 = 0; w2 < NCW; ++w2) v += sm.part[tid * 8 + w2];
           st_flag(p.xnew_f + ent.r0 + tid, xmid[ent.r0 + tid] + bmine + v, ep);
         }
-        pf.mark(tag + 3);
+        ck.at(11);
+        ck.dump(4);
         continue;
       }
 
@@ -774,6 +814,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
       const bool has_ln = ent.c1 != nullptr;
       // ---------------- phase top: issue every load whose address is known before the activation arrives ----
       // lanes 0/8/16/24 of warp w finish rows w, w + NCW, w + 2 NCW, w + 3 NCW of a batch
+      // the weights of the first batch are almost always in the ring already: test its barrier now, off the critical path
+#ifdef ZG_NO_EARLY_TRY
+      bool wready = false;
+#else
+      bool wready = mbar_try(sm.full0 + 8u * bslot, (fpar >> bslot) & 1u);
+#endif
       float bias_v = 0.0f, c1_v = 0.0f;
       if (elane && iloc < min(rb, ent.nrows)) {
         const int r = ent.r0 + iloc;
@@ -781,6 +827,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         if (has_ln) c1_v = __ldg(ent.c1 + r);
       }
 
+      ck.at(1);
       // ---------------- activation vector -> shared memory -> registers ----------------
       if (g == 0) {  // wte[token] + wpe[pos] (main.zig:179-183), recomputed by every CTA
         const float4 *te = reinterpret_cast<const float4 *>(p.wte + (size_t)tok * E);
@@ -795,21 +842,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
       } else {
         gather_flagged(vec, ent.src, E, ep - 1, sm.wd);
       }
-      pf.fmark(256 + 5);
+      ck.at(2);
       consumer_sync();
+      ck.at(3);
       float4 xs[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int i4 = lane + 32 * j;
         xs[j] = (i4 < Eq) ? vec4[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      float mean = 0.0f, rstd = 1.0f;
+      float mean = 0.0f, rstd = 1.0f, ln_s = 0.0f, ln_ss = 0.0f;
       if (has_ln) {
-        ln_stats<NJ>(xs, E, mean, rstd);
-        if (is_head && p.write_xout && step == last_step && cta == 0 && warp == 0)
+        ln_partial<NJ>(xs, ln_s, ln_ss);
+        if (is_head && p.write_xout && step == last_step && cta == 0 && warp == 0) {
+          ln_finish(ln_s, ln_ss, inv_E, mean, rstd);
           ln_write<NJ>(xs, mean, rstd, p.lnf_g, p.lnf_b, p.xout, p.xres_out, E, lane);
+        }
       }
-      pf.mark(tag + 1);
+      ck.at(4);
 
       // ---------------- GEMV: warp w takes rows w, w + NCW, ... of every batch ----------------
       float *kc = nullptr, *vc = nullptr;
@@ -831,9 +881,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           bias_v = ent.bias ? __ldg(ent.bias + r) : 0.0f;
           if (has_ln) c1_v = __ldg(ent.c1 + r);
         }
-        mbar_wait(sm.full0 + 8u * bslot, (fpar >> bslot) & 1u, sm.wd);
+        if (!wready) mbar_wait(sm.full0 + 8u * bslot, (fpar >> bslot) & 1u, sm.wd);
+        wready = false;
         fpar ^= 1u << bslot;
-        pf.fmark(256 + 7);
+        if (b0 == 0) ck.at(5);
         float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -860,8 +911,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           if (sl >= nslot) sl -= nslot;
           mbar_arrive(sm.empty0 + 8u * (uint32_t)sl);
         }
-        pf.fmark(256 + 8);
-        float v = packed_reduce<4>(acc, lane);  // lane L: total of the warp's row number L >> 3
+        if (b0 == 0) ck.at(6);
+        float v;  // lane L: total of the warp's row number L >> 3
+        if (b0 == 0) {  // the LayerNorm statistics ride along with the first batch's reduction (same basic block)
+          v = packed_reduce<4>(acc, lane);
+          ln_finish(ln_s, ln_ss, inv_E, mean, rstd);
+          ck.at(7);
+        } else {
+          v = packed_reduce<4>(acc, lane);
+        }
         bslot += nun;
         if (bslot >= nslot) bslot -= nslot;
         // ---------------- epilogue: lanes 0/8/16/24 finish one row each ----------------
@@ -889,10 +947,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         }
       }
 
+      ck.at(8);
       if (mode == M_MLP) {
         // ---------------- mlp c_proj, main.zig:81: out += f_j * c_proj^T[j, :] over the hidden units j this CTA owns.
         // Thread t accumulates output float4 t (and t + 224 for wide models); no shuffles. ----------------
+        // test the barrier of the first c_proj^T batch before the CTA sync
+#ifdef ZG_NO_EARLY_TRY
+        bool w2ready = false;
+#else
+        bool w2ready = mbar_try(sm.full0 + 8u * bslot, (fpar >> bslot) & 1u);
+#endif
         consumer_sync();  // fbuf complete
+        ck.at(9);
         constexpr int NK = (NJ * 32 > NCT) ? 2 : 1;  // output float4 per thread
         float4 o4[NK];
 #pragma unroll
@@ -901,31 +967,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         for (int b0 = 0; b0 < ent.nrows; b0 += rb) {
           const int nbr = min(rb, ent.nrows - b0);
           const int nun = (nbr + 3) >> 2;
-          mbar_wait(sm.full0 + 8u * bslot, (fpar >> bslot) & 1u, sm.wd);
+          if (!w2ready) mbar_wait(sm.full0 + 8u * bslot, (fpar >> bslot) & 1u, sm.wd);
+          w2ready = false;
           fpar ^= 1u << bslot;
+          // Branch-free and software-pipelined over the (up to NCW) ring units of the batch: unit q + 1 is loaded
+          // while unit q is multiplied; units / rows past the batch re-read a valid row with a zero factor.
 #pragma unroll
-          for (int q = 0; q < NCW; ++q) {  // ring unit q of the batch: 4 hidden units (bsz <= NCW units per batch)
-            if (q < nun) {
-              int sl = bslot + q;
-              if (sl >= nslot) sl -= nslot;
-              const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)sl * slotf);
-              const float4 f4 = *reinterpret_cast<const float4 *>(sm.fbuf + b0 + 4 * q);
-              // rows past the batch: re-read the unit's first row with a zero factor (stale ring contents may not be finite)
-              const int nv = nbr - 4 * q;
-              const float fj[4] = {f4.x, nv > 1 ? f4.y : 0.0f, nv > 2 ? f4.z : 0.0f, nv > 3 ? f4.w : 0.0f};
+          for (int k = 0; k < NK; ++k) {
+            const int i4 = min(tid + k * NCT, Eq - 1);
+            const bool live = tid + k * NCT < Eq;
+            float4 wq[2][4];
+            {
+              const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)bslot * slotf);
 #pragma unroll
-              for (int k = 0; k < NK; ++k) {
-                const int i4 = tid + k * NCT;
-                if (i4 < Eq) {
-                  float4 w[4];
+              for (int j = 0; j < 4; ++j) wq[0][j] = w4[(j < nbr ? j : 0) * Eq + i4];
+            }
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) w[j] = w4[(j < nv ? j : 0) * Eq + i4];
+            for (int q = 0; q < NCW; ++q) {
+              if (q + 1 < NCW) {
+                const int qn = min(q + 1, nun - 1);
+                int sl = bslot + qn;
+                if (sl >= nslot) sl -= nslot;
+                const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)sl * slotf);
+                const int nvn = nbr - 4 * qn;
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    o4[k].x = fmaf(fj[j], w[j].x, o4[k].x); o4[k].y = fmaf(fj[j], w[j].y, o4[k].y);
-                    o4[k].z = fmaf(fj[j], w[j].z, o4[k].z); o4[k].w = fmaf(fj[j], w[j].w, o4[k].w);
-                  }
-                }
+                for (int j = 0; j < 4; ++j) wq[(q + 1) & 1][j] = w4[(j < nvn ? j : 0) * Eq + i4];
+              }
+              const float4 f4 = *reinterpret_cast<const float4 *>(sm.fbuf + b0 + 4 * min(q, nun - 1));
+              const int nv = (q < nun && live) ? nbr - 4 * q : 0;
+              const float fj[4] = {nv > 0 ? f4.x : 0.0f, nv > 1 ? f4.y : 0.0f, nv > 2 ? f4.z : 0.0f, nv > 3 ? f4.w : 0.0f};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 w = wq[q & 1][j];
+                o4[k].x = fmaf(fj[j], w.x, o4[k].x); o4[k].y = fmaf(fj[j], w.y, o4[k].y);
+                o4[k].z = fmaf(fj[j], w.z, o4[k].z); o4[k].w = fmaf(fj[j], w.w, o4[k].w);
               }
             }
           }
@@ -938,6 +1013,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           bslot += nun;
           if (bslot >= nslot) bslot -= nslot;
         }
+        ck.at(10);
         u64 *mine = p.part_f + (size_t)cta * E;
 #pragma unroll
         for (int k = 0; k < NK; ++k) {
@@ -948,7 +1024,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           }
         }
       }
-      pf.mark(tag + 3);
+      ck.at(11);
+      ck.dump(is_head ? 5 : mode == M_QKV ? 0 : mode == M_RESID ? 2 : 3);
 
       if (is_head) {
         // argmax (value desc, index asc): warp -> CTA -> one flagged partial per CTA, then every CTA reduces the
@@ -999,7 +1076,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         if (cta == 0 && tid == 0) *p.last_token = amax;
         if (step >= p.n_prompt) out_tok = amax;  // generate(): main.zig:335-338
         consumer_sync();
-        pf.mark(tag + 4);
       }
     }
 
@@ -1016,8 +1092,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           const int i4 = lane + 32 * j;
           xs[j] = (i4 < Eq) ? reinterpret_cast<const float4 *>(vec)[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float mean, rstd;
-        ln_stats<NJ>(xs, E, mean, rstd);
+        float mean, rstd, ln_s, ln_ss;
+        ln_partial<NJ>(xs, ln_s, ln_ss);
+        ln_finish(ln_s, ln_ss, inv_E, mean, rstd);
         ln_write<NJ>(xs, mean, rstd, p.lnf_g, p.lnf_b, p.xout, p.xres_out, E, lane);
       }
     }
@@ -1027,8 +1104,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
     }
     prev_token = out_tok;
   }
-  pf.mark(1);
-  pf.finish();
 }
 
 typedef void (*decode_kernel_t)(const DecodeParams);
@@ -1236,7 +1311,6 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
   p.xres_out = state->o; p.xout = state->x; p.logits = state->logits;
   p.err = e->err_dev;
   p.tokens = e->tokens_dev; p.tokens_host = e->tokens_host_devptr; p.last_token = e->last_token_dev;
-  p.dbg = getenv("ZG_DEBUG") ? atoi(getenv("ZG_DEBUG")) : 0;
   zg_sync();
   return zg_last_error() ? (free(e), nullptr) : e;
 }
@@ -1275,6 +1349,7 @@ static void engine_launch(zg_engine *e, DecodeParams &p) {
   }
   p.epoch_base = e->epoch_count;
   p.prof = e->prof_enabled ? e->prof_dev : nullptr;
+  p.prof_cta = e->prof_enabled - 1;
   e->epoch_count += phases_for(e, p);
   void *args[] = {(void *)&p};
   ZG_CUDA(cudaLaunchCooperativeKernel((const void *)decode_kernel_for((int)e->cfg.n_embed), dim3(e->grid), dim3(NTHREADS),
@@ -1370,11 +1445,11 @@ int zg_engine_generate_greedy(zg_engine *e, const size_t *inputs, size_t n_input
 
 size_t zg_engine_read_profile(zg_engine *e, unsigned long long *out, size_t max_entries) {
   if (!require_ready("zg_engine_read_profile")) return 0;
-  if (out == nullptr) {  // toggle: calling with NULL enables (max_entries != 0) or disables profiling
-    e->prof_enabled = max_entries ? 1 : 0;
+  if (out == nullptr) {  // toggle: NULL + n enables the timeline of CTA n - 1 (n != 0) or disables profiling (n == 0)
+    e->prof_enabled = (int)max_entries;
     return 0;
   }
-  // out receives (tag, ns) pairs; returns the number of pairs
+  // out receives (tag, SM cycles) pairs; returns the number of pairs
   u64 *tmp = (u64 *)malloc((2 * PROF_MAX + 4) * 8);
   zg_download(tmp, e->prof_dev, (2 * PROF_MAX + 4) * 8);
   size_t n = (size_t)tmp[2 * PROF_MAX];
