@@ -24,6 +24,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import re
 import sys
 import threading
 import time
@@ -239,13 +240,19 @@ def run_ours(args):
     # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/), scaled to K steps
     traffic = None
     try:
-        import csv
-
+        cap_steps, m = 64, {}
         with open(os.path.join(ROOT, "profiles", "r01_decode_persistent_ncu_full.csv")) as f:
-            m = {r["metric"]: (float(r["value"]), r["unit"]) for r in csv.DictReader(f)}
+            for ln in f:
+                if ln.startswith("#"):
+                    mm = re.search(r"one (\d+)-token launch", ln)
+                    cap_steps = int(mm.group(1)) if mm else cap_steps
+                    continue
+                parts = ln.rstrip("\n").split(",")
+                if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and parts[2]:
+                    m[parts[0]] = (float(parts[2]), parts[1])
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-        per64 = sum(m[k][0] * scale[m[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-        traffic = per64 / 64.0 * K  # the capture was a 64-step launch
+        per_cap = sum(m[k][0] * scale[m[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        traffic = per_cap / cap_steps * K  # per-token DRAM bytes of the captured launch, scaled to this K-step launch
     except Exception:
         traffic = None
     achieved = bytes_per_launch / (float(np.median(trials)) * 1e-3) / 1e9

@@ -1,5 +1,5 @@
 """Cycle-level breakdown of the persistent decode kernel's phases (thread 0 of one CTA, %clock at tagged points).
-Usage: python scripts/clock_profile.py [size] [n_steps] [cta]"""
+Usage: python scripts/clock_profile.py [size] [n_steps] [cta] [first position]"""
 import ctypes as C
 import os
 import sys
@@ -16,6 +16,7 @@ from zig_gpt2_b200.weights import synth_for_size  # noqa: E402
 size = sys.argv[1] if len(sys.argv) > 1 else "124M"
 n_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 cta = int(sys.argv[3]) if len(sys.argv) > 3 else 100
+first = int(sys.argv[4]) if len(sys.argv) > 4 else 24
 L = lib.init(0)
 cfg = SIZES[size]
 model = G.gpt_from_numpy(cfg, synth_for_size(size))
@@ -23,15 +24,15 @@ state = G.State(cfg)
 eng = model.engine(state)
 prompt = np.random.Generator(np.random.PCG64(1235)).integers(0, cfg.vocab_size, 16).astype(np.uint64)
 L.zg_engine_set_prompt(eng, prompt.ctypes.data_as(lib.c_size_p), 16)
-L.zg_engine_run_steps(eng, 0, 24)
+L.zg_engine_run_steps(eng, 0, first)
 for _ in range(10):
-    L.zg_engine_run_steps(eng, 24, n_steps)
+    L.zg_engine_run_steps(eng, first, n_steps)
 L.zg_sync()
 L.zg_timer_begin()
-L.zg_engine_run_steps(eng, 24, n_steps)
+L.zg_engine_run_steps(eng, first, n_steps)
 print(f"{size}: {L.zg_timer_end_ms()*1e3/n_steps:.1f} us/token with the timeline off")
 L.zg_engine_read_profile(eng, None, 1 + cta)
-L.zg_engine_run_steps(eng, 24, n_steps)
+L.zg_engine_run_steps(eng, first, n_steps)
 L.zg_sync()
 buf = (C.c_ulonglong * (2 * 16384))()
 n = L.zg_engine_read_profile(eng, buf, 2 * 16384)
@@ -63,9 +64,9 @@ while i + 12 <= n:
     prev_end["t"] = t[11]
     i += 12
 L.zg_timer_begin()
-L.zg_engine_run_steps(eng, 24, n_steps)
+L.zg_engine_run_steps(eng, first, n_steps)
 print(f"{size}: {L.zg_timer_end_ms()*1e3/n_steps:.1f} us/token with the timeline on")
-print(f"{size}: cycles at the SM clock, thread 0 of CTA {cta}; mean over {n_steps} tokens")
+print(f"{size}: cycles at the SM clock, thread 0 of CTA {cta}; mean over {n_steps} tokens at positions {first}..{first + n_steps - 1}")
 for kind in sorted(kinds):
     tot = seg.get((kind, 0, 99))
     if not tot:
