@@ -297,7 +297,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--steps", type=int, default=64)  # SURVEY 8d cfg 2: 64 greedy tokens after a 16-token prompt
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--trials", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
