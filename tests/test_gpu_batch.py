@@ -115,6 +115,29 @@ def test_linear_fused_epilogues(L, epi, inplace, out_cols, direct):
     assert rel(dst.download().reshape(M, N), want) <= FP32_RTOL
 
 
+@pytest.mark.parametrize("M,N,K,precision,tol", [(64, 1600, 6400, 2, None), (1024, 768, 3072, 2, None), (64, 1600, 1600, 0, 2e-2),
+                                                  (200, 768, 768, 2, None)])
+def test_linear_split_k_inplace_residual(L, M, N, K, precision, tol):
+    """x += Linear(h) (main.zig:136-139,142-145) with few output tiles and a long K: gemm_plan cuts K into slices that
+    reduce-add their partial tiles into x (slice 0 adds the bias).  Shapes: 1.5B c_proj / mlp c_proj at batch 64 (cfg 4)
+    and 124M mlp c_proj at 1024 rows (cfg 5).  Summation order across slices is not fixed, so fp32-tolerance, not bits."""
+    import zg_oracle as zo
+    from zig_gpt2_b200 import lib
+    from zig_gpt2_b200.lib import DeviceBuffer, ZgLinear
+
+    rs = np.random.RandomState(M + N)
+    x = rs.randn(M, K).astype(np.float32)
+    w = (rs.randn(N, K) * 0.02).astype(np.float32)
+    b, r = rs.randn(N).astype(np.float32), rs.randn(M, N).astype(np.float32)
+    want = zo.linear(x, w, b) + r
+    dx, dw, db, dr = (DeviceBuffer.from_numpy(a) for a in (x, w, b, r))
+    lin = ZgLinear(K, N, dw.ptr, db.ptr)
+    L.zg_linear_forward_tc(C.byref(lin), dx.ptr, M * K, dr.ptr, precision, None, 2, dr.ptr, 0)
+    lib.check()
+    assert L.zg_tc_error() == 0
+    assert rel(dr.download().reshape(M, N), want) <= (tol if tol else FP32_RTOL)
+
+
 @pytest.mark.parametrize("B,T,H", [(1, 5, 12), (2, 128, 2), (2, 200, 3), (1, 1024, 2)])
 def test_prefill_attention_equals_incremental_kv_cache_attention(L, B, T, H):
     """tests.zig:245-334: feeding tokens one at a time through the KV cache must equal causal full-sequence attention.

@@ -42,8 +42,9 @@ __global__ void embed_rows_kernel(const float *__restrict__ wte, const float *__
 // that may be strided in the input (row r starts at in + r * in_stride); output dense, fp32 or fp16.  One warp per
 // row: the row is read once with 128-bit loads and stays in registers between the statistics and the normalisation,
 // reductions are warp shuffles, stores are 128-bit (fp32) / 64-bit (fp16).  HBM-bound: E*4 bytes in, E*(4|2) out.
-constexpr int LN_WARPS = 8, LN_MAXV = 16;  // up to 16 float4 per lane: n_embed <= 2048
-template <bool OUT_F16>
+constexpr int LN_WARPS = 8;
+// LN_MAXV float4 per lane (n_embed <= 128 LN_MAXV): 8 keeps the kernel at ~60 registers, i.e. 32 resident warps per SM
+template <bool OUT_F16, int LN_MAXV>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_rows_kernel(const float *__restrict__ in, size_t in_stride, void *out,
                                                                 const float *__restrict__ g, const float *__restrict__ b,
                                                                 int E, float eps, int rows) {
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_rows_kernel(const float *__r
   ss = warp_sum(ss);
   const float n = (float)E, mean = s / n;
   const float std_ = sqrtf(ss / n - mean * mean + eps);
+  const float rinv = 1.0f / std_;
   const float4 *g4 = reinterpret_cast<const float4 *>(g), *b4 = reinterpret_cast<const float4 *>(b);
 #pragma unroll
   for (int i = 0; i < LN_MAXV; ++i) {
@@ -73,10 +75,17 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_rows_kernel(const float *__r
     if (c < nv) {
       const float4 gg = __ldg(g4 + c), bb = __ldg(b4 + c);
       float4 y;
-      y.x = (v[i].x - mean) / std_ * gg.x + bb.x;
-      y.y = (v[i].y - mean) / std_ * gg.y + bb.y;
-      y.z = (v[i].z - mean) / std_ * gg.z + bb.z;
-      y.w = (v[i].w - mean) / std_ * gg.w + bb.w;
+      if (OUT_F16) {  // the f16 operand rounds at 2^-11: one reciprocal per row instead of four divisions per float4
+        y.x = (v[i].x - mean) * rinv * gg.x + bb.x;
+        y.y = (v[i].y - mean) * rinv * gg.y + bb.y;
+        y.z = (v[i].z - mean) * rinv * gg.z + bb.z;
+        y.w = (v[i].w - mean) * rinv * gg.w + bb.w;
+      } else {  // fp32 path: the reference's division (ops.zig:101), bit-for-bit the per-op kernel's arithmetic
+        y.x = (v[i].x - mean) / std_ * gg.x + bb.x;
+        y.y = (v[i].y - mean) / std_ * gg.y + bb.y;
+        y.z = (v[i].z - mean) / std_ * gg.z + bb.z;
+        y.w = (v[i].w - mean) / std_ * gg.w + bb.w;
+      }
       if (OUT_F16) {
         __half2 lo = __floats2half2_rn(y.x, y.y), hi = __floats2half2_rn(y.z, y.w);
         uint2 pk;
@@ -88,6 +97,14 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_rows_kernel(const float *__r
       }
     }
   }
+}
+
+template <bool OUT_F16>
+void launch_ln_rows(const float *in, size_t in_stride, void *out, const float *g, const float *b, int E, int rows, cudaStream_t s) {
+  const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+  if (E <= 1024) ln_rows_kernel<OUT_F16, 8><<<grid, LN_WARPS * 32, 0, s>>>(in, in_stride, out, g, b, E, 1e-5f, rows);
+  else ln_rows_kernel<OUT_F16, 16><<<grid, LN_WARPS * 32, 0, s>>>(in, in_stride, out, g, b, E, 1e-5f, rows);
+  ZG_LAUNCH_CHECK();
 }
 
 // greedy argmax per row (first maximum wins, like the oracle); writes the next token and the history row
@@ -276,20 +293,17 @@ void enqueue_step(zg_batch *e, bool from_prompt, int n_inputs, bool with_logits)
   for (size_t l = 0; l < e->layers.size(); ++l) {
     const LayerW &w = e->layers[l];
     const LayerPlans &p = e->dec_plans[l];
-    ln_rows_kernel<false><<<(B + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(e->x, E, e->h, w.ln1_g, w.ln1_b, E, 1e-5f, B);  // main.zig:121-123
-    ZG_LAUNCH_CHECK();
+    launch_ln_rows<false>(e->x, E, e->h, w.ln1_g, w.ln1_b, E, B, s);  // main.zig:121-123
     gemm_launch(p.attn);  // c_attn + K/V append at row *pos (ops.zig:143,151-152,156-157)
     attn_decode_batch_launch(e->qkv, 3 * E, e->k_cache + l * e->layer_stride, e->v_cache + l * e->layer_stride,
                              (long long)e->seq_stride, B, H, E, e->att, E, e->pos, 0);  // ops.zig:160-169
     gemm_launch(p.proj);  // c_proj + residual (ops.zig:172, main.zig:136-139)
-    ln_rows_kernel<false><<<(B + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(e->x, E, e->h, w.ln2_g, w.ln2_b, E, 1e-5f, B);  // main.zig:140
-    ZG_LAUNCH_CHECK();
+    launch_ln_rows<false>(e->x, E, e->h, w.ln2_g, w.ln2_b, E, B, s);  // main.zig:140
     gemm_launch(p.fc);     // c_fc + GELU (main.zig:79-80)
     gemm_launch(p.proj2);  // c_proj + residual (main.zig:81,142-145)
   }
   if (with_logits) {
-    ln_rows_kernel<false><<<(B + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(e->x, E, e->h, e->lnf_g, e->lnf_b, E, 1e-5f, B);  // main.zig:189
-    ZG_LAUNCH_CHECK();
+    launch_ln_rows<false>(e->x, E, e->h, e->lnf_g, e->lnf_b, E, B, s);  // main.zig:189
     gemm_launch(e->dec_head);  // tied lm_head (main.zig:192-194)
     argmax_rows_kernel<<<B, 256, 0, s>>>(e->logits, (size_t)e->Vp, V, e->tok, e->hist, B, e->pos);
     ZG_LAUNCH_CHECK();
@@ -306,19 +320,16 @@ void enqueue_prefill(zg_batch *e, int T, bool with_logits) {
   for (size_t l = 0; l < e->layers.size(); ++l) {
     const LayerW &w = e->layers[l];
     const LayerPlans &p = e->pre_plans[l];
-    ln_rows_kernel<true><<<(M + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(e->px, E, e->ph, w.ln1_g, w.ln1_b, E, 1e-5f, M);
-    ZG_LAUNCH_CHECK();
+    launch_ln_rows<true>(e->px, E, e->ph, w.ln1_g, w.ln1_b, E, M, s);
     gemm_launch(p.attn);
     attn_prefill_launch(e->pre_attn[l]);
     gemm_launch(p.proj);
-    ln_rows_kernel<true><<<(M + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(e->px, E, e->ph, w.ln2_g, w.ln2_b, E, 1e-5f, M);
-    ZG_LAUNCH_CHECK();
+    launch_ln_rows<true>(e->px, E, e->ph, w.ln2_g, w.ln2_b, E, M, s);
     gemm_launch(p.fc);
     gemm_launch(p.proj2);
   }
   if (with_logits) {  // last position of every prompt only (main.zig:192)
-    ln_rows_kernel<true><<<(B + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(e->px + (size_t)(T - 1) * E, (size_t)T * E, e->plast16, e->lnf_g, e->lnf_b, E, 1e-5f, B);
-    ZG_LAUNCH_CHECK();
+    launch_ln_rows<true>(e->px + (size_t)(T - 1) * E, (size_t)T * E, e->plast16, e->lnf_g, e->lnf_b, E, B, s);
     gemm_launch(e->pre_head);
   }
 }

@@ -10,6 +10,7 @@
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).  The epilogue of tile i
 // overlaps the main loop of tile i+1.  kind::tf32 reads the fp32 tensors as they are; kind::f16 reads f16 copies.
 #include <initializer_list>
+#include <stdlib.h>
 
 #include "zg_gemm.cuh"
 
@@ -91,9 +92,9 @@ __device__ __forceinline__ void stage_and_store(const float (&v)[32], bool as_f1
 }
 
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float (&v)[32], int row, int col0, int pos_now,
-                                               const EpiTma &t, int lane) {
+                                               const EpiTma &t, int lane, bool add_bias) {
   const bool full = (col0 + 32 <= g.N);
-  if (g.bias) {
+  if (g.bias && add_bias) {
     if (full) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -237,14 +238,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
   const int num_m = (g.M + BM - 1) / BM, num_n = (g.N + BN - 1) / BN, tiles = num_m * num_n;
   const int num_kb = (g.K + BK - 1) / BK;
+  // work item = (output tile, K slice); slice ks covers k-blocks [ks num_kb / ksplit, (ks + 1) num_kb / ksplit)
+  const int ksplit = g.ksplit, items = tiles * ksplit;
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer ----------------
       uint32_t stage = 0, phase = 0;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < tiles && ok; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < items && ok; item += gridDim.x) {
+        const int tile = item % tiles, ks = item / tiles;
         const int m_blk = g.n_fastest ? tile / num_n : tile % num_m, n_blk = g.n_fastest ? tile % num_n : tile / num_m;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = ks * num_kb / ksplit, kb1 = (ks + 1) * num_kb / ksplit;
+        for (int kb = kb0; kb < kb1; ++kb) {
           if (!tc::mbar_wait(empty_bar + 8 * stage, phase ^ 1, guard)) { ok = false; break; }
           tc::mbar_expect_tx(full_bar + 8 * stage, C::STAGE);
           tc::tma_load_2d(sA + stage * A_STAGE, &tm_a, kb * BK, m_blk * BM, full_bar + 8 * stage);
@@ -259,11 +264,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const uint32_t ready_bar = SPLIT ? split_bar : full_bar;
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < tiles && ok; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < items && ok; item += gridDim.x) {
+        const int ks = item / tiles;
+        const int kb0 = ks * num_kb / ksplit, kb1 = (ks + 1) * num_kb / ksplit;
         if (!tc::mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1, guard)) break;
         tc::fence_after_sync();
         const uint32_t d = tmem + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           if (!tc::mbar_wait(ready_bar + 8 * stage, phase, guard)) { ok = false; break; }
           tc::fence_after_sync();
           const uint32_t a = sA + stage * A_STAGE, b = sB + stage * C::B_STAGE;
@@ -273,11 +280,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             if constexpr (SPLIT) {
               const uint64_t da_lo = tc::umma_desc_sw128(sAlo + stage * A_STAGE + 32 * k, 16, 1024);
               const uint64_t db_lo = tc::umma_desc_sw128(sBlo + stage * C::B_STAGE + 32 * k, 16, 1024);
-              tc::umma<true>(d, da_lo, db, idesc, (uint32_t)((kb | k) != 0));
+              tc::umma<true>(d, da_lo, db, idesc, (uint32_t)(((kb - kb0) | k) != 0));
               tc::umma<true>(d, da, db_lo, idesc, 1u);
               tc::umma<true>(d, da, db, idesc, 1u);
             } else {
-              tc::umma<TF32>(d, da, db, idesc, (uint32_t)((kb | k) != 0));
+              tc::umma<TF32>(d, da, db, idesc, (uint32_t)(((kb - kb0) | k) != 0));
             }
           }
           tc::umma_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs have read it
@@ -291,8 +298,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const int t = threadIdx.x - 6 * 32;  // 0..127
     uint32_t stage = 0, phase = 0;
     bool ok = true;
-    for (int tile = blockIdx.x; tile < tiles && ok; tile += gridDim.x) {
-      for (int kb = 0; kb < num_kb; ++kb) {
+    for (int item = blockIdx.x; item < items && ok; item += gridDim.x) {
+      const int ks = item / tiles;
+      const int kb0 = ks * num_kb / ksplit, kb1 = (ks + 1) * num_kb / ksplit;
+      for (int kb = kb0; kb < kb1; ++kb) {
         if (!tc::mbar_wait(full_bar + 8 * stage, phase, guard)) { ok = false; break; }
         const uint32_t hi[2] = {sA + stage * A_STAGE, sB + stage * C::B_STAGE};
         const uint32_t lo[2] = {sAlo + stage * A_STAGE, sBlo + stage * C::B_STAGE};
@@ -324,7 +333,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       uint32_t acc = 0, acc_phase = 0;
       const int pos_now = g.pos_base + (g.pos_dev ? *g.pos_dev : 0);
       EpiTma et{&tm_out, &tm_k, &tm_v, staging + (uint32_t)e * 4096u, 0};
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int tile = item % tiles, ks = item / tiles;
         const int m_blk = g.n_fastest ? tile / num_n : tile % num_m, n_blk = g.n_fastest ? tile % num_n : tile / num_m;
         if (!tc::mbar_wait(tfull_bar + 8 * acc, acc_phase, guard)) break;
         tc::fence_after_sync();
@@ -341,7 +351,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            epilogue_chunk(g, v, row, col0, pos_now, et, lane);
+            epilogue_chunk(g, v, row, col0, pos_now, et, lane, ks == 0);
           }
         }
         tc::fence_before_sync();
@@ -405,6 +415,7 @@ void set_attr_mode() {
 
 unsigned *g_err_word = nullptr;
 bool g_disable_tma_out = false;  // test hook: force the direct-store epilogue
+bool g_disable_split_k = false;  // test / A-B hook: never split K (ZG_NO_SPLIT_K=1 in the environment)
 
 }  // namespace
 
@@ -461,19 +472,38 @@ bool gemm_plan(GemmPlan *p, int mode, const void *A, size_t lda, const void *W, 
     set_error(1, "Linear (tensor-core path): n_embed must be a multiple of 32 for the fused cache append", __FILE__, __LINE__);
     return false;
   }
+  static const bool env_no_split = getenv("ZG_NO_SPLIT_K") != nullptr;
+  if (env_no_split) g_disable_split_k = true;
   const int sms = ctx().sm_count > 0 ? ctx().sm_count : 148;
+  const int num_m = (args.M + BM - 1) / BM, num_kb = (args.K + bk - 1) / bk;
+  // An in-place residual (x += Linear(h), main.zig:136-145) goes out as TMA reduce-adds, so its K range may be split
+  // across work items: pick the widest tile whose (tiles x K slices) still occupy ~every SM with >= 6 k-blocks each.
+  const bool can_split = !g_disable_tma_out && !g_disable_split_k && bn == 0 && args.epi == TC_EPI_RESIDUAL &&
+                         args.resid == args.out && args.ldr == args.ldo && !args.out_f16 &&
+                         ((uintptr_t)args.out & 15) == 0 && ((size_t)args.ldo * 4) % 16 == 0;
+  int ksplit = 1;
   if (bn == 0) {  // widest tile that still gives every SM a tile; skinny problems stream W with narrow tiles
-    const int num_m = (args.M + BM - 1) / BM;
     bn = 32;
     for (int cand : {256, 128, 64}) {
       if (num_m * ((args.N + cand - 1) / cand) >= sms) { bn = cand; break; }
+    }
+    if (can_split && bn < 128) {
+      for (int cand : {128, 64, 32}) {
+        if (cand < bn) break;
+        const int t = num_m * ((args.N + cand - 1) / cand);
+        int ks = (sms + t - 1) / t;
+        if (ks > 16) ks = 16;
+        while (ks > 1 && num_kb / ks < 6) --ks;
+        if (t * ks * 10 >= sms * 9) { bn = cand; ksplit = ks; break; }
+      }
     }
   }
   p->bn = bn;
   p->mode = mode;
   p->args = args;
+  p->args.ksplit = ksplit;
   if (!p->args.err) p->args.err = gemm_error_word();
-  const int tiles = ((args.M + BM - 1) / BM) * ((args.N + bn - 1) / bn);
+  const int tiles = ((args.M + BM - 1) / BM) * ((args.N + bn - 1) / bn) * ksplit;
   p->grid = tiles < sms ? tiles : sms;
   if (!make_tmap_2d(&p->tm_a, A, tf32 ? 0 : 1, (uint64_t)args.M, (uint64_t)args.K, lda * es, BM, bk)) return false;
   if (!make_tmap_2d(&p->tm_b, W, tf32 ? 0 : 1, (uint64_t)args.N, (uint64_t)args.K, (uint64_t)args.K * es, bn, bk)) return false;
@@ -502,6 +532,10 @@ bool gemm_plan(GemmPlan *p, int mode, const void *A, size_t lda, const void *W, 
         return false;
       g.tma_kv = 1;
     }
+  }
+  if (g.ksplit > 1 && !g.tma_reduce) {
+    set_error(1, "gemm_plan: split-K needs the TMA reduce-add epilogue", __FILE__, __LINE__);
+    return false;
   }
   return true;
 }

@@ -31,6 +31,10 @@ struct GemmArgs {
   int tma_out = 0, tma_reduce = 0, tma_kv = 0;
   int cache_rows = 0;  // rows per sequence in the caches (tma_kv addressing)
   int n_fastest = 0;   // tile order (set by gemm_plan)
+  // split-K (set by gemm_plan, in-place residual GEMMs only): the K range is cut into `ksplit` slices that are separate
+  // work items; every slice reduce-adds its partial tile into `out` (which already holds the residual), slice 0 adds
+  // the bias.  Lets a skinny GEMM (few output tiles, long K) occupy every SM with wide tiles.
+  int ksplit = 1;
 };
 
 // A prepared launch: tensor maps are encoded once (start-up for the engines, per call for the op-level API).
