@@ -484,8 +484,23 @@ bool gemm_plan(GemmPlan *p, int mode, const void *A, size_t lda, const void *W, 
   int ksplit = 1;
   if (bn == 0) {  // widest tile that still gives every SM a tile; skinny problems stream W with narrow tiles
     bn = 32;
-    for (int cand : {256, 128, 64}) {
-      if (num_m * ((args.N + cand - 1) / cand) >= sms) { bn = cand; break; }
+    if (num_m == 1) {
+      // One row tile (batched decode, M <= 128): HBM/L2-bound.  Every tile re-reads the whole A panel (128 rows) next to
+      // its bn weight rows, and persistent CTAs work in waves, so cost ~ ceil(tiles / SMs) * (128 + bn): 150 tiles
+      // of 32 columns (two waves) lose to 75 tiles of 64.
+      long best = -1;
+      for (int cand : {256, 128, 64, 32}) {
+        const int t = (args.N + cand - 1) / cand;
+        const long cost = (long)((t + sms - 1) / sms) * (BM + cand);
+        if (best < 0 || cost < best) { best = cost; bn = cand; }
+      }
+    } else {
+      // 3xTF32 tiles are shared-memory-bound (operand split + three MMA reads per k-block), which favours wide tiles:
+      // accept a tile count a little under the SM count (144 tiles of 128 beat 288 of 64)
+      const int need = mode == MODE_TF32X3 ? (sms * 9) / 10 : sms;
+      for (int cand : {256, 128, 64}) {
+        if (num_m * ((args.N + cand - 1) / cand) >= need) { bn = cand; break; }
+      }
     }
     if (can_split && bn < 128) {
       for (int cand : {128, 64, 32}) {
