@@ -12,3 +12,9 @@ echo "== ncu full (decode kernel)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:decode_persistent -s 2 -c 1 -f -o gpurun_out/decode_full \
     python scripts/ncu_decode.py 124M 24 > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out/ | tail -12
+echo "== ncu launch lists (batched paths: cfg 3 / 5 / 4 shapes, 2 layers)"
+for w in prefill decode decode_xl; do
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_batch_$w.csv \
+      python scripts/profile_batch.py $w > gpurun_out/profile_batch_$w.log 2>&1
+done
+ls gpurun_out | tr '\n' ' '
