@@ -46,6 +46,64 @@ __device__ __forceinline__ float exp2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+// Row maximum of one 128-key score tile (this thread's query row r lives in TMEM lane r).  DIAG: the tile crosses the
+// causal boundary and keys c > r are masked; every other tile runs the mask-free instantiation (the per-element
+// compare / select pairs were a third of the kernel's instructions when the mask was evaluated for all tiles).
+// Row maximum of one 128-key score tile (this thread's query row r lives in TMEM lane r).  DIAG: the tile crosses the
+// causal boundary and keys c > r are masked; every other tile runs the mask-free instantiation (the per-element
+// compare / select pairs were a third of the kernel's instructions when the mask was evaluated for all tiles).
+// (Measured and rejected: 16-column tcgen05.ld kept one load ahead of the arithmetic -- 2 % slower end to end.)
+template <bool DIAG>
+__device__ __forceinline__ float tile_row_max(uint32_t ts_row, int r) {
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < KT; c += 32) {
+    uint32_t sr[32];
+    tc::tmem_ld32(ts_row + c, sr);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float v = __uint_as_float(sr[i]);
+      if (!DIAG || c + i <= r) mx = fmaxf(mx, v);
+    }
+  }
+  return mx;
+}
+
+// P = 2^(S scale2 - m_new) for one row of the tile, as f16 into the swizzled K-major P buffer; returns the row sum.
+template <bool DIAG>
+__device__ __forceinline__ float tile_row_exp(uint32_t ts_row, int r, float scale2, float m_new, uint32_t sP) {
+  float sum = 0.0f;
+#pragma unroll 1
+  for (int c = 0; c < KT; c += 32) {
+    uint32_t sr[32];
+    tc::tmem_ld32(ts_row + c, sr);
+    tc::tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), scale2, -m_new));
+      float p1 = exp2_poly(fmaf(__uint_as_float(sr[i + 1]), scale2, -m_new));
+      if (DIAG && c + i > r) p0 = 0.0f;
+      if (DIAG && c + i + 1 > r) p1 = 0.0f;
+      sum += p0 + p1;
+      __half2 t = __floats2half2_rn(p0, p1);
+      pk[i >> 1] = *reinterpret_cast<uint32_t *>(&t);
+    }
+    // K-major SWIZZLE_128B: atom = 64 keys; row r at r * 128 bytes; 16-byte chunk index XOR (r % 8)
+    const uint32_t atom = sP + (c >> 6) * TILE_BYTES + r * 128;
+    const int ch0 = (c & 63) >> 3;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t a = atom + ((uint32_t)((ch0 + q) ^ (r & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                   "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                   : "memory");
+    }
+  }
+  return sum;
+}
+
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_qkv, __half *__restrict__ out, int T, int H, int E,
                     int n_bh, unsigned *err) {
@@ -136,18 +194,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_qkv, __half *__restri
       if (!tc::mbar_wait(s_full, j & 1, guard)) { ok = false; break; }
       tc::fence_after_sync();
       const bool diag = (j == qt);  // only the last key tile crosses the causal boundary
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < KT; c += 32) {
-        uint32_t sr[32];
-        tc::tmem_ld32(tS + lane_base + c, sr);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float v = __uint_as_float(sr[i]);
-          if (!diag || c + i <= r) mx = fmaxf(mx, v);
-        }
-      }
+      const float mx = diag ? tile_row_max<true>(tS + lane_base, r) : tile_row_max<false>(tS + lane_base, r);
       const float m_new = fmaxf(m, mx * scale2);
       const float alpha = fast_exp2(m - m_new);
       if (j > 0) {  // fold the previous tile's P V (it was computed against the previous running maximum)
@@ -164,34 +211,8 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_qkv, __half *__restri
       }
       alpha_prev = alpha;
       m = m_new;
-      float sum = 0.0f;
-#pragma unroll 1
-      for (int c = 0; c < KT; c += 32) {
-        uint32_t sr[32];
-        tc::tmem_ld32(tS + lane_base + c, sr);
-        tc::tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), scale2, -m_new));
-          float p1 = exp2_poly(fmaf(__uint_as_float(sr[i + 1]), scale2, -m_new));
-          if (diag && c + i > r) p0 = 0.0f;
-          if (diag && c + i + 1 > r) p1 = 0.0f;
-          sum += p0 + p1;
-          __half2 t = __floats2half2_rn(p0, p1);
-          pk[i >> 1] = *reinterpret_cast<uint32_t *>(&t);
-        }
-        // K-major SWIZZLE_128B: atom = 64 keys; row r at r * 128 bytes; 16-byte chunk index XOR (r % 8)
-        const uint32_t atom = sP + (c >> 6) * TILE_BYTES + r * 128;
-        const int ch0 = (c & 63) >> 3;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t a = atom + ((uint32_t)((ch0 + q) ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
-                       "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
-                       : "memory");
-        }
-      }
+      const float sum = diag ? tile_row_exp<true>(tS + lane_base, r, scale2, m_new, sP)
+                             : tile_row_exp<false>(tS + lane_base, r, scale2, m_new, sP);
       l = fmaf(l, alpha, sum);
       tc::fence_proxy_async_smem();
       tc::fence_before_sync();
