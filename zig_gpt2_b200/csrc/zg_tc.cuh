@@ -33,6 +33,23 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or the hint expires, so
+// a waiting single-lane role (TMA producer, MMA issuer) or epilogue warp does not burn issue slots of the scheduler
+// it shares with the warps doing arithmetic.
+#ifndef ZG_TC_WAIT_HINT_NS
+#define ZG_TC_WAIT_HINT_NS 2000
+#endif
+__device__ __forceinline__ bool mbar_try_sleepy(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"((uint32_t)ZG_TC_WAIT_HINT_NS)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must never hang the GPU.  After ~1 s the CTA-local abort flag (shared) and the
 // sticky global error word are raised; every later wait in the CTA falls through immediately.
 struct Guard {
@@ -44,7 +61,7 @@ static __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity
   asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(aborted) : "r"(g.abort_smem));
   if (aborted) return false;
   const long long t0 = clock64();
-  while (!mbar_try(bar, parity)) {
+  while (!mbar_try_sleepy(bar, parity)) {
     if (clock64() - t0 > 2000000000ll) {
       asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(g.abort_smem), "r"(1u));
       if (g.err_global) atomicExch(g.err_global, 3u);
