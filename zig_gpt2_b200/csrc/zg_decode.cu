@@ -52,7 +52,6 @@ constexpr int MAX_LAYERS = 64;
 constexpr int ATT_CHUNK = 16 * NCW;  // KV rows per attention work item before splitting (one register round)
 constexpr int ATT_SMAX = 8;          // at most this many splits per head; longer contexts loop over rounds inside a split
 constexpr int PROF_MAX = 16384;
-constexpr int GB = 4;            // flagged pairs a thread keeps in flight while gathering an E-vector (E <= 8 * 224)
 constexpr int MAXNE = 16;        // elements of the stream a CTA owns in the reduce phase: ceil(E / SMs) <= 16
 
 struct LayerDesc {
@@ -207,6 +206,9 @@ __device__ __noinline__ u64 spin_word(const u64 *p, unsigned ep, Watchdog wd) {
 }
 // gather n floats (n even) whose words must carry epoch `ep` into shared memory; all loads of a thread are
 // issued before the first check, so the common case costs one L2 round trip; late pairs are re-polled together
+// GB = flagged pairs a thread keeps in flight per pass: 2 cover E <= 896 in one pass (half the code of 4 -- every phase
+// executes its code once, so straight-line code size is instruction-cache misses), 4 cover E <= 1792.
+template <int GB>
 __device__ __forceinline__ void gather_flagged(float *dst_smem, const u64 *src, int n, unsigned ep, Watchdog wd) {
   const int npairs = n >> 1;
 #pragma unroll 1
@@ -756,7 +758,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         const int lg = ne <= 8 ? 3 : 4;              // log2(threads per source)
         const int k = tid & ((1 << lg) - 1);         // element this thread sums
         const int sgrp = tid >> lg, nsg = NCT >> lg;  // sources advance by nsg per pass
-        constexpr int NP = 12;                        // passes: ceil(G / (NCT / 16)) <= 12 for G <= 168
+        // passes over the sources: 8 threads per source (E <= 1024: at most 8 elements per CTA, checked at create) need
+        // ceil(G / 28) <= 6, 16 threads per source need ceil(G / 14) <= 12 (G <= 168); half the unrolled code at 124M / 355M
+        constexpr int NP = NJ <= 8 ? 6 : 12;
         const u64 *col = p.part_f + ent.r0 + k;
         u64 w[NP];
         bool all_ok = true;
@@ -840,7 +844,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
       } else if (mode == M_RESID && att_splits(T, G, p.H) > 1) {
         gather_att_partials(vec, p.attp_f, E, att_splits(T, G, p.H), ep - 1, sm.wd);
       } else {
-        gather_flagged(vec, ent.src, E, ep - 1, sm.wd);
+        gather_flagged<(NJ <= 7 ? 2 : 4)>(vec, ent.src, E, ep - 1, sm.wd);
       }
       ck.at(2);
       consumer_sync();
@@ -970,37 +974,60 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           if (!w2ready) mbar_wait(sm.full0 + 8u * bslot, (fpar >> bslot) & 1u, sm.wd);
           w2ready = false;
           fpar ^= 1u << bslot;
-          // Branch-free and software-pipelined over the (up to NCW) ring units of the batch: unit q + 1 is loaded
-          // while unit q is multiplied; units / rows past the batch re-read a valid row with a zero factor.
+          // Software-pipelined over the ring units of the batch, two units per trip of a ROLLED loop (A / B register
+          // sets ping-pong): unit q + 1 is loaded while unit q is multiplied.  Rows past the batch re-read a valid row
+          // with a zero factor.  Rolled on purpose: a phase runs its code once, so the 7-unit unrolled form was 7 KB of
+          // straight-line code to fetch per layer for 6 units of work.
 #pragma unroll
           for (int k = 0; k < NK; ++k) {
             const int i4 = min(tid + k * NCT, Eq - 1);
             const bool live = tid + k * NCT < Eq;
-            float4 wq[2][4];
+            float4 wa[4], wb[4];
             {
               const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)bslot * slotf);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) wq[0][j] = w4[(j < nbr ? j : 0) * Eq + i4];
+              for (int j = 0; j < 4; ++j) wa[j] = w4[(j < nbr ? j : 0) * Eq + i4];
             }
-#pragma unroll
-            for (int q = 0; q < NCW; ++q) {
-              if (q + 1 < NCW) {
+#pragma unroll 1
+            for (int q = 0; q < nun; q += 2) {
+              {  // load unit q + 1 (clamped) into B
                 const int qn = min(q + 1, nun - 1);
                 int sl = bslot + qn;
                 if (sl >= nslot) sl -= nslot;
                 const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)sl * slotf);
                 const int nvn = nbr - 4 * qn;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) wq[(q + 1) & 1][j] = w4[(j < nvn ? j : 0) * Eq + i4];
+                for (int j = 0; j < 4; ++j) wb[j] = w4[(j < nvn ? j : 0) * Eq + i4];
               }
-              const float4 f4 = *reinterpret_cast<const float4 *>(sm.fbuf + b0 + 4 * min(q, nun - 1));
-              const int nv = (q < nun && live) ? nbr - 4 * q : 0;
-              const float fj[4] = {nv > 0 ? f4.x : 0.0f, nv > 1 ? f4.y : 0.0f, nv > 2 ? f4.z : 0.0f, nv > 3 ? f4.w : 0.0f};
+              {  // multiply unit q from A
+                const float4 f4 = *reinterpret_cast<const float4 *>(sm.fbuf + b0 + 4 * q);
+                const int nv = live ? nbr - 4 * q : 0;
+                const float fj[4] = {nv > 0 ? f4.x : 0.0f, nv > 1 ? f4.y : 0.0f, nv > 2 ? f4.z : 0.0f, nv > 3 ? f4.w : 0.0f};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 w = wq[q & 1][j];
-                o4[k].x = fmaf(fj[j], w.x, o4[k].x); o4[k].y = fmaf(fj[j], w.y, o4[k].y);
-                o4[k].z = fmaf(fj[j], w.z, o4[k].z); o4[k].w = fmaf(fj[j], w.w, o4[k].w);
+                for (int j = 0; j < 4; ++j) {
+                  o4[k].x = fmaf(fj[j], wa[j].x, o4[k].x); o4[k].y = fmaf(fj[j], wa[j].y, o4[k].y);
+                  o4[k].z = fmaf(fj[j], wa[j].z, o4[k].z); o4[k].w = fmaf(fj[j], wa[j].w, o4[k].w);
+                }
+              }
+              {  // load unit q + 2 (clamped) into A
+                const int qn = min(q + 2, nun - 1);
+                int sl = bslot + qn;
+                if (sl >= nslot) sl -= nslot;
+                const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)sl * slotf);
+                const int nvn = nbr - 4 * qn;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) wa[j] = w4[(j < nvn ? j : 0) * Eq + i4];
+              }
+              {  // multiply unit q + 1 from B (zero factors when the batch has no such unit)
+                const int q1 = min(q + 1, nun - 1);
+                const float4 f4 = *reinterpret_cast<const float4 *>(sm.fbuf + b0 + 4 * q1);
+                const int nv = (live && q + 1 < nun) ? nbr - 4 * (q + 1) : 0;
+                const float fj[4] = {nv > 0 ? f4.x : 0.0f, nv > 1 ? f4.y : 0.0f, nv > 2 ? f4.z : 0.0f, nv > 3 ? f4.w : 0.0f};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  o4[k].x = fmaf(fj[j], wb[j].x, o4[k].x); o4[k].y = fmaf(fj[j], wb[j].y, o4[k].y);
+                  o4[k].z = fmaf(fj[j], wb[j].z, o4[k].z); o4[k].w = fmaf(fj[j], wb[j].w, o4[k].w);
+                }
               }
             }
           }
@@ -1083,7 +1110,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
       // GPT.forward(compute_logits = false) still leaves ln_f(x) in state.x (main.zig:189)
       vsel ^= 1;
       float *vec = sm.vec + vsel * E;
-      gather_flagged(vec, p.xnew_f, E, ep, sm.wd);
+      gather_flagged<(NJ <= 7 ? 2 : 4)>(vec, p.xnew_f, E, ep, sm.wd);
       consumer_sync();
       if (warp == 0) {
         float4 xs[NJ];
@@ -1207,7 +1234,8 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
   e->state = *state;
   e->grid = c.sm_count;
   if ((size_t)e->grid < cfg.n_heads || e->grid > 168 || (size_t)e->grid > E ||
-      (4 * E + (size_t)e->grid - 1) / (size_t)e->grid > 64 || (E + (size_t)e->grid - 1) / (size_t)e->grid > MAXNE) {
+      (4 * E + (size_t)e->grid - 1) / (size_t)e->grid > 64 || (E + (size_t)e->grid - 1) / (size_t)e->grid > MAXNE ||
+      (E <= 1024 && (E + (size_t)e->grid - 1) / (size_t)e->grid > 8)) {
     set_error(1, "zg_engine_create: needs n_heads <= SMs <= min(168, n_embed), <= 64 hidden units and <= 16 stream elements per SM",
               __FILE__, __LINE__);
     free(e);
