@@ -149,6 +149,48 @@ def test_long_context_attention_splits(weights_124m):
     orc.close()
 
 
+def test_full_context_1024_tokens_identical_to_oracle(weights_124m):
+    """Maximum size: generate() runs to context_size (main.zig:336).  2-layer slice of the 124M model, a 1000-token
+    prompt, then greedy tokens up to position 1023: every attention split count (1..8) and the multi-round path
+    (more than 112 rows per split) against the oracle, tokens and the last layer's K/V cache."""
+    import zg_oracle as zo
+    from zig_gpt2_b200 import gpt
+
+    cfg = GPTConfig(50257, 1024, 2, 12, 768)
+    model = gpt.gpt_from_numpy(cfg, weights_124m)
+    state = gpt.State(cfg)
+    zo.use_openblas()
+    orc = zo.Model(cfg, weights_124m)
+    rs = np.random.RandomState(11)
+    prompt = rs.randint(0, cfg.vocab_size, 1000)
+    got = model.generate_greedy(prompt, 1024, state)
+    ref = orc.generate_greedy(prompt, 1024)
+    assert np.array_equal(got, ref)
+    k, v = orc.kv(1, 1024)
+    close(model.h[1].k_cache.download(1024 * 768), k.reshape(-1), "k_cache at T=1024")
+    close(model.h[1].v_cache.download(1024 * 768), v.reshape(-1), "v_cache at T=1024")
+    model.close()
+    orc.close()
+
+
+def test_generate_edge_cases(gpu_124m, oracle_124m, gpt_golden):
+    """Ragged ends of generate(): a one-token prompt, a prompt that fills the whole request (no token is sampled, the
+    output is the prompt), and a request longer than the context (refused, nothing written past the buffer)."""
+    model, state = gpu_124m
+    p = [int(t) for t in gpt_golden["prompt"]]
+    one = model.generate_greedy(p[:1], 6, state)
+    assert np.array_equal(one, oracle_124m.generate_greedy(p[:1], 6))
+    same = model.generate_greedy(p, len(p), state)
+    assert np.array_equal(same, np.asarray(p))
+    from zig_gpt2_b200 import lib
+
+    with pytest.raises(lib.ZgError):
+        model.generate_greedy(p, model.config.context_size + 1, state)
+    lib.load().zg_clear_error()
+    again = model.generate_greedy(p, len(p) + 4, state)  # the engine is still usable after a refused call
+    assert np.array_equal(again, oracle_124m.generate_greedy(p, len(p) + 4))
+
+
 @pytest.mark.parametrize("size,n_layer", [("355M", 3), ("774M", 2), ("1.5B", 2)])
 def test_other_widths_truncated_depth(size, n_layer):
     """E = 1024 / 1280 / 1600 (H = 16 / 20 / 25) with the layer count cut down so the oracle stays fast."""
