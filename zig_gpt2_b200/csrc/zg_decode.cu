@@ -106,6 +106,9 @@ struct Clk {
   u64 *buf;
   int i;
   __device__ __forceinline__ void at(int k) {
+#ifdef ZG_PROF_MASK  // experiment: compile in only the hooks whose bit is set
+    if (!((ZG_PROF_MASK >> k) & 1)) return;
+#endif
     if (buf) {
       if (k == 0) {
 #pragma unroll
@@ -115,6 +118,9 @@ struct Clk {
     }
   }
   __device__ __forceinline__ void dump(int kind) {
+#ifdef ZG_PROF_NODUMP
+    return;
+#endif
     if (buf && i + 12 < PROF_MAX) {
 #pragma unroll
       for (int k = 0; k < 12; ++k) {
