@@ -118,6 +118,9 @@ struct Clk {
     }
   }
   __device__ __forceinline__ void dump(int kind) {
+#ifdef ZG_SYNCWARP_END  // experiment: force warp reconvergence at the end of every phase
+    __syncwarp();
+#endif
 #ifdef ZG_PROF_NODUMP
     return;
 #endif
