@@ -159,6 +159,31 @@ __device__ __forceinline__ void poll_backoff() {
 #endif
 }
 
+// Hold-off before the first poll of a phase.  A CTA that finishes a phase early starts to poll the flagged words of the
+// next phase's input at once; 148 CTAs x 224 threads polling the very L2 lines that the slower CTAs are still storing
+// to slows those stores down (measured: 161.6 -> 145.7 us/token at 124M with the hold-offs below, the largest single
+// gain of the round; a back-off BETWEEN polls instead costs detection latency and loses).  The input of the QKV /
+// lm_head phases (P5's output) and of the reduce phase (P4's partials) never arrives sooner than ~1,000 cycles after a
+// CTA is ready for it, so these phases spin on the clock first; the attention consumers (P3) are not held off: the
+// attention CTAs themselves are the late ones there.  Cycles at the SM clock; 0 disables.
+#ifndef ZG_PD_P1
+#define ZG_PD_P1 800
+#endif
+#ifndef ZG_PD_P3
+#define ZG_PD_P3 0
+#endif
+#ifndef ZG_PD_P4
+#define ZG_PD_P4 0
+#endif
+#ifndef ZG_PD_P5
+#define ZG_PD_P5 800
+#endif
+__device__ __forceinline__ void predelay(int cycles) {
+  if (cycles <= 0) return;
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) {}
+}
+
 // ---- flag-in-data exchange ------------------------------------------------------------------------
 __device__ __forceinline__ void st_flag(u64 *p, float v, unsigned ep) {
   const u64 w = ((u64)ep << 32) | (u64)__float_as_uint(v);
@@ -780,6 +805,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         // ceil(G / 28) <= 6, 16 threads per source need ceil(G / 14) <= 12 (G <= 168); half the unrolled code at 124M / 355M
         constexpr int NP = NJ <= 8 ? 6 : 12;
         const u64 *col = p.part_f + ent.r0 + k;
+        predelay(ZG_PD_P5);
         u64 w[NP];
         bool all_ok = true;
 #pragma unroll
@@ -850,6 +876,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
       }
 
       ck.at(1);
+      if (mode == M_RESID) {  // attention CTAs are the late ones
+        if (ZG_PD_P3 > 0 && cta >= p.H * att_splits(T, G, p.H)) predelay(ZG_PD_P3);
+      }
+      else if (mode == M_MLP) predelay(ZG_PD_P4);
+      else if (g != 0) predelay(ZG_PD_P1);
       // ---------------- activation vector -> shared memory -> registers ----------------
       if (g == 0) {  // wte[token] + wpe[pos] (main.zig:179-183), recomputed by every CTA
         const float4 *te = reinterpret_cast<const float4 *>(p.wte + (size_t)tok * E);
