@@ -157,6 +157,10 @@ __device__ __forceinline__ void poll_backoff() {
 #ifdef ZG_POLL_NS
   __nanosleep(ZG_POLL_NS);
 #endif
+#ifdef ZG_POLL_CYCLES  // experiment: clock-spin between polls (finer than nanosleep)
+  const long long t0 = clock64();
+  while (clock64() - t0 < ZG_POLL_CYCLES) {}
+#endif
 }
 
 // Hold-off before the first poll of a phase.  A CTA that finishes a phase early starts to poll the flagged words of the
@@ -177,6 +181,9 @@ __device__ __forceinline__ void poll_backoff() {
 #endif
 #ifndef ZG_PD_P5
 #define ZG_PD_P5 800
+#endif
+#ifndef ZG_PD_AMAX  // before gathering the 148 argmax partials at the end of the lm_head phase
+#define ZG_PD_AMAX 1500
 #endif
 __device__ __forceinline__ void predelay(int cycles) {
   if (cycles <= 0) return;
@@ -1130,6 +1137,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
             st_flag(p.amax_f + 2 * cta, best, ep);
             st_flag(p.amax_f + 2 * cta + 1, __uint_as_float(best_i), ep);
           }
+          predelay(ZG_PD_AMAX);
           float bv = -INFINITY;
           unsigned bi = 0xffffffffu;
           for (int i = tid; i < G; i += 32) {
