@@ -30,6 +30,10 @@
 //     store {epoch : 32 | fp32 bits : 32}; a consumer gathers the vector it needs with 128-bit relaxed loads
 //     and spins until every word carries the epoch of the phase that produces it (the NCCL "LL" idea: the
 //     flag travels inside the datum, so there is nothing to fence);
+//   * a CTA that is early does NOT start polling at once: before the first poll of the QKV / lm_head gather, of the
+//     reduce phase and of the argmax gather it spins on the clock for a hold-off (ZG_PD_*): polling the L2 lines that
+//     the slower CTAs are still storing to slowed those stores -- the largest single loss found in the exchange
+//     (124M: 161 -> 147 us/token);
 //   * the layer table lives in __constant__ memory, so no phase starts with a dependent global load;
 //   * the token loop of generate() runs inside the kernel; each token is written to device memory and to a
 //     pinned host ring, so the host only waits once per call.
