@@ -53,7 +53,10 @@ typedef unsigned long long u64;
 constexpr int NTHREADS = NCT + 32;  // + producer warp
 constexpr int MAXSLOTS = 32;
 constexpr int MAX_LAYERS = 64;
-constexpr int ATT_CHUNK = 16 * NCW;  // KV rows per attention work item before splitting (one register round)
+#ifndef ZG_ATT_ROWS
+#define ZG_ATT_ROWS 16  // rows per warp of an attention work item before the head is split across CTAs
+#endif
+constexpr int ATT_CHUNK = ZG_ATT_ROWS * NCW;  // KV rows per attention work item before splitting (one register round)
 constexpr int ATT_SMAX = 8;          // at most this many splits per head; longer contexts loop over rounds inside a split
 constexpr int PROF_MAX = 16384;
 constexpr int MAXNE = 16;        // elements of the stream a CTA owns in the reduce phase: ceil(E / SMs) <= 16
@@ -794,7 +797,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           const int chunk = (T + S - 1) / S;
           if (chunk <= 4 * NCW) attention_item<4>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep);
           else if (chunk <= 8 * NCW) attention_item<8>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep);
+#ifdef ZG_ATT_MAX8  // experiment: never the 16-row instantiation; longer chunks loop over 8-row rounds
+          else attention_item<8>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep);
+#else
           else attention_item<16>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep);
+#endif
         }
         ck.at(11);
         ck.dump(1);
