@@ -13,8 +13,13 @@ main.zig:198-207).  Prompt fill and W warm-up tokens are untimed; exactly K toke
             prompt and HOST token output (H2D prompt copy, prompt fill, per-token D2H into the pinned ring
             and the final synchronisation are all inside the timed region) -- generated tokens / wall time.
   roofline  achieved = algorithmic bytes per K-step launch / its CUDA-event duration,
-            against MEASURED_PEAKS.json's HBM copy bandwidth.
+            against MEASURED_PEAKS.json's HBM copy bandwidth.  `traffic` is null in the line: DRAM counters cannot be
+            read outside a profiler; the `ncu --set full` capture of the same kernel is profiles/r02_decode_persistent_*.
   cpu_baseline  the oracle (C restatement of the reference + OpenBLAS, every host thread) on cfg 1.
+  configs   full sub-records for the other BASELINE configs, measured in the same run (scripts/bench_configs.py):
+            N = 1: cfg3 (355M prefill 16 x 1024), cfg4 (1.5B batch-64 decode, TF32 and 3xTF32, context 1024 / 512), cfg5;
+            N > 1 (torchrun): cfg5 only -- the 1024 sequences split 1024/N per rank, "scaling": "strong".
+            `--no-configs` skips them (the headline keys are unaffected either way).
 
 `--impl reference` times the reference's CPU path (the oracle port: no Zig toolchain exists to build the
 reference itself) on the host cores for the same K/W.
@@ -24,9 +29,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import re
 import sys
-import threading
 import time
 
 import numpy as np
@@ -37,11 +40,17 @@ sys.path.insert(0, ROOT)
 from zig_gpt2_b200.config import SIZES  # noqa: E402
 from zig_gpt2_b200.weights import synth_for_size  # noqa: E402
 
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+from bench_configs import ClockSampler  # noqa: E402
+
 SIZE = "124M"
 N_PROMPT = 16
 METRIC = "decode_tokens_per_sec"
 UNIT = "tok/s"
 FALLBACK_HBM_GBS = 6650.0
+# the same string on both arms (ours and --impl reference): the driver compares it
+WORKLOAD = (f"GPT-2 {SIZE} random-init fp32, batch-1 greedy decode with KV cache, {N_PROMPT}-token synthetic prompt "
+            "(BASELINE configs[1]); one step = one decoded token")
 
 
 def peaks():
@@ -54,58 +63,6 @@ def peaks():
 
 def prompt_for(rank: int, vocab: int) -> np.ndarray:
     return np.random.Generator(np.random.PCG64(1235 + rank)).integers(0, vocab, N_PROMPT).astype(np.uint64)
-
-
-class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
-
-    def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.max_mhz, self.ok = index, [], set(), None, False
-        self._stop_evt = threading.Event()
-        try:
-            import pynvml
-
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            self.ok = True
-        except Exception:
-            self.ok = False
-
-    def run(self):
-        if not self.ok:
-            return
-        nv = self.nv
-        names = {
-            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
-            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
-            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
-            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
-            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
-        }
-        while not self._stop_evt.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.002)
-
-    def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=2)
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
 
 
 def cpu_reference(steps: int, warmup: int, threads=None):
@@ -149,7 +106,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"GPT-2 {SIZE} random-init fp32, batch-1 greedy decode with KV cache, {N_PROMPT}-token synthetic prompt",
+        "config": {"workload": WORKLOAD,
                    "note": "reference CPU path = line-for-line C port of src/ops.zig+main.zig (no Zig toolchain in this image) + " + blas},
         "cpu_baseline": {"value": tps, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{steps} greedy tokens after a {N_PROMPT}-token prompt and {args.warmup} warm-up tokens"},
@@ -237,24 +194,6 @@ def run_ours(args):
 
     bytes_per_launch = sum(cfg.decode_bytes(seq_len=s + 1) for s in range(first, first + K))
     peak, peak_kind = peaks()
-    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/), scaled to K steps
-    traffic = None
-    try:
-        cap_steps, m = 64, {}
-        with open(os.path.join(ROOT, "profiles", "r01_decode_persistent_ncu_full.csv")) as f:
-            for ln in f:
-                if ln.startswith("#"):
-                    mm = re.search(r"one (\d+)-token launch", ln)
-                    cap_steps = int(mm.group(1)) if mm else cap_steps
-                    continue
-                parts = ln.rstrip("\n").split(",")
-                if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and parts[2]:
-                    m[parts[0]] = (float(parts[2]), parts[1])
-        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-        per_cap = sum(m[k][0] * scale[m[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-        traffic = per_cap / cap_steps * K  # per-token DRAM bytes of the captured launch, scaled to this K-step launch
-    except Exception:
-        traffic = None
     achieved = bytes_per_launch / (float(np.median(trials)) * 1e-3) / 1e9
     value = world * K / (ms_total * 1e-3)
     e2e_value = world * (W + K) / e2e_s
@@ -263,8 +202,7 @@ def run_ours(args):
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": f"GPT-2 {SIZE} random-init fp32, batch-1 greedy decode with KV cache on 1xB200 per sequence "
-                        f"(BASELINE configs[1]); {N_PROMPT}-token synthetic prompt, positions {first}..{first + K - 1} timed",
+            "workload": WORKLOAD, "positions_timed": [first, first + K - 1],
             "sequences": world, "parallelism": f"{world} independent sequence(s), one per GPU, replicated weights, no collective",
             "l2": "inputs larger than L2 (495 MB of weights streamed per token vs 126 MB L2)",
             "trials": args.trials, "timing": "median of trials; CUDA events on the launching stream; max over ranks",
@@ -275,7 +213,8 @@ def run_ours(args):
                         "generated tokens / wall time"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_kind": peak_kind, "kernel": "decode_persistent_kernel",
+                     "traffic": None, "peak_kind": peak_kind, "kernel": "decode_persistent_kernel",
+                     "traffic_note": "not measurable in-run; ncu --set full of this kernel: profiles/r02_decode_persistent_ncu_full.csv",
                      "bytes_per_launch": bytes_per_launch, "frac_of_nominal_8TBs": achieved / 8000.0},
         "clocks": clocks,
         "tokens_tail": [int(t) for t in tokens[-4:]],
@@ -286,12 +225,39 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
                                 "sample": f"{cpu_steps} greedy tokens after a {N_PROMPT}-token prompt + 2 warm-up tokens; "
                                           f"C port of the reference + {blas}"}
+    if not args.no_configs:
+        # free the batch-1 engine before the large configs take the memory
+        model.close()
+        del eng, model, state
+        line["configs"] = other_configs(args, L, lib, rank, local_rank, world, dist)
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def other_configs(args, L, lib, rank, local_rank, world, dist):
+    """BASELINE configs[2..4] as sub-records.  cfg5 shards over the ranks; cfg3 / cfg4 are one-GPU configs and run at N = 1."""
+    import bench_configs as BC
+
+    out = {}
+
+    def guarded(name, fn):
+        try:
+            r = fn()
+            out.update(r if name is None else {name: r})
+        except Exception as e:  # a failing sub-bench must not take the headline line with it
+            lib.load().zg_clear_error()
+            out[name or "cfg"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    guarded(None, lambda: BC.measure_cfg5(L, lib, rank, world, dist, trials=3, device_index=local_rank,
+                                          both_prompt_modes=(world == 1)))
+    if world == 1:
+        guarded("cfg3", lambda: BC.measure_cfg3(L, lib, trials=5, device_index=local_rank))
+        guarded(None, lambda: BC.measure_cfg4(L, lib, trials=3, steps=4, device_index=local_rank))
+    return out
 
 
 def main():
@@ -302,6 +268,7 @@ def main():
     ap.add_argument("--trials", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg3 / cfg4 / cfg5 sub-records")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

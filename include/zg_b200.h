@@ -50,6 +50,11 @@ void zg_clear_error(void);
 int zg_set_stream(void *cuda_stream);
 /* Number of kernels this library has launched since zg_init (bench.py's gpu_launches). */
 unsigned long long zg_launch_count(void);
+/* Number of allocations (cudaMalloc, cudaHostAlloc, CUDA-graph instantiations) and tensor-map encodes since zg_init.
+ * The reference's rule is "no memory allocations at runtime" (README.md): this counter must not move across
+ * zg_engine_generate_greedy / zg_engine_run_steps / zg_engine_forward / zg_batch_forward / zg_batch_run_steps once the
+ * engine exists (tests/test_gpu_model.py, tests/test_gpu_batch.py assert it). */
+unsigned long long zg_alloc_count(void);
 /* CUDA-event stopwatch on the library's stream (bench.py times kernels on the stream they are launched on). */
 int zg_timer_begin(void);
 float zg_timer_end_ms(void); /* records the stop event, synchronises, returns elapsed milliseconds */
@@ -215,6 +220,7 @@ int zg_batch_generate_greedy(zg_batch *e, const size_t *prompts, size_t n_inputs
                              int use_prefill);
 void zg_batch_set_position(zg_batch *e, size_t pos); /* next step attends to cache rows [0, pos] (timing at a given context) */
 void zg_batch_run_steps(zg_batch *e, size_t n_steps); /* n greedy steps from the current position, device resident, async */
+int zg_batch_read_tokens(zg_batch *e, size_t *out_tokens); /* argmax token of every sequence's last step (HOST, n_seqs ids); synchronises */
 const float *zg_batch_k_cache(const zg_batch *e, size_t layer); /* device, [n_seqs, cache_rows, n_embed] */
 const float *zg_batch_v_cache(const zg_batch *e, size_t layer);
 /* the two attention kernels on their own (per-op parity tests) */

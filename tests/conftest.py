@@ -15,6 +15,28 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "slow: takes more than ~30 s on CPU")
 
 
+def _gpu_box_ready() -> str:
+    """'' when the CUDA extension can run here, else why not (a CPU box: skip instead of erroring in every fixture)."""
+    try:
+        from zig_gpt2_b200 import lib
+
+        if lib.load().zg_device_count() == 0:
+            return "no CUDA device"
+    except Exception as e:  # missing .so
+        return f"libzg_b200.so unavailable: {e}"
+    return ""
+
+
+def pytest_collection_modifyitems(config, items):
+    why = None
+    for item in items:
+        if "gpu" in item.keywords:
+            if why is None:
+                why = _gpu_box_ready()
+            if why:
+                item.add_marker(pytest.mark.skip(reason=f"gpu test: {why}"))
+
+
 def assert_tensors_approx_equal(expected, actual, abs_tol=5e-7, rel_tol=6e-4, what=""):
     """The reference's comparator, src/tests.zig:4-20: per element, if |expected| < 1e-3 the
     absolute tolerance is 5e-7, otherwise the relative tolerance is 6e-4."""

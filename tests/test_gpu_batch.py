@@ -330,3 +330,78 @@ def test_batch_other_widths_truncated_depth(size, n_layer):
         assert rel(k[b], kvs[b][0][:n_in]) <= TC_RTOL and rel(v[b], kvs[b][1][:n_in]) <= TC_RTOL
     eng.close()
     model.close()
+
+
+def test_batch_decode_loop_does_not_allocate(small_model):
+    """No allocation, graph instantiation or tensor-map encode once the engine has run its first step (plans are
+    pre-encoded at zg_batch_create, the step graph is captured on first use)."""
+    from zig_gpt2_b200 import lib
+    from zig_gpt2_b200.batch import BatchEngine
+
+    cfg, w, model = small_model
+    L = lib.load()
+    B = 6
+    prompts = np.random.RandomState(3).randint(0, cfg.vocab_size, (B, 5))
+    eng = BatchEngine(model, B, cache_rows=64)
+    eng.generate_greedy(prompts, 12)  # captures the prompt / sampling graphs
+    before = L.zg_alloc_count()
+    eng.generate_greedy(prompts, 40)
+    eng.forward(9, prompts[:, 0], True)
+    eng.set_position(9)
+    eng.run_steps(6)
+    L.zg_sync()
+    lib.check()
+    assert L.zg_alloc_count() == before
+    eng.close()
+
+
+def test_batch_generate_is_repeatable_and_bit_exact_without_split_k(small_model):
+    """Split-K (TMA reduce-adds in arrival order) makes the two in-place residual GEMMs of a decode step
+    run-to-run non-deterministic in the last bits: tokens must still repeat, logits agree to fp32 tolerance.  With
+    ZG_NO_SPLIT_K=1 (a child process: the switch is read once) the logits are bit-identical run to run."""
+    import os
+    import subprocess
+    import sys
+
+    from zig_gpt2_b200.batch import BatchEngine
+
+    cfg, w, model = small_model
+    B, n_in, n_total = 7, 6, 48
+    prompts = np.random.RandomState(21).randint(0, cfg.vocab_size, (B, n_in))
+    eng = BatchEngine(model, B, cache_rows=64)
+    a = eng.generate_greedy(prompts, n_total)
+    la = eng.logits().copy()
+    b = eng.generate_greedy(prompts, n_total)
+    lb = eng.logits().copy()
+    eng.close()
+    assert np.array_equal(a, b)
+    assert rel(la, lb) <= FP32_RTOL
+
+    code = r'''
+import numpy as np, sys
+sys.path.insert(0, ".")
+from zig_gpt2_b200 import gpt, lib
+from zig_gpt2_b200.batch import BatchEngine
+from zig_gpt2_b200.config import GPTConfig
+from zig_gpt2_b200.weights import synth_weights
+lib.init(0)
+cfg = GPTConfig(vocab_size=4099, context_size=160, n_layer=2, n_heads=4, n_embed=256)
+model = gpt.gpt_from_numpy(cfg, synth_weights(cfg, seed=3))
+prompts = np.random.RandomState(21).randint(0, cfg.vocab_size, (7, 6))
+eng = BatchEngine(model, 7, cache_rows=64)
+outs = []
+for _ in range(3):
+    t = eng.generate_greedy(prompts, 48)
+    outs.append((t, eng.logits().copy()))
+assert all(np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1]) for o in outs[1:]), "not bit-exact"
+np.save(sys.argv[1], outs[0][0])
+print("deterministic ok")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "gpurun_out", "_nosplit_tokens.npy")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    r = subprocess.run([sys.executable, "-c", code, out], cwd=root, capture_output=True, text=True, timeout=600,
+                       env={**os.environ, "ZG_NO_SPLIT_K": "1"})
+    assert r.returncode == 0 and "deterministic ok" in r.stdout, r.stderr[-1500:]
+    assert np.array_equal(np.load(out), a)  # and the two reduction orders pick the same tokens
+    os.remove(out)

@@ -213,3 +213,90 @@ def test_other_widths_truncated_depth(size, n_layer):
     close(state.logits.download(), orc.forward(21, int(ref[-1]), True), f"{size} logits")
     model.close()
     orc.close()
+
+
+def test_no_allocation_in_the_decode_loop(gpu_124m, gpt_golden):
+    """README.md "No memory allocations at runtime": once the engine exists, generate / run_steps / forward / sample
+    must not allocate (cudaMalloc, cudaHostAlloc, graph instantiation) or encode a tensor map -- zg_alloc_count is flat."""
+    from zig_gpt2_b200 import lib
+
+    model, state = gpu_124m
+    L = lib.load()
+    p = [int(t) for t in gpt_golden["prompt"]]
+    model.generate_greedy(p, len(p) + 2, state)  # engine exists from here on
+    before, launches = L.zg_alloc_count(), L.zg_launch_count()
+    model.generate_greedy(p, len(p) + 24, state)
+    eng = model.engine(state)
+    L.zg_engine_run_steps(eng, len(p), 8)
+    model.forward(5, 17, True, state)
+    model.sample_greedy(6, 17, state)
+    model.sample(7, 0.8, 17, state, u=0.25)
+    L.zg_sync()
+    lib.check()
+    assert L.zg_alloc_count() == before
+    assert L.zg_launch_count() > launches
+
+
+def test_bad_positions_and_tokens_are_rejected_on_both_paths(gpu_124m):
+    """The op-by-op GPT.forward and the fused engine refuse seq_len outside [1, context_size] and token >= vocab_size
+    with the same sticky error instead of indexing wte / wpe / the caches out of bounds."""
+    from zig_gpt2_b200 import lib
+
+    model, state = gpu_124m
+    cfg = model.config
+    for fwd in (model.forward, model.forward_unfused):
+        for seq_len, token in ((0, 1), (cfg.context_size + 1, 1), (3, cfg.vocab_size), (3, 2**40)):
+            with pytest.raises(lib.ZgError):
+                fwd(seq_len, token, True, state)
+    model.forward(1, 0, True, state)  # the engine still works afterwards
+    assert np.isfinite(state.logits.download()).all()
+
+
+def test_shutdown_and_reinit_contract():
+    """zg_shutdown + zg_init starts clean: per-device lazily created state (tensor-core watchdog word, max-dynamic-smem
+    attributes, timer events, the __constant__ layer-table owner) is forgotten, and results are unchanged.  Runs in a
+    child process so that the module fixtures of this session keep their context."""
+    import subprocess
+    import sys
+
+    code = r'''
+import ctypes as C, numpy as np, sys
+sys.path.insert(0, ".")
+from zig_gpt2_b200 import gpt, lib
+from zig_gpt2_b200.config import GPTConfig
+from zig_gpt2_b200.lib import DeviceBuffer, ZgLinear
+from zig_gpt2_b200.weights import synth_weights
+cfg = GPTConfig(vocab_size=1031, context_size=64, n_layer=2, n_heads=2, n_embed=128)
+w = synth_weights(cfg, seed=5)
+rs = np.random.RandomState(0)
+x, wm = rs.randn(64, 256).astype(np.float32), rs.randn(384, 256).astype(np.float32)
+def once():
+    L = lib.init(0)
+    model, state = gpt.gpt_from_numpy(cfg, w), gpt.State(cfg)
+    toks = model.generate_greedy([1, 2, 3], 20, state)
+    dx, dw, out = DeviceBuffer.from_numpy(x), DeviceBuffer.from_numpy(wm), DeviceBuffer(64 * 384)
+    lin = ZgLinear(256, 384, dw.ptr, None)
+    L.zg_linear_forward_tc(C.byref(lin), dx.ptr, x.size, out.ptr, 2, None, 0, None, 0)
+    lib.check()
+    assert L.zg_tc_error() == 0
+    L.zg_timer_begin(); ms = L.zg_timer_end_ms(); assert ms >= 0
+    y = out.download()
+    model.close()
+    for b in (dx, dw, out): b.free()
+    return toks, y
+t1, y1 = once()
+L = lib.load()
+assert L.zg_shutdown() == 0
+lib._inited_device = None
+t2, y2 = once()
+assert np.array_equal(t1, t2) and np.array_equal(y1, y2)
+assert L.zg_shutdown() == 0 and L.zg_shutdown() == 0   # idempotent
+L.zg_gelu(None, 4)
+assert L.zg_last_error() != 0                             # not initialised: sticky error, no CPU fallback
+print("reinit ok")
+'''
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "reinit ok" in r.stdout, r.stderr[-1500:]

@@ -78,6 +78,15 @@ class BatchEngine:
             raise _lib.ZgError(f"zg_batch_generate_greedy -> {rc}")
         return out.reshape(self.n_seqs, n_total).astype(np.int64)
 
+    def read_tokens(self) -> np.ndarray:
+        """argmax token of every sequence's last sampling step."""
+        out = np.zeros(self.n_seqs, np.uint64)
+        rc = _lib.load().zg_batch_read_tokens(self._h, out.ctypes.data_as(_lib.c_size_p))
+        _lib.check()
+        if rc:
+            raise _lib.ZgError(f"zg_batch_read_tokens -> {rc}")
+        return out.astype(np.int64)
+
     def set_position(self, pos: int) -> None:
         _lib.load().zg_batch_set_position(self._h, pos)
         _lib.check()

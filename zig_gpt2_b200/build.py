@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libzg_b200.so")
 HOST_OUT = os.path.join(HERE, "libzg_host.so")
+CLI_OUT = os.path.join(HERE, "zig_gpt2.bin")  # *.bin is git-ignored; the binary still travels to the GPU box
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -67,6 +68,24 @@ def build_host(force: bool = False) -> str:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("g++ failed building libzg_host.so")
     return HOST_OUT
+
+
+def build_cli(force: bool = False) -> str:
+    """g++ build of the `zig_gpt2 "<prompt>"` program (main.zig:344-371): csrc/host/main.cpp + bpe.cpp linked against
+    libzg_b200.so (found through $ORIGIN at run time).  The CUDA driver library only exists on the GPU box, hence
+    --allow-shlib-undefined."""
+    host_dir = os.path.join(CSRC, "host")
+    srcs = [os.path.join(host_dir, "main.cpp"), os.path.join(host_dir, "bpe.cpp")]
+    deps = srcs + [os.path.join(host_dir, f) for f in os.listdir(host_dir) if f.endswith((".h", ".hpp"))] + [OUT]
+    if not force and os.path.exists(CLI_OUT) and all(os.path.getmtime(p) <= os.path.getmtime(CLI_OUT) for p in deps):
+        return CLI_OUT
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-o", CLI_OUT, *srcs, "-L", HERE, "-l:libzg_b200.so",
+           "-Wl,-rpath,$ORIGIN", "-Wl,--allow-shlib-undefined"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building zig_gpt2.bin")
+    return CLI_OUT
 
 
 if __name__ == "__main__":

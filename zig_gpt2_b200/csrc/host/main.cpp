@@ -1,7 +1,9 @@
 // main.cpp -- `zig_gpt2 "<prompt>"` (main.zig:344-371) over the CUDA shim.
-//   zig_gpt2 [--size 124M] [--model-dir models/124M] [--device 0] [--greedy] [--temp 0.8] [--seed N]
-//            [--max-tokens N] "<prompt>"
-// Build: g++ -O2 -std=c++17 main.cpp bpe.cpp -L../.. -lzg_b200 -o zig_gpt2   
+//   zig_gpt2 [--size 124M | --config V,C,L,H,E] [--model-dir models/124M] [--device 0] [--greedy] [--temp 0.8]
+//            [--seed N] [--max-tokens N] "<prompt>"
+// Built by zig_gpt2_b200/build.py:build_cli (g++ main.cpp bpe.cpp + libzg_b200.so) -> zig_gpt2_b200/zig_gpt2.bin;
+// tests/test_gpu_cli.py runs it end to end against the oracle.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
@@ -10,7 +12,7 @@
 #include "gpt2.hpp"
 
 int main(int argc, char **argv) {
-  std::string size = "124M", model_dir, prompt;
+  std::string size = "124M", model_dir, prompt, custom;
   int device = 0;
   bool greedy = false;
   float temp = 0.8f;  // main.zig:345
@@ -23,6 +25,7 @@ int main(int argc, char **argv) {
       return argv[++i];
     };
     if (a == "--size") size = next("--size");
+    else if (a == "--config") custom = next("--config");  // vocab,context,layers,heads,embed (synthetic test models)
     else if (a == "--model-dir") model_dir = next("--model-dir");
     else if (a == "--device") device = atoi(next("--device"));
     else if (a == "--greedy") greedy = true;
@@ -37,7 +40,14 @@ int main(int argc, char **argv) {
   }
   if (model_dir.empty()) model_dir = "models/" + size;
   zgh::GPTConfig config;
-  if (!zgh::config_for_size(size, &config)) { std::cerr << "unknown size " << size << "\n"; return 2; }
+  if (!custom.empty()) {
+    unsigned long v[5];
+    if (sscanf(custom.c_str(), "%lu,%lu,%lu,%lu,%lu", &v[0], &v[1], &v[2], &v[3], &v[4]) != 5) {
+      std::cerr << "--config wants vocab,context,layers,heads,embed\n";
+      return 2;
+    }
+    config = {v[0], v[1], v[2], v[3], v[4]};
+  } else if (!zgh::config_for_size(size, &config)) { std::cerr << "unknown size " << size << "\n"; return 2; }
 
   zgh::Encoder encoder;  // load_encoder, main.zig:316-320
   if (!encoder.init_from_files(model_dir + "/encoder.json", model_dir + "/byte_encoder.json")) {

@@ -370,10 +370,10 @@ bool attn_prefill_plan(AttnPrefillPlan *p, const void *qkv_f16, void *out_f16, i
 }
 
 void attn_init_attrs() {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned attr_gen = 0;  // per device: redone after every zg_init
+  if (attr_gen != ctx().generation) {
     ZG_CUDA(cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    attr_set = true;
+    attr_gen = ctx().generation;
   }
 }
 

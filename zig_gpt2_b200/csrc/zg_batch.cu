@@ -26,9 +26,11 @@ typedef unsigned long long u64;
 // x[m,:] = wte[tok(m)] + wpe[pos(m)]  (main.zig:179-183).  decode: one row per sequence, pos = *pos_dev;
 // prefill: row m = b*T + t, pos = t.
 __global__ void embed_rows_kernel(const float *__restrict__ wte, const float *__restrict__ wpe,
-                                  const u64 *__restrict__ tok, int T, const int *pos_dev, int E, float *__restrict__ x) {
+                                  const u64 *__restrict__ tok, int T, const int *pos_dev, int E, int V,
+                                  float *__restrict__ x) {
   const int m = blockIdx.x;
-  const size_t token = (size_t)tok[m];
+  size_t token = (size_t)tok[m];
+  if (token >= (size_t)V) token = 0;  // host-supplied ids never index wte out of bounds (same clamp as the batch-1 engine)
   const int pos = pos_dev ? *pos_dev : (m % T);
   const float4 *a = reinterpret_cast<const float4 *>(wte + token * E), *p = reinterpret_cast<const float4 *>(wpe + (size_t)pos * E);
   float4 *o = reinterpret_cast<float4 *>(x + (size_t)m * E);
@@ -189,6 +191,7 @@ struct zg_batch {
   float *px = nullptr, *plast = nullptr;
   __half *ph = nullptr, *pqkv = nullptr, *patt = nullptr, *ph4 = nullptr, *plast16 = nullptr;
   u64 *tok = nullptr, *hist = nullptr, *prompts = nullptr, *ptok = nullptr;
+  u64 *hist_host = nullptr;  // pinned [hist_cap][B]: generate() reads the token history back through it
   size_t hist_cap = 0;
   int *pos = nullptr;
   // plans
@@ -288,7 +291,7 @@ void enqueue_step(zg_batch *e, bool from_prompt, int n_inputs, bool with_logits)
     load_prompt_tokens_kernel<<<(B + 127) / 128, 128, 0, s>>>(e->prompts, n_inputs, e->tok, e->hist, B, e->pos);
     ZG_LAUNCH_CHECK();
   }
-  embed_rows_kernel<<<B, 128, 0, s>>>(e->wte, e->wpe, e->tok, 1, e->pos, E, e->x);
+  embed_rows_kernel<<<B, 128, 0, s>>>(e->wte, e->wpe, e->tok, 1, e->pos, E, V, e->x);
   ZG_LAUNCH_CHECK();
   for (size_t l = 0; l < e->layers.size(); ++l) {
     const LayerW &w = e->layers[l];
@@ -315,7 +318,7 @@ void enqueue_step(zg_batch *e, bool from_prompt, int n_inputs, bool with_logits)
 void enqueue_prefill(zg_batch *e, int T, bool with_logits) {
   cudaStream_t s = ctx().stream;
   const int B = e->B, E = (int)e->cfg.n_embed, M = B * T;
-  embed_rows_kernel<<<M, 128, 0, s>>>(e->wte, e->wpe, e->ptok, T, nullptr, E, e->px);
+  embed_rows_kernel<<<M, 128, 0, s>>>(e->wte, e->wpe, e->ptok, T, nullptr, E, (int)e->cfg.vocab_size, e->px);
   ZG_LAUNCH_CHECK();
   for (size_t l = 0; l < e->layers.size(); ++l) {
     const LayerW &w = e->layers[l];
@@ -338,12 +341,15 @@ bool capture(zg_batch *e, cudaGraphExec_t *exec, bool from_prompt, int n_inputs,
   cudaStream_t s = ctx().stream;
   cudaGraph_t g = nullptr;
   if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return false;
+  ctx().capturing = true;  // recorded, not executed: zg_launch_count counts the replays
   enqueue_step(e, from_prompt, n_inputs, with_logits);
+  ctx().capturing = false;
   if (cudaStreamEndCapture(s, &g) != cudaSuccess || !g) {
     cudaGetLastError();
     return false;
   }
   const cudaError_t r = cudaGraphInstantiate(exec, g, 0);
+  note_alloc();  // start-up work (first generate / run_steps of an engine), never repeated per step
   cudaGraphDestroy(g);
   return r == cudaSuccess;
 }
@@ -411,6 +417,12 @@ zg_batch *zg_batch_create(const zg_gpt *gpt, size_t n_seqs, size_t cache_rows, s
   e->hist_cap = (size_t)c.context_size;
   e->hist = balloc<u64>(e, e->hist_cap * B);
   e->prompts = balloc<u64>(e, B * (size_t)c.context_size);
+  if (cudaHostAlloc(&e->hist_host, e->hist_cap * B * sizeof(u64), cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    e->hist_host = nullptr;
+    set_error(1, "zg_batch_create: pinned token history", __FILE__, __LINE__);
+  }
+  note_alloc();
   e->pos = balloc<int>(e, 4);
   if (e->f16_prefill) {
     const size_t M = B * max_prompt;
@@ -446,6 +458,7 @@ void zg_batch_destroy(zg_batch *e) {
   if (e->graph_sample) cudaGraphExecDestroy(e->graph_sample);
   if (e->graph_prompt) cudaGraphExecDestroy(e->graph_prompt);
   for (void *p : e->owned) zg_free(p);
+  if (e->hist_host) cudaFreeHost(e->hist_host);
   delete e;
 }
 
@@ -548,11 +561,10 @@ int zg_batch_generate_greedy(zg_batch *e, const size_t *prompts, size_t n_inputs
   }
   e->host_pos = (int)n_total;
   // history [n_total][B] -> out [B][n_total]
-  std::vector<u64> tmp((size_t)B * n_total);
-  ZG_CUDA(cudaMemcpyAsync(tmp.data(), e->hist, tmp.size() * sizeof(u64), cudaMemcpyDeviceToHost, s));
+  ZG_CUDA(cudaMemcpyAsync(e->hist_host, e->hist, (size_t)B * n_total * sizeof(u64), cudaMemcpyDeviceToHost, s));
   ZG_CUDA(cudaStreamSynchronize(s));
   for (size_t st = 0; st < n_total; ++st)
-    for (int b = 0; b < B; ++b) out_tokens[(size_t)b * n_total + st] = (size_t)tmp[st * B + b];
+    for (int b = 0; b < B; ++b) out_tokens[(size_t)b * n_total + st] = (size_t)e->hist_host[st * B + b];
   if (zg_tc_error()) set_error(1, "tensor-core kernel watchdog tripped", __FILE__, __LINE__);
   return zg_last_error();
 }
@@ -582,6 +594,15 @@ void zg_batch_set_position(zg_batch *e, size_t pos) {
   set_pos_kernel<<<1, 1, 0, ctx().stream>>>(e->pos, (int)pos, 0);
   ZG_LAUNCH_CHECK();
   e->host_pos = (int)pos;
+}
+// The token every sequence produced in its last sampling step (argmax of its logits): n_seqs ids, HOST.  Synchronises.
+int zg_batch_read_tokens(zg_batch *e, size_t *out_tokens) {
+  if (!require_ready("zg_batch_read_tokens")) return 1;
+  cudaStream_t s = ctx().stream;
+  ZG_CUDA(cudaMemcpyAsync(e->hist_host, e->tok, (size_t)e->B * sizeof(u64), cudaMemcpyDeviceToHost, s));
+  ZG_CUDA(cudaStreamSynchronize(s));
+  for (int b = 0; b < e->B; ++b) out_tokens[b] = (size_t)e->hist_host[b];
+  return zg_last_error();
 }
 const float *zg_batch_k_cache(const zg_batch *e, size_t layer) { return e->k_cache + layer * e->layer_stride; }
 const float *zg_batch_v_cache(const zg_batch *e, size_t layer) { return e->v_cache + layer * e->layer_stride; }

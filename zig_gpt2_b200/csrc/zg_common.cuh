@@ -20,6 +20,9 @@ struct Context {
   int last_error = 0;
   char last_error_msg[256] = {0};
   unsigned long long launches = 0;
+  unsigned generation = 0;           // bumped by every successful zg_init: per-device lazily initialised state keys on it
+  unsigned long long alloc_calls = 0;  // cudaMalloc / cudaHostAlloc / tensor-map encodes since zg_init (zg_alloc_count)
+  bool capturing = false;              // a CUDA graph is being captured: launches are recorded, not executed
   // start-up scratch
   size_t *idx_staging = nullptr;  // device, for Embedding.forward with many indices
   size_t idx_staging_cap = 0;
@@ -31,6 +34,11 @@ struct Context {
 Context &ctx();
 void set_error(int code, const char *what, const char *file, int line);
 bool require_ready(const char *fn);
+// Called by zg_shutdown before the context is torn down: frees / forgets lazily created per-device state (watchdog
+// words, timer events, which engine owns the __constant__ layer table), so that zg_shutdown + zg_init -- on the same
+// or on another device -- starts clean.
+void register_shutdown_hook(void (*fn)());
+inline void note_alloc() { ctx().alloc_calls++; }
 
 #define ZG_CUDA(expr)                                                   \
   do {                                                                  \
@@ -40,7 +48,7 @@ bool require_ready(const char *fn);
 
 #define ZG_LAUNCH_CHECK()                                               \
   do {                                                                  \
-    ::zg::ctx().launches++;                                             \
+    if (!::zg::ctx().capturing) ::zg::ctx().launches++;                 \
     cudaError_t _e = cudaGetLastError();                                \
     if (_e != cudaSuccess) ::zg::set_error((int)_e, "kernel launch", __FILE__, __LINE__); \
   } while (0)

@@ -54,12 +54,28 @@ constexpr int NTHREADS = NCT + 32;  // + producer warp
 constexpr int MAXSLOTS = 32;
 constexpr int MAX_LAYERS = 64;
 #ifndef ZG_ATT_ROWS
-#define ZG_ATT_ROWS 16  // rows per warp of an attention work item before the head is split across CTAs
+#define ZG_ATT_ROWS (ZG_NCW > 7 ? 8 : 16)  // rows per warp of an attention work item before the head is split across CTAs
 #endif
 constexpr int ATT_CHUNK = ZG_ATT_ROWS * NCW;  // KV rows per attention work item before splitting (one register round)
-constexpr int ATT_SMAX = 8;          // at most this many splits per head; longer contexts loop over rounds inside a split
+#ifndef ZG_ATT_SMAX
+#define ZG_ATT_SMAX 8
+#endif
+constexpr int ATT_SMAX = ZG_ATT_SMAX;          // at most this many splits per head; longer contexts loop over rounds inside a split
 constexpr int PROF_MAX = 16384;
+// sm.red layout: per-warp attention (m, l), per-warp argmax (value, index), the reduced token
+constexpr int RED_M = 0, RED_L = 16, RED_B = 32, RED_I = 48, RED_TOK = 64, RED_FLOATS = 96;
+static_assert(NCW <= 16, "sm.red and sm.part hold 16 per-warp entries");
 constexpr int MAXNE = 16;        // elements of the stream a CTA owns in the reduce phase: ceil(E / SMs) <= 16
+// Replicas of the broadcast vectors of the flagged exchange (the stream after each half of a block, the attention
+// output, the argmax partials).  Every one of the G CTAs gathers these vectors at the same moment, so with one copy
+// the 48 L2 lines of a 768-element vector serve 148 requests each per poll round (and the producers' stores queue
+// behind them); a producer writes XREP copies (lanes 0..XREP-1 of the 8-lane group that holds a finished row) and CTA
+// c reads copy c mod XREP.  q and the new K/V row are read by the attention CTAs only and are not replicated.
+#ifndef ZG_XREP
+#define ZG_XREP 1
+#endif
+constexpr int XREP = ZG_XREP;
+static_assert(XREP >= 1 && XREP <= 8, "one replica per lane of an 8-lane row group");
 
 struct LayerDesc {
   const float *wq, *c1q, *c2q;    // LN1-folded c_attn: W diag(g) [3E,E], its row sums, W b + bias
@@ -198,10 +214,34 @@ __device__ __forceinline__ void predelay(int cycles) {
   while (clock64() - t0 < cycles) {}
 }
 
+// Transcendentals of the attention softmax and of GELU.  Default: the SFU forms (ex2.approx / rcp.approx, relative error
+// ~1e-6: two orders of magnitude inside the 1e-4 tolerance the per-op comparator allows, tests/test_gpu_model.py), because
+// libm-accurate expf / tanhf / division are 20-40 dependent instructions each ON the critical path of a phase that runs
+// once per layer (the final combine of the attention phase alone went from ~720 to ~300 cycles).  -DZG_EXACT_MATH
+// restores the libm forms.  GELU: 0.5 x (1 + tanh u) == x / (1 + e^(-2u)) with u = x 0.7978845608 (1 + 0.044715 x^2), ops.zig:225.
+#ifdef ZG_EXACT_MATH
+__device__ __forceinline__ float fexp(float x) { return expf(x); }
+__device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
+__device__ __forceinline__ float gelu_dec(float x) { return gelu_ref(x); }
+#else
+__device__ __forceinline__ float fexp(float x) { return __expf(x); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float gelu_dec(float x) {
+  const float u = x * 0.7978845608f * (1.0f + 0.044715f * x * x);
+  return __fdividef(x, 1.0f + __expf(-2.0f * u));
+}
+#endif
+
 // ---- flag-in-data exchange ------------------------------------------------------------------------
 __device__ __forceinline__ void st_flag(u64 *p, float v, unsigned ep) {
   const u64 w = ((u64)ep << 32) | (u64)__float_as_uint(v);
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+// The new K/V row goes to the cache with a gpu-scope relaxed store: other CTAs read it with ld.global.cg in LATER steps
+// of the same launch (this step's readers take it from the flagged exchange), ordered only by the chain of flagged
+// words in between -- a morally strong store keeps that well-defined in the PTX memory model.
+__device__ __forceinline__ void st_cache(float *p, float v) {
+  asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 __device__ __forceinline__ ulonglong2 ld_pair(const u64 *p) {
   ulonglong2 v;
@@ -265,21 +305,21 @@ __device__ __noinline__ u64 spin_word(const u64 *p, unsigned ep, Watchdog wd) {
 // issued before the first check, so the common case costs one L2 round trip; late pairs are re-polled together
 // GB = flagged pairs a thread keeps in flight per pass: 2 cover E <= 896 in one pass (half the code of 4 -- every phase
 // executes its code once, so straight-line code size is instruction-cache misses), 4 cover E <= 1792.
-template <int GB>
+template <int GB, int NT = NCT>
 __device__ __forceinline__ void gather_flagged(float *dst_smem, const u64 *src, int n, unsigned ep, Watchdog wd) {
   const int npairs = n >> 1;
 #pragma unroll 1
-  for (int base = 0; base < npairs; base += GB * NCT) {
+  for (int base = 0; base < npairs; base += GB * NT) {
     ulonglong2 v[GB];
     bool all_ok = true;
 #pragma unroll
     for (int j = 0; j < GB; ++j) {
-      const int idx = base + j * NCT + (int)threadIdx.x;
+      const int idx = base + j * NT + (int)threadIdx.x;
       if (idx < npairs) v[j] = ld_pair(src + 2 * idx);
     }
 #pragma unroll
     for (int j = 0; j < GB; ++j) {
-      const int idx = base + j * NCT + (int)threadIdx.x;
+      const int idx = base + j * NT + (int)threadIdx.x;
       if (idx < npairs) all_ok = all_ok && pair_ok(v[j], ep);
     }
     if (!all_ok && !wd_tripped(wd)) {
@@ -289,12 +329,12 @@ __device__ __forceinline__ void gather_flagged(float *dst_smem, const u64 *src, 
         all_ok = true;
 #pragma unroll
         for (int j = 0; j < GB; ++j) {
-          const int idx = base + j * NCT + (int)threadIdx.x;
+          const int idx = base + j * NT + (int)threadIdx.x;
           if (idx < npairs && !pair_ok(v[j], ep)) v[j] = ld_pair(src + 2 * idx);
         }
 #pragma unroll
         for (int j = 0; j < GB; ++j) {
-          const int idx = base + j * NCT + (int)threadIdx.x;
+          const int idx = base + j * NT + (int)threadIdx.x;
           if (idx < npairs) all_ok = all_ok && pair_ok(v[j], ep);
         }
         if (!all_ok && clock64() - t0 > WATCHDOG_CYCLES) {
@@ -305,8 +345,70 @@ __device__ __forceinline__ void gather_flagged(float *dst_smem, const u64 *src, 
     }
 #pragma unroll
     for (int j = 0; j < GB; ++j) {
-      const int idx = base + j * NCT + (int)threadIdx.x;
+      const int idx = base + j * NT + (int)threadIdx.x;
       if (idx < npairs) reinterpret_cast<float2 *>(dst_smem)[idx] = make_float2(lo_f(v[j].x), lo_f(v[j].y));
+    }
+  }
+}
+// The same gather with ONE 256-bit load per thread and pass (LDG.E.ENL2.256.STRONG.GPU: four flagged words = one 32-byte
+// sector).  A thread's strong loads do not overlap well -- every additional flagged load per thread and pass was measured
+// at +100..200 cycles on the gather's critical path (one polling warp with 12 pairs per lane: 207 us/token against 144.5
+// for seven warps with 2 pairs per lane) -- so the widest load wins: E = 768 needs 192 loads, one per thread.
+struct Quad { u64 a, b, c, d; };
+__device__ __forceinline__ Quad ld_quad(const u64 *p) {
+  Quad v;
+  asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(p) : "memory");
+  return v;
+}
+#ifdef ZG_NOWAIT
+__device__ __forceinline__ bool quad_ok(const Quad &, unsigned) { return true; }
+#else
+__device__ __forceinline__ bool quad_ok(const Quad &v, unsigned ep) {
+  return (unsigned)(v.a >> 32) == ep && (unsigned)(v.b >> 32) == ep && (unsigned)(v.c >> 32) == ep && (unsigned)(v.d >> 32) == ep;
+}
+#endif
+template <int GB>
+__device__ __forceinline__ void gather_flagged256(float *dst_smem, const u64 *src, int n, unsigned ep, Watchdog wd) {
+  const int nquads = n >> 2;  // n % 4 == 0 (n_embed % 8 == 0 is checked at create)
+#pragma unroll 1
+  for (int base = 0; base < nquads; base += GB * NCT) {
+    Quad v[GB];
+    bool all_ok = true;
+#pragma unroll
+    for (int j = 0; j < GB; ++j) {
+      const int idx = base + j * NCT + (int)threadIdx.x;
+      if (idx < nquads) v[j] = ld_quad(src + 4 * idx);
+    }
+#pragma unroll
+    for (int j = 0; j < GB; ++j) {
+      const int idx = base + j * NCT + (int)threadIdx.x;
+      if (idx < nquads) all_ok = all_ok && quad_ok(v[j], ep);
+    }
+    if (!all_ok && !wd_tripped(wd)) {
+      const long long t0 = clock64();
+      do {
+        all_ok = true;
+#pragma unroll
+        for (int j = 0; j < GB; ++j) {
+          const int idx = base + j * NCT + (int)threadIdx.x;
+          if (idx < nquads && !quad_ok(v[j], ep)) v[j] = ld_quad(src + 4 * idx);
+        }
+#pragma unroll
+        for (int j = 0; j < GB; ++j) {
+          const int idx = base + j * NCT + (int)threadIdx.x;
+          if (idx < nquads) all_ok = all_ok && quad_ok(v[j], ep);
+        }
+        if (!all_ok && clock64() - t0 > WATCHDOG_CYCLES) {
+          wd_trip(wd, 3u);
+          break;
+        }
+      } while (!all_ok);
+    }
+#pragma unroll
+    for (int j = 0; j < GB; ++j) {
+      const int idx = base + j * NCT + (int)threadIdx.x;
+      if (idx < nquads)
+        reinterpret_cast<float4 *>(dst_smem)[idx] = make_float4(lo_f(v[j].a), lo_f(v[j].b), lo_f(v[j].c), lo_f(v[j].d));
     }
   }
 }
@@ -336,7 +438,7 @@ struct Smem {
                  // may already be gathering the next vector while a slow one still reads the current one
   float *fbuf;   // 64: GELU outputs of the hidden units this CTA owns
   float *part;   // NCW * hd attention partial outputs
-  float *red;    // 64
+  float *red;    // RED_FLOATS
   uint32_t full0, empty0;  // shared addresses of mbarrier arrays
   Watchdog wd;             // sticky global error word + CTA-local tripped flag
 };
@@ -382,7 +484,7 @@ __device__ __forceinline__ float packed_reduce(float (&v)[N], int lane) {
 #endif
 template <int AR>
 __device__ ZG_ATT_INLINE void attention_item(const DecodeParams &p, const Smem &sm, int l, int h, int s, int S, int T,
-                                               unsigned ep_in, unsigned ep_out) {
+                                               unsigned ep_in, unsigned ep_out, Clk &ck) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int hd = 64;
   constexpr int LG = AR == 16 ? 4 : AR == 8 ? 3 : 2;  // log2 AR
@@ -407,6 +509,7 @@ __device__ ZG_ATT_INLINE void attention_item(const DecodeParams &p, const Smem &
       vv[u] = __ldcg(reinterpret_cast<const float2 *>(vh + (size_t)tt * E) + lane);
     }
   }
+  ck.at(1);
   ulonglong2 qw = ld_pair(p.q_f + h * hd + 2 * lane);
   ulonglong2 kw = qw, vw = qw;
   if (has_new) {
@@ -418,6 +521,7 @@ __device__ ZG_ATT_INLINE void attention_item(const DecodeParams &p, const Smem &
     if (!pair_ok(kw, ep_in)) kw = spin_pair(p.kvn_f + h * hd + 2 * lane, ep_in, sm.wd);
     if (!pair_ok(vw, ep_in)) vw = spin_pair(p.kvn_f + E + h * hd + 2 * lane, ep_in, sm.wd);
   }
+  ck.at(2);
   const float2 qv = make_float2(lo_f(qw.x), lo_f(qw.y));
   const float2 knew = make_float2(lo_f(kw.x), lo_f(kw.y)), vnew = make_float2(lo_f(vw.x), lo_f(vw.y));
   // row index (within a round) whose score this lane holds after the packed butterfly: the top LG lane bits
@@ -449,8 +553,8 @@ __device__ ZG_ATT_INLINE void attention_item(const DecodeParams &p, const Smem &
     const float sc = packed_reduce<AR>(a, lane) * scale;  // score of row t + myu * NCW
     const bool valid = (t + myu * NCW) < t1;
     const float mnew = fmaxf(mw, warp_max_redux(valid ? sc : -INFINITY));
-    const float corr = (mw == -INFINITY) ? 0.0f : expf(mw - mnew);
-    const float pt = valid ? expf(sc - mnew) : 0.0f;
+    const float corr = (mw == -INFINITY) ? 0.0f : fexp(mw - mnew);
+    const float pt = valid ? fexp(sc - mnew) : 0.0f;
     lw *= corr;
     acc.x *= corr;
     acc.y *= corr;
@@ -463,27 +567,31 @@ __device__ ZG_ATT_INLINE void attention_item(const DecodeParams &p, const Smem &
     }
     mw = mnew;
   }
+  ck.at(3);
   po[warp * hd + 2 * lane] = acc.x;
   po[warp * hd + 2 * lane + 1] = acc.y;
   if (lane == 0) {
-    sm.red[16 + warp] = mw;
-    sm.red[24 + warp] = lw;
+    sm.red[RED_M + warp] = mw;
+    sm.red[RED_L + warp] = lw;
   }
   consumer_sync();
+  ck.at(4);
   if (tid < hd) {
     float m = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < NCW; ++w) m = fmaxf(m, sm.red[16 + w]);
+    for (int w = 0; w < NCW; ++w) m = fmaxf(m, sm.red[RED_M + w]);
     float lsum = 0.0f, o = 0.0f;
 #pragma unroll
     for (int w = 0; w < NCW; ++w) {
-      const float mwv = sm.red[16 + w];
-      const float sc = (mwv == -INFINITY) ? 0.0f : expf(mwv - m);
-      lsum = fmaf(sm.red[24 + w], sc, lsum);
+      const float mwv = sm.red[RED_M + w];
+      const float sc = (mwv == -INFINITY) ? 0.0f : fexp(mwv - m);
+      lsum = fmaf(sm.red[RED_L + w], sc, lsum);
       o = fmaf(po[w * hd + tid], sc, o);
     }
     if (S == 1) {
-      st_flag(p.att_f + h * hd + tid, o / lsum, ep_out);
+      const float ov = fdiv(o, lsum);
+#pragma unroll
+      for (int rep = 0; rep < XREP; ++rep) st_flag(p.att_f + (size_t)rep * E + h * hd + tid, ov, ep_out);
     } else {  // flash-decoding partial (m, l, unnormalised o): every consumer of the attention output combines the S
               // partials of a head itself while it gathers the vector (gather_att_partials), so no fence, no counter
       u64 *mine = p.attp_f + ((size_t)h * ATT_SMAX + s) * (hd + 2);
@@ -543,13 +651,13 @@ __device__ ZG_GAP_INLINE void gather_att_partials(float *dst_smem, const u64 *at
 #pragma unroll
     for (int q = 0; q < ATT_SMAX; ++q) {
       if (q < S) {
-        const float sc = expf(lo_f(ml[q].x) - M);
+        const float sc = fexp(lo_f(ml[q].x) - M);
         lsum = fmaf(lo_f(ml[q].y), sc, lsum);
         o0 = fmaf(lo_f(ov[q].x), sc, o0);
         o1 = fmaf(lo_f(ov[q].y), sc, o1);
       }
     }
-    reinterpret_cast<float2 *>(dst_smem)[idx] = make_float2(o0 / lsum, o1 / lsum);
+    reinterpret_cast<float2 *>(dst_smem)[idx] = make_float2(fdiv(o0, lsum), fdiv(o1, lsum));
   }
 }
 
@@ -643,7 +751,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
   sm.fbuf = sm.vec + 2 * E;
   sm.part = sm.fbuf + 64;
   sm.red = sm.part + NCW * p.hd;
-  PhaseEnt *table = reinterpret_cast<PhaseEnt *>(sm.red + 64);
+  PhaseEnt *table = reinterpret_cast<PhaseEnt *>(sm.red + RED_FLOATS);
   sm.full0 = smem_u32(mbar_store);
   sm.empty0 = smem_u32(mbar_store + MAXSLOTS);
   sm.wd.err_global = p.err;
@@ -669,16 +777,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
     e.r0 = 0; e.nrows = 0; e.mode = M_ATTN;
     int N = 0, rot = 0;
     if (g == L5) {
-      e.W = p.wte_f; e.bias = p.c2h; e.c1 = p.c1h; e.src = p.xnew_f; e.mode = M_LMHEAD; N = p.V;
+      e.W = p.wte_f; e.bias = p.c2h; e.c1 = p.c1h; e.src = p.xnew_f + (size_t)(cta % XREP) * E; e.mode = M_LMHEAD; N = p.V;
     } else {
       const LayerDesc &ld = c_layers[l];
       rot = phase_rot(l, ph, G);
       if (ph == 0) {
-        e.W = ld.wq; e.bias = ld.c2q; e.c1 = ld.c1q; e.src = p.xnew_f; e.mode = M_QKV; N = 3 * E;
+        e.W = ld.wq; e.bias = ld.c2q; e.c1 = ld.c1q; e.src = p.xnew_f + (size_t)(cta % XREP) * E; e.mode = M_QKV; N = 3 * E;
       } else if (ph == 2) {
-        e.W = ld.w_proj; e.bias = ld.b_proj; e.src = p.att_f; e.mode = M_RESID; N = E;
+        e.W = ld.w_proj; e.bias = ld.b_proj; e.src = p.att_f + (size_t)(cta % XREP) * E; e.mode = M_RESID; N = E;
       } else if (ph == 3) {
-        e.W = ld.wfc; e.W2 = ld.w2t; e.bias = ld.c2f; e.c1 = ld.c1f; e.src = p.xres_f; e.mode = M_MLP; N = 4 * E;
+        e.W = ld.wfc; e.W2 = ld.w2t; e.bias = ld.c2f; e.c1 = ld.c1f; e.src = p.xres_f + (size_t)(cta % XREP) * E; e.mode = M_MLP; N = 4 * E;
       } else if (ph == 4) {
         e.bias = ld.b_proj2; e.mode = M_REDUCE; N = E;
       }
@@ -795,12 +903,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         const int S = att_splits(T, G, p.H);
         if (cta < p.H * S) {
           const int chunk = (T + S - 1) / S;
-          if (chunk <= 4 * NCW) attention_item<4>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep);
-          else if (chunk <= 8 * NCW) attention_item<8>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep);
-#ifdef ZG_ATT_MAX8  // experiment: never the 16-row instantiation; longer chunks loop over 8-row rounds
-          else attention_item<8>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep);
+          if (chunk <= 4 * NCW) attention_item<4>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep, ck);
+          else if (chunk <= 8 * NCW) attention_item<8>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep, ck);
+#if defined(ZG_ATT_MAX8) || ZG_NCW > 7  // never the 16-row instantiation (64 registers of K/V): 8-row rounds
+          else attention_item<8>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep, ck);
 #else
-          else attention_item<16>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep);
+          else attention_item<16>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep, ck);
 #endif
         }
         ck.at(11);
@@ -858,15 +966,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         for (int q = 0; q < NP; ++q) tot += lo_f(w[q]);
         tot += __shfl_xor_sync(0xffffffffu, tot, 16);
         if (lg == 3) tot += __shfl_xor_sync(0xffffffffu, tot, 8);
-        if (lane < (1 << lg)) sm.part[lane * 8 + warp] = tot;
+        if (lane < (1 << lg)) sm.part[lane * 16 + warp] = tot;
         ck.at(3);
         consumer_sync();
         ck.at(4);
         if (tid < ne) {
           float v = 0.0f;
 #pragma unroll
-          for (int w2 = 0; w2 < NCW; ++w2) v += sm.part[tid * 8 + w2];
-          st_flag(p.xnew_f + ent.r0 + tid, xmid[ent.r0 + tid] + bmine + v, ep);
+          for (int w2 = 0; w2 < NCW; ++w2) v += sm.part[tid * 16 + w2];
+          v += xmid[ent.r0 + tid] + bmine;
+#pragma unroll
+          for (int rep = 0; rep < XREP; ++rep) st_flag(p.xnew_f + (size_t)rep * E + ent.r0 + tid, v, ep);
         }
         ck.at(11);
         ck.dump(4);
@@ -911,7 +1021,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
       } else if (mode == M_RESID && att_splits(T, G, p.H) > 1) {
         gather_att_partials(vec, p.attp_f, E, att_splits(T, G, p.H), ep - 1, sm.wd);
       } else {
+#ifdef ZG_GATHER128  // the previous form: 128-bit loads, two (wide models: four) flagged pairs per thread and pass
         gather_flagged<(NJ <= 7 ? 2 : 4)>(vec, ent.src, E, ep - 1, sm.wd);
+#else
+        gather_flagged256<(NJ <= 7 ? 1 : 2)>(vec, ent.src, E, ep - 1, sm.wd);
+#endif
       }
       ck.at(2);
       consumer_sync();
@@ -1001,16 +1115,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
             if (r < E) {
               st_flag(p.q_f + r, v, ep);
             } else if (r < 2 * E) {
-              kc[r - E] = v;
+              st_cache(kc + (r - E), v);
               st_flag(p.kvn_f + (r - E), v, ep);
             } else {
-              vc[r - 2 * E] = v;
+              st_cache(vc + (r - 2 * E), v);
               st_flag(p.kvn_f + E + (r - 2 * E), v, ep);
             }
           } else if (mode == M_RESID) {  // residual 1, main.zig:136-139: the stream is this CTA's own copy
-            st_flag(p.xres_f + r, v + vprev[r], ep);
+            const float xv = v + vprev[r];
+#pragma unroll
+            for (int rep = 0; rep < XREP; ++rep) st_flag(p.xres_f + (size_t)rep * E + r, xv, ep);
           } else if (mode == M_MLP) {  // main.zig:79-80
-            sm.fbuf[b0 + iloc] = gelu_ref(v);
+            sm.fbuf[b0 + iloc] = gelu_dec(v);
           } else {  // tied lm_head (main.zig:193) + running argmax; this lane sees increasing r, so strict >
             if (logits) logits[r] = v;
             if (v > best) { best = v; best_i = (unsigned)r; }
@@ -1041,6 +1157,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           if (!w2ready) mbar_wait(sm.full0 + 8u * bslot, (fpar >> bslot) & 1u, sm.wd);
           w2ready = false;
           fpar ^= 1u << bslot;
+#ifndef ZG_PASS2_V1
+          // One ring unit (4 rows of c_proj^T) per trip: one broadcast LDS.128 for the unit's four GELU factors, four
+          // LDS.128 for this thread's column of the four rows, 16 FMAs.  Rows past the batch re-read row 0 of their unit
+          // (always valid) with a zero factor.  Two trips are unrolled together so that the loads of unit q + 1 are in
+          // flight under the FMAs of unit q; the slot index wraps with one compare per unit (uniform registers).
+#pragma unroll
+          for (int k = 0; k < NK; ++k) {
+            const int i4 = min(tid + k * NCT, Eq - 1);
+            const bool live = tid + k * NCT < Eq;
+            int sl = bslot;
+#pragma unroll 2
+            for (int q = 0; q < nun; ++q) {
+              const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)sl * slotf) + i4;
+              const int nv = live ? nbr - 4 * q : 0;  // valid rows of this unit (>= 1 for a live thread)
+              const float4 f4 = *reinterpret_cast<const float4 *>(sm.fbuf + b0 + 4 * q);
+              const float4 w0 = w4[0];
+              const float4 w1 = w4[nv > 1 ? Eq : 0];
+              const float4 w2 = w4[nv > 2 ? 2 * Eq : 0];
+              const float4 w3 = w4[nv > 3 ? 3 * Eq : 0];
+              const float f0 = nv > 0 ? f4.x : 0.0f, f1 = nv > 1 ? f4.y : 0.0f, f2 = nv > 2 ? f4.z : 0.0f, f3 = nv > 3 ? f4.w : 0.0f;
+              o4[k].x = fmaf(f0, w0.x, o4[k].x); o4[k].y = fmaf(f0, w0.y, o4[k].y);
+              o4[k].z = fmaf(f0, w0.z, o4[k].z); o4[k].w = fmaf(f0, w0.w, o4[k].w);
+              o4[k].x = fmaf(f1, w1.x, o4[k].x); o4[k].y = fmaf(f1, w1.y, o4[k].y);
+              o4[k].z = fmaf(f1, w1.z, o4[k].z); o4[k].w = fmaf(f1, w1.w, o4[k].w);
+              o4[k].x = fmaf(f2, w2.x, o4[k].x); o4[k].y = fmaf(f2, w2.y, o4[k].y);
+              o4[k].z = fmaf(f2, w2.z, o4[k].z); o4[k].w = fmaf(f2, w2.w, o4[k].w);
+              o4[k].x = fmaf(f3, w3.x, o4[k].x); o4[k].y = fmaf(f3, w3.y, o4[k].y);
+              o4[k].z = fmaf(f3, w3.z, o4[k].z); o4[k].w = fmaf(f3, w3.w, o4[k].w);
+              if (++sl == nslot) sl = 0;
+            }
+          }
+#else
           // Software-pipelined over the ring units of the batch, two units per trip of a ROLLED loop (A / B register
           // sets ping-pong): unit q + 1 is loaded while unit q is multiplied.  Rows past the batch re-read a valid row
           // with a zero factor.  Rolled on purpose: a phase runs its code once, so the 7-unit unrolled form was 7 KB of
@@ -1098,6 +1246,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
               }
             }
           }
+#endif
           __syncwarp();
           if (lane < nun) {
             int sl = bslot + lane;
@@ -1131,29 +1280,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
         }
         if (lane == 0) {
-          sm.red[44 + warp] = best;
-          sm.red[52 + warp] = __uint_as_float(best_i);
+          sm.red[RED_B + warp] = best;
+          sm.red[RED_I + warp] = __uint_as_float(best_i);
         }
         consumer_sync();
         if (tid < 32) {
-          best = (lane < NCW) ? sm.red[44 + lane] : -INFINITY;
-          best_i = (lane < NCW) ? __float_as_uint(sm.red[52 + lane]) : 0xffffffffu;
+          best = (lane < NCW) ? sm.red[RED_B + lane] : -INFINITY;
+          best_i = (lane < NCW) ? __float_as_uint(sm.red[RED_I + lane]) : 0xffffffffu;
 #pragma unroll
-          for (int o = 4; o > 0; o >>= 1) {
+          for (int o = (NCW > 8 ? 8 : 4); o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, best, o);
             const unsigned oi = __shfl_xor_sync(0xffffffffu, best_i, o);
             if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
           }
-          if (tid == 0) {
-            st_flag(p.amax_f + 2 * cta, best, ep);
-            st_flag(p.amax_f + 2 * cta + 1, __uint_as_float(best_i), ep);
-          }
+          if (tid < XREP) st_flag2(p.amax_f + 2 * ((size_t)tid * G + cta), best, __uint_as_float(best_i), ep);
           predelay(ZG_PD_AMAX);
           float bv = -INFINITY;
           unsigned bi = 0xffffffffu;
+          const u64 *amax_mine = p.amax_f + 2 * (size_t)(cta % XREP) * G;
           for (int i = tid; i < G; i += 32) {
-            ulonglong2 w = ld_pair(p.amax_f + 2 * i);
-            if (!pair_ok(w, ep)) w = spin_pair(p.amax_f + 2 * i, ep, sm.wd);
+            ulonglong2 w = ld_pair(amax_mine + 2 * i);
+            if (!pair_ok(w, ep)) w = spin_pair(amax_mine + 2 * i, ep, sm.wd);
             const float ov = lo_f(w.x);
             const unsigned oi = (unsigned)w.y;
             if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
@@ -1164,10 +1311,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
             const unsigned oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
           }
-          if (tid == 0) sm.red[40] = __uint_as_float(bi);
+          if (tid == 0) sm.red[RED_TOK] = __uint_as_float(bi);
         }
         consumer_sync();
-        const u64 amax = (u64)__float_as_uint(sm.red[40]);
+        const u64 amax = (u64)__float_as_uint(sm.red[RED_TOK]);
         if (cta == 0 && tid == 0) *p.last_token = amax;
         if (step >= p.n_prompt) out_tok = amax;  // generate(): main.zig:335-338
         consumer_sync();
@@ -1277,11 +1424,12 @@ struct zg_engine {
   int prof_enabled;
 };
 
-static zg_engine *g_table_owner = nullptr;  // whose layer table currently sits in __constant__ memory
+static zg_engine *g_table_owner = nullptr;  // whose layer table currently sits in __constant__ memory ...
+static unsigned g_table_gen = 0;            // ... of the device selected by this zg_init generation
 
 static size_t engine_smem_bytes(const zg_config &c, int nslot) {
   const size_t E = c.n_embed, hd = E / c.n_heads;
-  const size_t floats = (size_t)nslot * 4 * E + 2 * E + 64 + NCW * hd + 64;
+  const size_t floats = (size_t)nslot * 4 * E + 2 * E + 64 + NCW * hd + RED_FLOATS;
   return floats * sizeof(float) + (5 * c.n_layer + 1) * sizeof(PhaseEnt);
 }
 
@@ -1369,7 +1517,8 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
 
   const size_t C = cfg.context_size, hd = 64;
   const size_t n_attp = cfg.n_heads * (size_t)ATT_SMAX * (hd + 2);
-  const size_t n_exchange = E + E + 2 * E + E + 2 * (size_t)e->grid + E + n_attp + (size_t)e->grid * E;
+  const size_t n_amax = (XREP * 2 * (size_t)e->grid + 3) & ~(size_t)3;  // keeps the vectors behind it 32-byte aligned (256-bit loads)
+  const size_t n_exchange = XREP * E + E + 2 * E + XREP * E + n_amax + XREP * E + n_attp + (size_t)e->grid * E;
   e->exchange_dev = (u64 *)zg_alloc(n_exchange * 8);
   e->prompt_dev = (u64 *)zg_alloc(C * 8);
   e->tokens_dev = (u64 *)zg_alloc(C * 8);
@@ -1377,6 +1526,7 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
   e->prof_dev = (u64 *)zg_alloc((2 * PROF_MAX + 4) * 8);
   e->err_dev = (unsigned *)zg_alloc(256);
   ZG_CUDA(cudaHostAlloc(&e->tokens_host, C * 8, cudaHostAllocMapped));
+  note_alloc();
   ZG_CUDA(cudaHostGetDevicePointer((void **)&e->tokens_host_devptr, e->tokens_host, 0));
   if (zg_last_error()) {
     free(e);
@@ -1396,12 +1546,12 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
   p.wte = gpt->wte.weight; p.wpe = gpt->wpe.weight; p.lnf_g = gpt->ln_f.weight; p.lnf_b = gpt->ln_f.bias;
   p.wte_f = wte_f; p.c1h = c1h; p.c2h = c2h;
   u64 *x = e->exchange_dev;
-  p.xres_f = x; x += E;
+  p.xres_f = x; x += XREP * E;
   p.q_f = x; x += E;
   p.kvn_f = x; x += 2 * E;
-  p.att_f = x; x += E;
-  p.amax_f = x; x += 2 * (size_t)e->grid;
-  p.xnew_f = x; x += E;
+  p.att_f = x; x += XREP * E;
+  p.amax_f = x; x += n_amax;
+  p.xnew_f = x; x += XREP * E;
   p.attp_f = x; x += n_attp;
   p.part_f = x;
   p.xres_out = state->o; p.xout = state->x; p.logits = state->logits;
@@ -1438,10 +1588,11 @@ static void engine_launch(zg_engine *e, DecodeParams &p) {
     set_error(1, "decode engine: step range exceeds context_size", __FILE__, __LINE__);
     return;
   }
-  if (g_table_owner != e) {  // stream-ordered, so a launch in flight keeps the table it was given
+  if (g_table_owner != e || g_table_gen != ctx().generation) {  // stream-ordered, so a launch in flight keeps the table it was given
     ZG_CUDA(cudaMemcpyToSymbolAsync(c_layers, e->layers_host, sizeof(LayerDesc) * MAX_LAYERS, 0,
                                     cudaMemcpyHostToDevice, ctx().stream));
     g_table_owner = e;
+    g_table_gen = ctx().generation;
   }
   p.epoch_base = e->epoch_count;
   p.prof = e->prof_enabled ? e->prof_dev : nullptr;
@@ -1470,6 +1621,10 @@ extern "C" {
 
 void zg_engine_forward(zg_engine *e, size_t seq_len, size_t token, int compute_logits) {
   if (!require_ready("zg_engine_forward")) return;
+  if (seq_len == 0 || seq_len > e->cfg.context_size || token >= e->cfg.vocab_size) {  // same contract as zg_gpt_forward
+    set_error(1, "zg_engine_forward: need 1 <= seq_len <= context_size and token < vocab_size", __FILE__, __LINE__);
+    return;
+  }
   const size_t step = seq_len - 1;
   DecodeParams p = e->base;
   p.prompt = nullptr;  // the forced token rides in the kernel parameters
@@ -1487,6 +1642,7 @@ size_t zg_engine_sample_greedy(zg_engine *e, size_t seq_len, size_t token) {
   if (!require_ready("zg_engine_sample_greedy")) return (size_t)-1;
   Context &c = ctx();
   zg_engine_forward(e, seq_len, token, 1);
+  if (zg_last_error()) return (size_t)-1;
   ZG_CUDA(cudaMemcpyAsync(c.token_slot_host, e->last_token_dev, 8, cudaMemcpyDeviceToHost, c.stream));
   ZG_CUDA(cudaStreamSynchronize(c.stream));
   if (engine_check_watchdog(e)) return (size_t)-1;
@@ -1497,6 +1653,7 @@ size_t zg_engine_sample(zg_engine *e, size_t seq_len, float temp, size_t token, 
   if (!require_ready("zg_engine_sample")) return (size_t)-1;
   Context &c = ctx();
   zg_engine_forward(e, seq_len, token, 1);
+  if (zg_last_error()) return (size_t)-1;
   launch_softmax_temp(e->state.logits, e->cfg.vocab_size, temp);  // main.zig:200-203
   launch_weighted_index(e->state.logits, e->cfg.vocab_size, (float)u, c.token_slot);
   ZG_CUDA(cudaMemcpyAsync(c.token_slot_host, c.token_slot, 8, cudaMemcpyDeviceToHost, c.stream));

@@ -385,10 +385,10 @@ EncodeTiledFn encode_fn() {
 
 template <int MODE, int BN>
 void set_attr() {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned attr_gen = 0;  // the attribute is per device: redo it after every zg_init
+  if (attr_gen != ctx().generation) {
     ZG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE, BN>::SMEM));
-    attr_set = true;
+    attr_gen = ctx().generation;
   }
 }
 
@@ -426,10 +426,17 @@ void gemm_init_attrs() {  // outside any stream capture
   gemm_error_word();
 }
 
+static void gemm_forget_device_state() {  // zg_shutdown hook: the watchdog word lives on the device being left
+  if (g_err_word) cudaFree(g_err_word);
+  g_err_word = nullptr;
+}
+
 unsigned *gemm_error_word() {
   if (!g_err_word) {
     ZG_CUDA(cudaMalloc(&g_err_word, sizeof(unsigned)));
     ZG_CUDA(cudaMemset(g_err_word, 0, sizeof(unsigned)));
+    note_alloc();
+    register_shutdown_hook(gemm_forget_device_state);
   }
   return g_err_word;
 }
@@ -451,6 +458,7 @@ bool make_tmap_2d(CUtensorMap *out, const void *base, int dtype, uint64_t rows, 
   const cuuint32_t estride[2] = {1, 1};
   const CUtensorMapDataType dt = dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const CUtensorMapSwizzle sw = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  note_alloc();  // a tensor-map encode counts as start-up work: the hot path replays pre-encoded plans
   const CUresult r = fn(out, dt, 2, const_cast<void *>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

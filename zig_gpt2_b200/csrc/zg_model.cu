@@ -79,6 +79,12 @@ void zg_block_forward(const zg_block *self, size_t seq_len, const float *inputs,
 // ---- GPT.forward, main.zig:178-195 ----------------------------------------------------------------
 void zg_gpt_forward(const zg_gpt *self, size_t seq_len, size_t token, int compute_logits, const zg_state *state) {
   if (!require_ready("zg_gpt_forward")) return;
+  // The reference indexes wte / wpe / the caches unchecked (a Zig safety panic in debug builds); here a bad position
+  // or token would silently corrupt device memory, so both are rejected like the fused engine rejects them.
+  if (seq_len == 0 || seq_len > self->config.context_size || token >= self->config.vocab_size) {
+    set_error(1, "zg_gpt_forward: need 1 <= seq_len <= context_size and token < vocab_size", __FILE__, __LINE__);
+    return;
+  }
   const int E = (int)self->config.n_embed;
   launch_embed_add(self->wte.weight, self->wpe.weight, token, seq_len - 1, E, state->x, state->pos_emb);
   for (size_t i = 0; i < self->config.n_layer; ++i) zg_block_forward(&self->h[i], seq_len, state->x, state);
@@ -99,6 +105,7 @@ static size_t read_token_slot() {
 size_t zg_gpt_sample_greedy(const zg_gpt *self, size_t seq_len, size_t token, const zg_state *state) {
   if (!require_ready("zg_gpt_sample_greedy")) return (size_t)-1;
   zg_gpt_forward(self, seq_len, token, 1, state);
+  if (zg_last_error()) return (size_t)-1;
   launch_argmax(state->logits, self->config.vocab_size, ctx().token_slot);
   return read_token_slot();
 }
@@ -107,6 +114,7 @@ size_t zg_gpt_sample_greedy(const zg_gpt *self, size_t seq_len, size_t token, co
 size_t zg_gpt_sample(const zg_gpt *self, size_t seq_len, float temp, size_t token, const zg_state *state, double u) {
   if (!require_ready("zg_gpt_sample")) return (size_t)-1;
   zg_gpt_forward(self, seq_len, token, 1, state);
+  if (zg_last_error()) return (size_t)-1;
   launch_softmax_temp(state->logits, self->config.vocab_size, temp);  // :200-203
   launch_weighted_index(state->logits, self->config.vocab_size, (float)u, ctx().token_slot);
   return read_token_slot();

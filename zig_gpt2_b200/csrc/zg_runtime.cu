@@ -29,9 +29,20 @@ bool require_ready(const char *fn) {
   return true;
 }
 
+static void (*g_hooks[16])() = {nullptr};
+static int g_nhooks = 0;
+void register_shutdown_hook(void (*fn)()) {
+  for (int i = 0; i < g_nhooks; ++i)
+    if (g_hooks[i] == fn) return;
+  if (g_nhooks < 16) g_hooks[g_nhooks++] = fn;
+}
+
 }  // namespace zg
 
 using namespace zg;
+
+static unsigned g_generation = 0;
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 
 extern "C" {
 
@@ -81,6 +92,8 @@ int zg_init(int device) {
     return (int)e;
   }
   c.launches = 0;
+  c.alloc_calls = 0;
+  c.generation = ++g_generation;
   c.ready = true;
   return 0;
 }
@@ -89,6 +102,12 @@ int zg_shutdown(void) {
   Context &c = ctx();
   if (!c.ready) return 0;
   cudaStreamSynchronize(c.stream);
+  for (int i = 0; i < g_nhooks; ++i) g_hooks[i]();  // per-device lazily created state of the other translation units
+  if (g_ev0) {
+    cudaEventDestroy(g_ev0);
+    cudaEventDestroy(g_ev1);
+    g_ev0 = g_ev1 = nullptr;
+  }
   cudaFree(c.idx_staging);
   cudaFree(c.scratch);
   cudaFree(c.token_slot);
@@ -104,6 +123,7 @@ void *zg_alloc(size_t bytes) {
   if (!require_ready("zg_alloc")) return nullptr;
   void *p = nullptr;
   cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+  note_alloc();
   if (e != cudaSuccess) {
     set_error((int)e, "zg_alloc", __FILE__, __LINE__);
     return nullptr;
@@ -161,8 +181,8 @@ int zg_set_stream(void *s) {
 }
 
 unsigned long long zg_launch_count(void) { return ctx().launches; }
+unsigned long long zg_alloc_count(void) { return ctx().alloc_calls; }
 
-static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 int zg_timer_begin(void) {
   if (!require_ready("zg_timer_begin")) return 1;
   if (!g_ev0) {

@@ -62,7 +62,7 @@ SIGNATURES = {
     "zg_alloc": (P, [Z]), "zg_free": (I, [P]), "zg_memset": (I, [P, I, Z]),
     "zg_upload": (I, [P, P, Z]), "zg_download": (I, [P, P, Z]), "zg_sync": (I, []),
     "zg_last_error": (I, []), "zg_last_error_string": (C.c_char_p, []), "zg_clear_error": (V, []),
-    "zg_set_stream": (I, [P]), "zg_launch_count": (C.c_ulonglong, []),
+    "zg_set_stream": (I, [P]), "zg_launch_count": (C.c_ulonglong, []), "zg_alloc_count": (C.c_ulonglong, []),
     "zg_timer_begin": (I, []), "zg_timer_end_ms": (C.c_float, []),
     "zg_linear_forward": (V, [C.POINTER(ZgLinear), P, Z, P]),
     "zg_linear_forward_tc": (V, [C.POINTER(ZgLinear), P, Z, P, I, P, I, P, I]),
@@ -95,6 +95,7 @@ SIGNATURES = {
     "zg_batch_prefill": (I, [P, c_size_p, Z, I]), "zg_batch_prefill_resident": (I, [P, Z, I]),
     "zg_batch_generate_greedy": (I, [P, c_size_p, Z, Z, c_size_p, I]),
     "zg_batch_set_position": (V, [P, Z]), "zg_batch_run_steps": (V, [P, Z]),
+    "zg_batch_read_tokens": (I, [P, c_size_p]),
     "zg_batch_k_cache": (P, [P, Z]), "zg_batch_v_cache": (P, [P, Z]),
     "zg_attention_prefill": (V, [P, P, Z, Z, Z, Z]),
     "zg_attention_decode_batch": (V, [P, P, P, Z, Z, Z, Z, Z, P]),
