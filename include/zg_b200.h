@@ -83,6 +83,20 @@ void zg_linear_forward(const zg_linear *self, const float *inputs, size_t inputs
  * zg_linear_forward itself takes this path (precision 2) when M >= 16. */
 void zg_linear_forward_tc(const zg_linear *self, const void *inputs, size_t inputs_len, float *outputs, int precision,
                           const void *weight_lowp, int epi, const float *resid, int tile_n);
+/* Linear.forward for 1 <= M <= 128 rows (the batched decode step) on the tensor cores with the operands swapped: 128
+ * weight rows are the UMMA M operand, the whole batch is N, the (weight tile, k-block) grid is split evenly over the SMs
+ * (stream-K) and partial sums are reduced into `outputs` with fp32 atomics.  `outputs` must hold zeros (plain Linear) or
+ * the residual (x += Linear(h), main.zig:136-145) on entry; in_features % 32 == 0.  precision 0 = TF32, 2 = 3xTF32.
+ * xform bit 0 applies GELU (ops.zig:221-228) to `inputs` on the fly (mlp c_proj reading c_fc's pre-activation,
+ * main.zig:80); bit 1 is a test hook (element-wise fp32 atomics instead of TMA reduce-adds in the epilogue). */
+void zg_linear_forward_skinny(const zg_linear *self, const float *inputs, size_t inputs_len, float *outputs, int precision,
+                              int xform);
+/* Greedy sampling through a Linear without materialising its outputs (the tied lm_head + argmax, main.zig:193): for every
+ * row m of `inputs`, tokens_dev[m] (DEVICE, 64-bit) = index of the first maximum of inputs[m,:] . W^T + bias.  The argmax
+ * runs in the GEMM epilogue (whole weight tiles per CTA, packed atomicMax per row); `best_scratch` is 2 * M 64-bit words
+ * of device scratch.  1 <= M <= 128, in_features % 32 == 0.  Asynchronous. */
+void zg_linear_argmax_skinny(const zg_linear *self, const float *inputs, size_t inputs_len, int precision,
+                             unsigned long long *best_scratch, size_t *tokens_dev);
 void zg_to_f16(const float *src, void *dst_f16, size_t n); /* fp32 -> f16 round-to-nearest-even copy (start-up) */
 void zg_tc_set_direct_epilogue(int on); /* test hook: 1 = per-row direct stores instead of the staged TMA-store epilogue */
 int zg_tc_error(void); /* watchdog word of the tensor-core kernels (0 = clean); synchronises */
@@ -204,10 +218,13 @@ size_t zg_engine_read_profile(zg_engine *e, unsigned long long *out, size_t max_
 typedef struct zg_batch zg_batch;
 /* start-up: caches for n_seqs sequences of up to cache_rows positions, activation sets, plans (tensor maps), f16
  * weight copies when max_prompt > 0 (prefill enabled for prompts up to max_prompt tokens).  flags bit 0: no CUDA graph;
- * bit 1: single-pass TF32 decode GEMMs instead of the error-compensated 3xTF32 default. */
+ * bit 1: single-pass TF32 decode GEMMs instead of the error-compensated 3xTF32 default; bit 3: never the swapped-operand
+ * stream-K GEMMs (the default decode step for n_seqs <= 128, zg_linear_forward_skinny), always the general kernel. */
 zg_batch *zg_batch_create(const zg_gpt *gpt, size_t n_seqs, size_t cache_rows, size_t max_prompt, int flags);
 void zg_batch_destroy(zg_batch *e);
-/* GPT.forward(seq_len, tokens[b], compute_logits) for every sequence b (tokens: HOST, n_seqs entries). */
+/* GPT.forward(seq_len, tokens[b], compute_logits) for every sequence b (tokens: HOST, n_seqs entries).  compute_logits:
+ * 0 = none, 1 = logits (zg_batch_logits) and their argmax (zg_batch_read_tokens), 2 = argmax only -- fused into the
+ * lm_head GEMM's epilogue when zg_batch_fused_argmax() is 1, so no logits are written (what generate / run_steps use). */
 void zg_batch_forward(zg_batch *e, size_t seq_len, const size_t *tokens, int compute_logits);
 const float *zg_batch_logits(const zg_batch *e);      /* device, [n_seqs, pitch] */
 size_t zg_batch_logits_pitch(const zg_batch *e);      /* floats per row (vocab_size rounded up to 4) */
@@ -220,6 +237,7 @@ int zg_batch_generate_greedy(zg_batch *e, const size_t *prompts, size_t n_inputs
                              int use_prefill);
 void zg_batch_set_position(zg_batch *e, size_t pos); /* next step attends to cache rows [0, pos] (timing at a given context) */
 void zg_batch_run_steps(zg_batch *e, size_t n_steps); /* n greedy steps from the current position, device resident, async */
+int zg_batch_fused_argmax(const zg_batch *e); /* 1 when the decode step runs the stream-K GEMMs (n_seqs <= 128) and fuses the argmax */
 int zg_batch_read_tokens(zg_batch *e, size_t *out_tokens); /* argmax token of every sequence's last step (HOST, n_seqs ids); synchronises */
 const float *zg_batch_k_cache(const zg_batch *e, size_t layer); /* device, [n_seqs, cache_rows, n_embed] */
 const float *zg_batch_v_cache(const zg_batch *e, size_t layer);

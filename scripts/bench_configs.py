@@ -179,7 +179,7 @@ def measure_cfg4(L, lib, trials: int = 5, steps: int = 8, small: bool = False, d
                 L.zg_sync()
                 t0 = time.perf_counter()
                 for _ in range(steps):
-                    eng.forward(Tctx, tok_host, True)
+                    eng.forward(Tctx, tok_host, 2)
                     L.zg_batch_read_tokens(eng._h, got.ctypes.data_as(lib.c_size_p))
                 e2e.append(time.perf_counter() - t0)
             clocks = sampler.stop()

@@ -22,7 +22,7 @@ if which == "decode":
 elif which == "decode_xl":
     cfg = GPTConfig(50257, 1024, 2, 25, 1600)
     model = G.gpt_from_numpy(cfg, synth_weights(cfg, seed=1))
-    eng = BatchEngine(model, 64, cache_rows=1024, graph=False)
+    eng = BatchEngine(model, 64, cache_rows=1024, graph=False, tf32_single_pass=os.environ.get("ZG_TF32") == "1")
     for _ in range(3):
         eng.set_position(1023)
         eng.run_steps(1)

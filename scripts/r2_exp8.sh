@@ -1,0 +1,16 @@
+#!/bin/bash
+mkdir -p gpurun_out
+{
+echo skip tests
+for lvl in 7 3 11 15; do
+echo "ZG_PDL=$lvl"
+env ZG_PDL=$lvl timeout 900 python scripts/bench_configs.py cfg4 --trials 3 --steps 4 2>&1 | python -c "
+import sys, json
+for ln in sys.stdin:
+    if ln.startswith('{'):
+        r = json.loads(ln); print(r['record'], round(r['value']), round(r['ms_per_step'],3), round(r['roofline']['frac'],3), round(r['e2e']['value']))
+    else: print(ln.rstrip()[:300])
+"
+done
+} > gpurun_out/r2_exp8.txt 2>&1
+tail -25 gpurun_out/r2_exp8.txt

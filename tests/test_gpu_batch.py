@@ -241,19 +241,55 @@ def test_batch_forward_logits_and_caches_match_oracle(small_model):
 
 
 @pytest.mark.parametrize("graph", [True, False])
-def test_batch_generate_tokens_identical_to_oracle(small_model, graph):
+@pytest.mark.parametrize("general", [False, True])
+def test_batch_generate_tokens_identical_to_oracle(small_model, graph, general):
     """generate() per sequence (main.zig:322-342) incl. the duplicated last prompt token; empty-ish and ragged cases:
-    prompt of one token, and a batch whose size is not a multiple of anything (B = 3)."""
+    prompt of one token, and a batch whose size is not a multiple of anything (B = 3).  Both decode-step
+    implementations: the stream-K GEMMs with the argmax fused into the lm_head (default for <= 128 sequences) and the
+    general kernel with logits + a separate argmax."""
     from zig_gpt2_b200.batch import BatchEngine
 
     cfg, w, model = small_model
     for B, n_in, n_total in ((3, 1, 20), (5, 8, 72)):
         prompts = np.random.RandomState(B).randint(0, cfg.vocab_size, (B, n_in))
         toks, _, _ = _oracle_runs(cfg, w, prompts, n_total)
-        eng = BatchEngine(model, B, cache_rows=n_total, graph=graph)
+        eng = BatchEngine(model, B, cache_rows=n_total, graph=graph, general_gemm_only=general)
+        assert eng.fused_argmax == (not general)
         got = eng.generate_greedy(prompts, n_total)
         assert np.array_equal(got, toks)
         eng.close()
+
+
+def test_batch_forward_argmax_only_equals_logits_argmax(small_model):
+    """compute_logits = 2 (next-token ids only, argmax in the lm_head epilogue) gives the ids that the logits path gives."""
+    from zig_gpt2_b200.batch import BatchEngine
+
+    cfg, w, model = small_model
+    B = 9
+    toks = np.random.RandomState(4).randint(0, cfg.vocab_size, (6, B))
+    a, b = BatchEngine(model, B, cache_rows=16), BatchEngine(model, B, cache_rows=16)
+    for s in range(6):
+        a.forward(s + 1, toks[s], 1)
+        b.forward(s + 1, toks[s], 2)
+        want = a.logits().argmax(axis=1)
+        assert np.array_equal(a.read_tokens(), want)
+        assert np.array_equal(b.read_tokens(), want)
+    a.close()
+    b.close()
+
+
+def test_batch_above_128_sequences_uses_the_general_kernel(small_model):
+    from zig_gpt2_b200.batch import BatchEngine
+
+    cfg, w, model = small_model
+    B, n_in, n_total = 130, 3, 12
+    prompts = np.random.RandomState(130).randint(0, cfg.vocab_size, (B, n_in))
+    toks, _, _ = _oracle_runs(cfg, w, prompts[:6], n_total)
+    eng = BatchEngine(model, B, cache_rows=16)
+    assert not eng.fused_argmax
+    got = eng.generate_greedy(prompts, n_total)
+    assert np.array_equal(got[:6], toks)
+    eng.close()
 
 
 def test_batch_prefill_matches_oracle(small_model):
@@ -370,11 +406,13 @@ def test_batch_generate_is_repeatable_and_bit_exact_without_split_k(small_model)
     prompts = np.random.RandomState(21).randint(0, cfg.vocab_size, (B, n_in))
     eng = BatchEngine(model, B, cache_rows=64)
     a = eng.generate_greedy(prompts, n_total)
-    la = eng.logits().copy()
     b = eng.generate_greedy(prompts, n_total)
+    assert np.array_equal(a, b)
+    eng.forward(n_total, a[:, -1], 1)  # greedy steps fuse the argmax and write no logits: ask for them explicitly
+    la = eng.logits().copy()
+    eng.forward(n_total, a[:, -1], 1)
     lb = eng.logits().copy()
     eng.close()
-    assert np.array_equal(a, b)
     assert rel(la, lb) <= FP32_RTOL
 
     code = r'''
@@ -389,6 +427,7 @@ cfg = GPTConfig(vocab_size=4099, context_size=160, n_layer=2, n_heads=4, n_embed
 model = gpt.gpt_from_numpy(cfg, synth_weights(cfg, seed=3))
 prompts = np.random.RandomState(21).randint(0, cfg.vocab_size, (7, 6))
 eng = BatchEngine(model, 7, cache_rows=64)
+assert not eng.fused_argmax  # ZG_NO_SPLIT_K=1: general kernel, no reduction in arrival order anywhere
 outs = []
 for _ in range(3):
     t = eng.generate_greedy(prompts, 48)

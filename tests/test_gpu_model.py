@@ -266,10 +266,10 @@ from zig_gpt2_b200 import gpt, lib
 from zig_gpt2_b200.config import GPTConfig
 from zig_gpt2_b200.lib import DeviceBuffer, ZgLinear
 from zig_gpt2_b200.weights import synth_weights
-cfg = GPTConfig(vocab_size=1031, context_size=64, n_layer=2, n_heads=2, n_embed=128)
+cfg = GPTConfig(vocab_size=1031, context_size=64, n_layer=2, n_heads=4, n_embed=256)
 w = synth_weights(cfg, seed=5)
 rs = np.random.RandomState(0)
-x, wm = rs.randn(64, 256).astype(np.float32), rs.randn(384, 256).astype(np.float32)
+x, wm = rs.randn(64, 256).astype(np.float32), rs.randn(384, 256).astype(np.float32)  # M >= 16: tensor-core path
 def once():
     L = lib.init(0)
     model, state = gpt.gpt_from_numpy(cfg, w), gpt.State(cfg)

@@ -15,7 +15,7 @@ from zig_gpt2_b200.config import GPTConfig
 from zig_gpt2_b200.weights import load_raw, save_raw, synth_weights, tensor_shapes
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CFG = GPTConfig(vocab_size=1031, context_size=64, n_layer=2, n_heads=2, n_embed=128)
+CFG = GPTConfig(vocab_size=1031, context_size=64, n_layer=2, n_heads=4, n_embed=256)  # the fused engine needs n_embed >= SMs
 
 
 def test_raw_format_is_headerless_little_endian_f32(tmp_path):

@@ -14,24 +14,26 @@ from .gpt import GPT
 
 class BatchEngine:
     def __init__(self, gpt: GPT, n_seqs: int, cache_rows: Optional[int] = None, max_prompt: int = 0, graph: bool = True,
-                 tf32_single_pass: bool = False):
+                 tf32_single_pass: bool = False, general_gemm_only: bool = False):
         self.gpt, self.n_seqs = gpt, int(n_seqs)
         self.cache_rows = int(cache_rows or gpt.config.context_size)
         self.max_prompt = int(max_prompt)
         L = _lib.load()
         self._h = L.zg_batch_create(C.byref(gpt.c), self.n_seqs, self.cache_rows, self.max_prompt,
-                                    (0 if graph else 1) | (2 if tf32_single_pass else 0))
+                                    (0 if graph else 1) | (2 if tf32_single_pass else 0) | (8 if general_gemm_only else 0))
         _lib.check()
         if not self._h:
             raise _lib.ZgError("zg_batch_create failed")
         self.pitch = int(L.zg_batch_logits_pitch(self._h))
+        self.fused_argmax = bool(L.zg_batch_fused_argmax(self._h))  # greedy steps never write logits (stream-K path)
 
     def _tok(self, a, n) -> np.ndarray:
         t = np.ascontiguousarray(a, np.uint64).reshape(-1)
         assert t.size == n, (t.size, n)
         return t
 
-    def forward(self, seq_len: int, tokens: Sequence[int], compute_logits: bool = True) -> None:
+    def forward(self, seq_len: int, tokens: Sequence[int], compute_logits=True) -> None:
+        """compute_logits: False / True as in GPT.forward; 2 = next-token ids only (read_tokens), no logits written."""
         t = self._tok(tokens, self.n_seqs)
         _lib.load().zg_batch_forward(self._h, seq_len, t.ctypes.data_as(_lib.c_size_p), int(compute_logits))
         _lib.check()

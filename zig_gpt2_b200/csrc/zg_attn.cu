@@ -264,23 +264,37 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_qkv, __half *__restri
 // -------------------------------------------------------------------------------------------------------------------
 // Batched single-query attention off the fp32 caches.  cache layout: [B][C][E] (time-major, heads interleaved -- the
 // reference's per-block cache, main.zig:298-299, once per sequence).  q: [B, ldq] (row b holds q at columns h*64..).
-// T = *pos_dev + pos_base + 1 rows are attended (the new token's K/V row is already in the cache).
+// T = *pos_dev + pos_base + 1 rows are attended.  knew == null: the new token's K/V row is already in the cache (the
+// general GEMM's epilogue appended it).  knew != null: row T-1 is taken from knew / vnew (row b, columns h*64.., pitch
+// ldq: the c_attn output, complete only at this kernel boundary because the stream-K GEMM reduces partial sums) and this
+// CTA appends it to the caches (ops.zig:151-152,156-157) -- read through plain loads, never through the cache, because
+// the non-coherent streaming loads below must not see data written by this same kernel.
 // -------------------------------------------------------------------------------------------------------------------
 constexpr int DEC_WARPS = 8;
 
 __global__ void __launch_bounds__(DEC_WARPS * 32)
-attn_decode_batch_kernel(const float *__restrict__ q, int ldq, const float *__restrict__ k_cache,
-                         const float *__restrict__ v_cache, long long seq_stride, int E, float *__restrict__ out, int ldo,
-                         const int *pos_dev, int pos_base) {
+attn_decode_batch_kernel(const float *__restrict__ q, int ldq, const float *k_cache, const float *v_cache, long long seq_stride, int E, float *__restrict__ out, int ldo,
+                         const int *pos_dev, int pos_base, const float *knew, const float *vnew, int trigger) {
   __shared__ float s_m[DEC_WARPS], s_l[DEC_WARPS];
   __shared__ float s_o[DEC_WARPS][HD];
   const int h = blockIdx.x, b = blockIdx.y;
+  if (trigger) pdl_trigger();  // the c_proj GEMM that follows fills its ring with weights while the caches stream
+  pdl_wait();  // q / the new K,V row are the c_attn GEMM's output (no-op for an ordinary launch)
   const int T = pos_base + (pos_dev ? *pos_dev : 0) + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = lane >> 4, l16 = lane & 15;  // a half-warp covers one 256-byte head row with float4 loads
   const float4 qv = *reinterpret_cast<const float4 *>(q + (size_t)b * ldq + h * HD + 4 * l16);
   const float *kb = k_cache + (size_t)b * seq_stride + h * HD + 4 * l16;
   const float *vb = v_cache + (size_t)b * seq_stride + h * HD + 4 * l16;
+  float4 k_last = make_float4(0.f, 0.f, 0.f, 0.f), v_last = k_last;
+  if (knew) {
+    k_last = *reinterpret_cast<const float4 *>(knew + (size_t)b * ldq + h * HD + 4 * l16);
+    v_last = *reinterpret_cast<const float4 *>(vnew + (size_t)b * ldq + h * HD + 4 * l16);
+    if (threadIdx.x < 16) {  // cache append: 16 lanes x float4 = this head's 64 floats of row T-1
+      *reinterpret_cast<float4 *>(const_cast<float *>(kb) + (size_t)(T - 1) * E) = k_last;
+      *reinterpret_cast<float4 *>(const_cast<float *>(vb) + (size_t)(T - 1) * E) = v_last;
+    }
+  }
   const float scale = 0.125f;
   float m = -INFINITY, l = 0.0f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -294,8 +308,13 @@ attn_decode_batch_kernel(const float *__restrict__ q, int ldq, const float *__re
     for (int u = 0; u < 4; ++u) {
       const int t = t0 + u * STEP;
       if (t < T) {
-        kk[u] = ld_stream(reinterpret_cast<const float4 *>(kb + (size_t)t * E));
-        vv[u] = ld_stream(reinterpret_cast<const float4 *>(vb + (size_t)t * E));
+        if (knew && t == T - 1) {
+          kk[u] = k_last;
+          vv[u] = v_last;
+        } else {
+          kk[u] = ld_stream(reinterpret_cast<const float4 *>(kb + (size_t)t * E));
+          vv[u] = ld_stream(reinterpret_cast<const float4 *>(vb + (size_t)t * E));
+        }
       }
     }
 #pragma unroll
@@ -386,9 +405,10 @@ void attn_prefill_launch(const AttnPrefillPlan &p) {
 }
 
 void attn_decode_batch_launch(const float *q, int ldq, const float *k_cache, const float *v_cache, long long seq_stride,
-                              int B, int H, int E, float *out, int ldo, const int *pos_dev, int pos_base) {
-  attn_decode_batch_kernel<<<dim3(H, B), DEC_WARPS * 32, 0, ctx().stream>>>(q, ldq, k_cache, v_cache, seq_stride, E, out,
-                                                                             ldo, pos_dev, pos_base);
+                              int B, int H, int E, float *out, int ldo, const int *pos_dev, int pos_base,
+                              const float *knew, const float *vnew) {
+  ZG_CUDA(launch_pdl(PDL_ATTN_DEP, attn_decode_batch_kernel, dim3(H, B), dim3(DEC_WARPS * 32), 0, ctx().stream, q, ldq, k_cache, v_cache,
+                     seq_stride, E, out, ldo, pos_dev, pos_base, knew, vnew, (knew && (pdl_mask() & PDL_ATTN_TRIGGER)) ? 1 : 0));
   ZG_LAUNCH_CHECK();
 }
 
@@ -412,7 +432,7 @@ void zg_attention_decode_batch(const float *q, const float *k_cache, const float
                                size_t n_heads, size_t n_embed, size_t seq_len, float *out) {
   if (!require_ready("zg_attention_decode_batch") || seq_len == 0) return;
   attn_decode_batch_launch(q, (int)n_embed, k_cache, v_cache, (long long)(context * n_embed), (int)B, (int)n_heads,
-                           (int)n_embed, out, (int)n_embed, nullptr, (int)seq_len - 1);
+                           (int)n_embed, out, (int)n_embed, nullptr, (int)seq_len - 1, nullptr, nullptr);
 }
 
 }  // extern "C"

@@ -16,6 +16,7 @@
 
 #include "zg_attn.cuh"
 #include "zg_gemm.cuh"
+#include "zg_skinny.cuh"
 
 namespace zg {
 
@@ -109,6 +110,69 @@ void launch_ln_rows(const float *in, size_t in_stride, void *out, const float *g
   ZG_LAUNCH_CHECK();
 }
 
+// LayerNorm.forward of row r of x into h (ops.zig:82-104: single pass sums of x and x^2, eps inside the square root,
+// division) AND zero-fill of row r of the output that the next (stream-K) GEMM reduces its partial sums into.  One CTA of
+// four warps per row -- the decode step has <= 128 rows, so the row is split over 128 threads instead of giving a single
+// warp ~2,000 dependent instructions (the one-warp-per-row kernel took 11-12 us per call at E = 1600).
+constexpr int LNZ_THREADS = 128;
+template <int LN_MAXV>  // float4 per thread: n_embed <= 4 * LNZ_THREADS * LN_MAXV
+__global__ void __launch_bounds__(LNZ_THREADS) ln_zero_rows_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                                   const float *__restrict__ g, const float *__restrict__ b,
+                                                                   int E, float eps, float *__restrict__ zero, int zero_n,
+                                                                   int trigger) {
+  __shared__ float red[2][LNZ_THREADS / 32];
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (trigger) pdl_trigger();
+  pdl_wait();  // x is the previous GEMM's output; the buffer zeroed below may still be read by it
+  const float4 *src = reinterpret_cast<const float4 *>(in + (size_t)row * E);
+  const int nv = E >> 2;
+  float4 v[LN_MAXV];
+  float s = 0.0f, ss = 0.0f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = i * LNZ_THREADS + tid;
+    if (c < nv) {
+      v[i] = src[c];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      ss = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, fmaf(v[i].w, v[i].w, ss))));
+    }
+  }
+  if (zero) {  // independent of the row's statistics: issued while the loads above are in flight
+    float4 *z = reinterpret_cast<float4 *>(zero + (size_t)row * zero_n);
+    for (int c = tid; c < (zero_n >> 2); c += LNZ_THREADS) z[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  if (lane == 0) { red[0][warp] = s; red[1][warp] = ss; }
+  __syncthreads();
+  s = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+  ss = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+  const float n = (float)E, mean = s / n;
+  const float std_ = sqrtf(ss / n - mean * mean + eps);
+  const float4 *g4 = reinterpret_cast<const float4 *>(g), *b4 = reinterpret_cast<const float4 *>(b);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = i * LNZ_THREADS + tid;
+    if (c < nv) {
+      const float4 gg = __ldg(g4 + c), bb = __ldg(b4 + c);
+      float4 y;
+      y.x = (v[i].x - mean) / std_ * gg.x + bb.x;
+      y.y = (v[i].y - mean) / std_ * gg.y + bb.y;
+      y.z = (v[i].z - mean) / std_ * gg.z + bb.z;
+      y.w = (v[i].w - mean) / std_ * gg.w + bb.w;
+      reinterpret_cast<float4 *>(out + (size_t)row * E)[c] = y;
+    }
+  }
+}
+void launch_ln_zero_rows(const float *in, float *out, const float *g, const float *b, int E, int rows, float *zero, int zero_n,
+                         cudaStream_t s) {
+  if (E <= 1024) ZG_CUDA(launch_pdl(PDL_LN_DEP, ln_zero_rows_kernel<2>, dim3(rows), dim3(LNZ_THREADS), 0, s, in, out, g, b, E, 1e-5f, zero, zero_n,
+                                    (pdl_mask() & PDL_LN_TRIGGER) ? 1 : 0));
+  else ZG_CUDA(launch_pdl(PDL_LN_DEP, ln_zero_rows_kernel<4>, dim3(rows), dim3(LNZ_THREADS), 0, s, in, out, g, b, E, 1e-5f, zero, zero_n,
+                                    (pdl_mask() & PDL_LN_TRIGGER) ? 1 : 0));
+  ZG_LAUNCH_CHECK();
+}
+
 // greedy argmax per row (first maximum wins, like the oracle); writes the next token and the history row
 __global__ void __launch_bounds__(256) argmax_rows_kernel(const float *__restrict__ logits, size_t pitch, int V,
                                                           u64 *__restrict__ tok, u64 *__restrict__ hist, int B,
@@ -168,6 +232,9 @@ struct LayerW {
 struct LayerPlans {
   GemmPlan attn, proj, fc, proj2;
 };
+struct SkinnyLayerPlans {
+  SkinnyPlan attn, proj, fc, proj2;
+};
 
 }  // namespace
 
@@ -196,6 +263,10 @@ struct zg_batch {
   int *pos = nullptr;
   // plans
   std::vector<LayerPlans> dec_plans, pre_plans;
+  std::vector<SkinnyLayerPlans> sk_plans;  // decode step with <= 128 sequences: swapped-operand stream-K GEMMs
+  SkinnyPlan sk_head;                      // tied lm_head with the argmax in its epilogue (no logits leave the kernel)
+  unsigned long long *best = nullptr;      // [B][2] packed (orderable logit, ~column) words of the fused argmax
+  bool skinny = false;
   GemmPlan dec_head, pre_head;
   std::vector<AttnPrefillPlan> pre_attn;
   int pre_T = -1;
@@ -253,6 +324,33 @@ bool build_decode_plans(zg_batch *e) {
   return gemm_plan(&e->dec_head, e->dec_mode, e->h, E, e->wte, a, 0);
 }
 
+// Decode step with <= 128 sequences: every layer GEMM through the stream-K kernel.  c_attn reduces into a zeroed qkv
+// (its K/V columns are appended to the caches by the attention kernel), c_fc into a zeroed pre-activation buffer whose
+// GELU is applied by mlp c_proj's operand load, both c_proj's into the residual stream in place.
+bool build_skinny_plans(zg_batch *e) {
+  const int B = e->B, E = (int)e->cfg.n_embed;
+  e->sk_plans.resize(e->layers.size());
+  for (size_t l = 0; l < e->layers.size(); ++l) {
+    const LayerW &w = e->layers[l];
+    SkinnyLayerPlans &p = e->sk_plans[l];
+    SkinnyArgs a;
+    a.M = B; a.N = 3 * E; a.K = E; a.bias = w.attn_b; a.out = e->qkv; a.ldo = 3 * E;
+    if (!skinny_plan(&p.attn, e->dec_mode, e->h, E, w.attn_w, a)) return false;
+    a = SkinnyArgs();
+    a.M = B; a.N = E; a.K = E; a.bias = w.proj_b; a.out = e->x; a.ldo = E;
+    if (!skinny_plan(&p.proj, e->dec_mode, e->att, E, w.proj_w, a)) return false;
+    a = SkinnyArgs();
+    a.M = B; a.N = 4 * E; a.K = E; a.bias = w.fc_b; a.out = e->h4; a.ldo = 4 * E;
+    if (!skinny_plan(&p.fc, e->dec_mode, e->h, E, w.fc_w, a)) return false;
+    a = SkinnyArgs();
+    a.M = B; a.N = E; a.K = 4 * E; a.bias = w.proj2_b; a.out = e->x; a.ldo = E; a.xform = SK_XFORM_GELU;
+    if (!skinny_plan(&p.proj2, e->dec_mode, e->h4, 4 * E, w.proj2_w, a)) return false;
+  }
+  SkinnyArgs a;
+  a.M = B; a.N = (int)e->cfg.vocab_size; a.K = E; a.best = e->best;
+  return skinny_plan(&e->sk_head, e->dec_mode, e->h, E, e->wte, a);
+}
+
 bool build_prefill_plans(zg_batch *e, int T) {
   if (e->pre_T == T) return true;
   const int B = e->B, E = (int)e->cfg.n_embed, V = (int)e->cfg.vocab_size, M = B * T, H = (int)e->cfg.n_heads;
@@ -284,7 +382,9 @@ bool build_prefill_plans(zg_batch *e, int T) {
 }
 
 // One decode step for every sequence at position *pos: GPT.forward(seq_len = *pos + 1, tok[b]) (main.zig:178-195).
-void enqueue_step(zg_batch *e, bool from_prompt, int n_inputs, bool with_logits) {
+// head: 0 = no logits, 1 = logits in e->logits + argmax over them, 2 = argmax only, fused into the lm_head GEMM when the
+// stream-K path is active (greedy generate / run_steps never need the logits themselves)
+void enqueue_step(zg_batch *e, bool from_prompt, int n_inputs, int head) {
   cudaStream_t s = ctx().stream;
   const int B = e->B, E = (int)e->cfg.n_embed, H = (int)e->cfg.n_heads, V = (int)e->cfg.vocab_size;
   if (from_prompt) {
@@ -293,7 +393,19 @@ void enqueue_step(zg_batch *e, bool from_prompt, int n_inputs, bool with_logits)
   }
   embed_rows_kernel<<<B, 128, 0, s>>>(e->wte, e->wpe, e->tok, 1, e->pos, E, V, e->x);
   ZG_LAUNCH_CHECK();
-  for (size_t l = 0; l < e->layers.size(); ++l) {
+  for (size_t l = 0; e->skinny && l < e->layers.size(); ++l) {
+    const LayerW &w = e->layers[l];
+    const SkinnyLayerPlans &p = e->sk_plans[l];
+    launch_ln_zero_rows(e->x, e->h, w.ln1_g, w.ln1_b, E, B, e->qkv, 3 * E, s);  // main.zig:121-123; qkv := 0
+    skinny_launch(p.attn);                                                       // c_attn (ops.zig:143)
+    attn_decode_batch_launch(e->qkv, 3 * E, e->k_cache + l * e->layer_stride, e->v_cache + l * e->layer_stride,
+                             (long long)e->seq_stride, B, H, E, e->att, E, e->pos, 0, e->qkv + E, e->qkv + 2 * E);
+    skinny_launch(p.proj);                                                       // x += c_proj(att) (ops.zig:172, main.zig:136-139)
+    launch_ln_zero_rows(e->x, e->h, w.ln2_g, w.ln2_b, E, B, e->h4, 4 * E, s);    // main.zig:140; h4 := 0
+    skinny_launch(p.fc);                                                         // c_fc pre-activation (main.zig:79)
+    skinny_launch(p.proj2);                                                      // x += c_proj(gelu(.)) (main.zig:80-81,142-145)
+  }
+  for (size_t l = 0; !e->skinny && l < e->layers.size(); ++l) {
     const LayerW &w = e->layers[l];
     const LayerPlans &p = e->dec_plans[l];
     launch_ln_rows<false>(e->x, E, e->h, w.ln1_g, w.ln1_b, E, B, s);  // main.zig:121-123
@@ -305,7 +417,11 @@ void enqueue_step(zg_batch *e, bool from_prompt, int n_inputs, bool with_logits)
     gemm_launch(p.fc);     // c_fc + GELU (main.zig:79-80)
     gemm_launch(p.proj2);  // c_proj + residual (main.zig:81,142-145)
   }
-  if (with_logits) {
+  if (head == 2 && e->skinny) {
+    launch_ln_zero_rows(e->x, e->h, e->lnf_g, e->lnf_b, E, B, reinterpret_cast<float *>(e->best), 4, s);  // main.zig:189; best := 0
+    skinny_launch(e->sk_head);                                         // tied lm_head + argmax (main.zig:192-194)
+    skinny_finish_argmax(e->best, e->tok, e->hist, B, e->pos);
+  } else if (head) {
     launch_ln_rows<false>(e->x, E, e->h, e->lnf_g, e->lnf_b, E, B, s);  // main.zig:189
     gemm_launch(e->dec_head);  // tied lm_head (main.zig:192-194)
     argmax_rows_kernel<<<B, 256, 0, s>>>(e->logits, (size_t)e->Vp, V, e->tok, e->hist, B, e->pos);
@@ -337,12 +453,12 @@ void enqueue_prefill(zg_batch *e, int T, bool with_logits) {
   }
 }
 
-bool capture(zg_batch *e, cudaGraphExec_t *exec, bool from_prompt, int n_inputs, bool with_logits) {
+bool capture(zg_batch *e, cudaGraphExec_t *exec, bool from_prompt, int n_inputs, int head) {
   cudaStream_t s = ctx().stream;
   cudaGraph_t g = nullptr;
   if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return false;
   ctx().capturing = true;  // recorded, not executed: zg_launch_count counts the replays
-  enqueue_step(e, from_prompt, n_inputs, with_logits);
+  enqueue_step(e, from_prompt, n_inputs, head);
   ctx().capturing = false;
   if (cudaStreamEndCapture(s, &g) != cudaSuccess || !g) {
     cudaGetLastError();
@@ -424,6 +540,7 @@ zg_batch *zg_batch_create(const zg_gpt *gpt, size_t n_seqs, size_t cache_rows, s
   }
   note_alloc();
   e->pos = balloc<int>(e, 4);
+  e->best = balloc<unsigned long long>(e, 2 * B);
   if (e->f16_prefill) {
     const size_t M = B * max_prompt;
     e->px = balloc<float>(e, M * E);
@@ -444,7 +561,11 @@ zg_batch *zg_batch_create(const zg_gpt *gpt, size_t n_seqs, size_t cache_rows, s
   zg_memset(e->tok, 0, B * sizeof(u64));
   gemm_init_attrs();
   attn_init_attrs();
-  if (!build_decode_plans(e)) {
+  skinny_init_attrs();
+  // ZG_NO_SPLIT_K=1 asks for run-to-run bit-reproducible steps: no reduction in arrival order anywhere, i.e. no split-K
+  // in the general kernel and no stream-K kernel at all
+  e->skinny = !(flags & 8) && getenv("ZG_NO_SPLIT_K") == nullptr && skinny_supported(e->B, (int)E, (int)E);
+  if (!build_decode_plans(e) || (e->skinny && !build_skinny_plans(e))) {
     zg_batch_destroy(e);
     return nullptr;
   }
@@ -478,7 +599,7 @@ void zg_batch_forward(zg_batch *e, size_t seq_len, const size_t *tokens, int com
   ZG_LAUNCH_CHECK();
   u64 *hist = e->hist;
   e->hist = nullptr;  // explicit forwards do not record history
-  enqueue_step(e, false, 0, compute_logits != 0);
+  enqueue_step(e, false, 0, compute_logits);
   e->hist = hist;
   e->host_pos = (int)seq_len;
 }
@@ -542,11 +663,11 @@ int zg_batch_generate_greedy(zg_batch *e, const size_t *prompts, size_t n_inputs
     ZG_LAUNCH_CHECK();
   }
   if (e->use_graph) {
-    if (!e->graph_sample && !capture(e, &e->graph_sample, false, 0, true)) e->use_graph = false;
+    if (!e->graph_sample && !capture(e, &e->graph_sample, false, 0, 2)) e->use_graph = false;
     if (e->use_graph && first < n_inputs && (e->graph_n_inputs != (int)n_inputs || !e->graph_prompt)) {
       if (e->graph_prompt) cudaGraphExecDestroy(e->graph_prompt);
       e->graph_prompt = nullptr;
-      if (capture(e, &e->graph_prompt, true, (int)n_inputs, false)) e->graph_n_inputs = (int)n_inputs;
+      if (capture(e, &e->graph_prompt, true, (int)n_inputs, 0)) e->graph_n_inputs = (int)n_inputs;
       else e->use_graph = false;
     }
   }
@@ -556,7 +677,7 @@ int zg_batch_generate_greedy(zg_batch *e, const size_t *prompts, size_t n_inputs
       ZG_CUDA(cudaGraphLaunch(prompt_step ? e->graph_prompt : e->graph_sample, s));
       ctx().launches += prompt_step ? 2 + 7 * e->layers.size() + 1 : 1 + 7 * e->layers.size() + 4;
     } else {
-      enqueue_step(e, prompt_step, (int)n_inputs, !prompt_step);
+      enqueue_step(e, prompt_step, (int)n_inputs, prompt_step ? 0 : 2);
     }
   }
   e->host_pos = (int)n_total;
@@ -578,16 +699,17 @@ void zg_batch_run_steps(zg_batch *e, size_t n_steps) {
     return;
   }
   e->host_pos += (int)n_steps;
-  if (e->use_graph && !e->graph_sample && !capture(e, &e->graph_sample, false, 0, true)) e->use_graph = false;
+  if (e->use_graph && !e->graph_sample && !capture(e, &e->graph_sample, false, 0, 2)) e->use_graph = false;
   for (size_t i = 0; i < n_steps; ++i) {
     if (e->use_graph) {
       ZG_CUDA(cudaGraphLaunch(e->graph_sample, s));
       ctx().launches += 1 + 7 * e->layers.size() + 4;
     } else {
-      enqueue_step(e, false, 0, true);
+      enqueue_step(e, false, 0, 2);
     }
   }
 }
+int zg_batch_fused_argmax(const zg_batch *e) { return e->skinny ? 1 : 0; }
 // Set the common position (and so the attended length) directly: timing a step at T = 1024 needs no 1023 real steps.
 void zg_batch_set_position(zg_batch *e, size_t pos) {
   if (!require_ready("zg_batch_set_position")) return;

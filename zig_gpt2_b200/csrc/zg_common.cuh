@@ -55,6 +55,33 @@ inline void note_alloc() { ctx().alloc_calls++; }
 
 // ---- device helpers ---------------------------------------------------------------------------
 #ifdef __CUDACC__
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl may begin -- prologue, barrier / TMEM set-up,
+// loads of data that no earlier kernel writes (weights) -- while its predecessor in the stream is still draining;
+// pdl_wait() returns once every prerequisite grid has completed and its writes are visible, and must precede the first
+// access to anything an earlier kernel produces and the first global write.  pdl_trigger() lets the NEXT kernel start
+// launching.  Both are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+enum { PDL_GEMM_DEP = 1, PDL_LN_TRIGGER = 2, PDL_ATTN_TRIGGER = 4, PDL_GEMM_TRIGGER = 8, PDL_ATTN_DEP = 16, PDL_LN_DEP = 32 };
+int pdl_mask();  // which kernels of the stream-K decode step take part (zg_runtime.cu; environment ZG_PDL for A/B runs)
+// the launch carries the PDL attribute only when `bit` is set in pdl_mask()
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int bit, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = (pdl_mask() & bit) ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

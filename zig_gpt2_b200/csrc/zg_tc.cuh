@@ -206,7 +206,8 @@ __device__ __forceinline__ bool elect_one() {
 // ---- host side: tensor maps ---------------------------------------------------------------------------
 // 2-D row-major tensor [rows, cols] of `elem_bytes`-wide elements with row pitch `pitch_bytes`; box = [box_rows,
 // box_cols] with box_cols * elem_bytes == 128 (one swizzle row).  dtype: 0 = fp32 (tf32 operand), 1 = fp16.
-// swizzle_bytes: 128 (default) or 64 -- must equal box_cols * elem_bytes.
+// swizzle_bytes: 128 (default) or 64 -- must equal box_cols * elem_bytes -- or 0 for an unswizzled box (plain row-major
+// rows of box_cols elements in shared memory: staged epilogue tiles that no tensor-core instruction reads).
 bool make_tmap_2d(CUtensorMap *out, const void *base, int dtype, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
                   uint32_t box_rows, uint32_t box_cols, int swizzle_bytes = 128);
 
