@@ -67,3 +67,26 @@ def test_cli_reports_missing_model_files(model_dir, tmp_path):
     _, _, exe = model_dir
     r = subprocess.run([exe, "--config", "4099,128,2,4,256", "--model-dir", str(tmp_path), "hi"], capture_output=True, timeout=60)
     assert r.returncode == 1 and b"cannot load" in r.stderr
+
+
+def test_cli_fidelity_tokenizer_mode(model_dir, tmp_path):
+    """--tokenizer gpt2: the opt-in byte-pair tokenizer drives the same generate loop.  With an empty merge list every
+    byte is its own token (ids 0..255 of the synthetic vocabulary), which the oracle loop can follow."""
+    import zg_oracle as zo
+
+    d, w, exe = model_dir
+    merges = tmp_path / "vocab.bpe"
+    merges.write_text("#version: 0.2\n")
+    from zig_gpt2_b200.vocab import synth_encoder, unicode_to_bytes
+
+    enc, u2b = synth_encoder(CFG.vocab_size), unicode_to_bytes()
+    b2u = {b: u for u, b in u2b.items()}
+    ids = [enc[b2u[c]] for c in PROMPT]
+    zo.use_scalar_blas()
+    orc = zo.Model(CFG, w)
+    toks = orc.generate_greedy(np.array(ids), len(ids) + 8)
+    orc.close()
+    dec = zo.Encoder(enc, u2b)
+    want = b"".join(dec.decode([int(t)]) for t in toks) + b"\n"
+    got = run_cli(exe, d, "--greedy", "--max-tokens", "8", "--tokenizer", "gpt2", "--merges", str(merges))
+    assert got == want

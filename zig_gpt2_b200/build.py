@@ -75,7 +75,7 @@ def build_cli(force: bool = False) -> str:
     libzg_b200.so (found through $ORIGIN at run time).  The CUDA driver library only exists on the GPU box, hence
     --allow-shlib-undefined."""
     host_dir = os.path.join(CSRC, "host")
-    srcs = [os.path.join(host_dir, "main.cpp"), os.path.join(host_dir, "bpe.cpp")]
+    srcs = [os.path.join(host_dir, "main.cpp"), os.path.join(host_dir, "bpe.cpp"), os.path.join(host_dir, "bpe_gpt2.cpp")]
     deps = srcs + [os.path.join(host_dir, f) for f in os.listdir(host_dir) if f.endswith((".h", ".hpp"))] + [OUT]
     if not force and os.path.exists(CLI_OUT) and all(os.path.getmtime(p) <= os.path.getmtime(CLI_OUT) for p in deps):
         return CLI_OUT

@@ -84,15 +84,17 @@ struct SplitMix64 {
 
 // generate (main.zig:322-342): prompt tokens one at a time without logits, then sampling up to n_total; the last
 // prompt token is forwarded twice, as in the reference.  Every token (prompt included) is decoded and emitted.
-inline void generate(GPT &gpt, const Encoder &encoder, float temp, const std::vector<size_t> &inputs, size_t n_total,
-                     bool greedy, uint64_t seed, const std::function<void(const std::string &)> &emit) {
+// `decode` turns one token id into its bytes: Encoder::decode (bpe.zig:99-118) or the fidelity tokenizer's.
+inline void generate(GPT &gpt, const std::function<void(size_t, std::string *)> &decode, float temp,
+                     const std::vector<size_t> &inputs, size_t n_total, bool greedy, uint64_t seed,
+                     const std::function<void(const std::string &)> &emit) {
   std::string piece;
   if (greedy) {  // one persistent-kernel launch for the whole loop
     std::vector<size_t> toks;
     if (gpt.generate_greedy(inputs, n_total, &toks) != 0) return;
     for (size_t t : toks) {
       piece.clear();
-      encoder.decode(&t, 1, &piece);
+      decode(t, &piece);
       emit(piece);
     }
     return;
@@ -107,9 +109,13 @@ inline void generate(GPT &gpt, const Encoder &encoder, float temp, const std::ve
       token = gpt.sample(s + 1, temp, token, rng.next());
     }
     piece.clear();
-    encoder.decode(&token, 1, &piece);
+    decode(token, &piece);
     emit(piece);
   }
+}
+inline void generate(GPT &gpt, const Encoder &encoder, float temp, const std::vector<size_t> &inputs, size_t n_total,
+                     bool greedy, uint64_t seed, const std::function<void(const std::string &)> &emit) {
+  generate(gpt, [&](size_t t, std::string *out) { encoder.decode(&t, 1, out); }, temp, inputs, n_total, greedy, seed, emit);
 }
 
 }  // namespace zgh
