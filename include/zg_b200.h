@@ -55,6 +55,11 @@ unsigned long long zg_launch_count(void);
  * zg_engine_generate_greedy / zg_engine_run_steps / zg_engine_forward / zg_batch_forward / zg_batch_run_steps once the
  * engine exists (tests/test_gpu_model.py, tests/test_gpu_batch.py assert it). */
 unsigned long long zg_alloc_count(void);
+/* Philox4x32-10 counter-based generator behind the sampling paths: the uniform draw in [0,1) of sampling step `step` of
+ * sequence `sequence` under `seed` -- a pure function, identical on host and device (csrc/zg_philox.cuh).  The
+ * reference re-seeds its PRNG from the wall clock on every GPT.sample call (main.zig:204), which cannot be reproduced. */
+double zg_philox_uniform(unsigned long long seed, unsigned long long step, unsigned long long sequence);
+void zg_philox4x32_10(const unsigned counter[4], const unsigned key[2], unsigned out[4]); /* the raw block function (known-answer tests) */
 /* CUDA-event stopwatch on the library's stream (bench.py times kernels on the stream they are launched on). */
 int zg_timer_begin(void);
 float zg_timer_end_ms(void); /* records the stop event, synchronises, returns elapsed milliseconds */
@@ -196,6 +201,10 @@ size_t zg_engine_sample(zg_engine *e, size_t seq_len, float temp, size_t token, 
  * written to out_tokens (HOST).  One kernel launch covers all steps; tokens are also streamed into a pinned
  * host ring as they are produced.  Returns 0 or an error code. */
 int zg_engine_generate_greedy(zg_engine *e, const size_t *inputs, size_t n_inputs, size_t n_total, size_t *out_tokens);
+/* generate() with GPT.sample (main.zig:198-207, 322-342) instead of greedy argmax, device resident: temperature softmax and
+ * inverse-CDF draw run on the device with u = zg_philox_uniform(seed, step, sequence); one wait for the whole call. */
+int zg_engine_generate_sample(zg_engine *e, const size_t *inputs, size_t n_inputs, size_t n_total, float temp,
+                              unsigned long long seed, unsigned long long sequence, size_t *out_tokens);
 /* Device-only variant for timing: runs steps [first_step, first_step + n_steps) of a generation whose prompt
  * (device-resident copy made by zg_engine_set_prompt) has n_inputs tokens.  Asynchronous. */
 int zg_engine_set_prompt(zg_engine *e, const size_t *inputs, size_t n_inputs);
@@ -235,6 +244,9 @@ int zg_batch_prefill_resident(zg_batch *e, size_t T, int compute_logits); /* tok
 /* generate() (main.zig:322-342), greedy, per sequence: prompts[b*n_inputs + s] (HOST) -> out_tokens[b*n_total + s] (HOST). */
 int zg_batch_generate_greedy(zg_batch *e, const size_t *prompts, size_t n_inputs, size_t n_total, size_t *out_tokens,
                              int use_prefill);
+/* the same with GPT.sample: sequence b draws u = zg_philox_uniform(seed, step, seq_base + b) at every sampling step */
+int zg_batch_generate_sample(zg_batch *e, const size_t *prompts, size_t n_inputs, size_t n_total, float temp,
+                             unsigned long long seed, unsigned long long seq_base, size_t *out_tokens, int use_prefill);
 void zg_batch_set_position(zg_batch *e, size_t pos); /* next step attends to cache rows [0, pos] (timing at a given context) */
 void zg_batch_run_steps(zg_batch *e, size_t n_steps); /* n greedy steps from the current position, device resident, async */
 int zg_batch_fused_argmax(const zg_batch *e); /* 1 when the decode step runs the stream-K GEMMs (n_seqs <= 128) and fuses the argmax */

@@ -80,6 +80,20 @@ class BatchEngine:
             raise _lib.ZgError(f"zg_batch_generate_greedy -> {rc}")
         return out.reshape(self.n_seqs, n_total).astype(np.int64)
 
+    def generate_sample(self, prompts: np.ndarray, n_total: int, temp: float, seed: int, seq_base: int = 0,
+                        use_prefill: bool = False) -> np.ndarray:
+        """generate() with GPT.sample per sequence; sequence b draws u = zg_philox_uniform(seed, step, seq_base + b)."""
+        prompts = np.asarray(prompts)
+        assert prompts.ndim == 2 and prompts.shape[0] == self.n_seqs
+        p = self._tok(prompts, prompts.size)
+        out = np.zeros(self.n_seqs * n_total, np.uint64)
+        rc = _lib.load().zg_batch_generate_sample(self._h, p.ctypes.data_as(_lib.c_size_p), prompts.shape[1], n_total, temp,
+                                                  seed, seq_base, out.ctypes.data_as(_lib.c_size_p), int(use_prefill))
+        _lib.check()
+        if rc:
+            raise _lib.ZgError(f"zg_batch_generate_sample -> {rc}")
+        return out.reshape(self.n_seqs, n_total).astype(np.int64)
+
     def read_tokens(self) -> np.ndarray:
         """argmax token of every sequence's last sampling step."""
         out = np.zeros(self.n_seqs, np.uint64)

@@ -55,6 +55,11 @@ class GPT {  // main.zig:149-208; owns the device model, the preallocated State 
     return zg_engine_sample(engine_, seq_len, temp, token, u);
   }
   size_t sample_greedy(size_t seq_len, size_t token) { return zg_engine_sample_greedy(engine_, seq_len, token); }
+  // the whole sampling loop on the device, u(step) = zg_philox_uniform(seed, step, 0): reproducible with --seed
+  int generate_sample(const std::vector<size_t> &inputs, size_t n_total, float temp, uint64_t seed, std::vector<size_t> *out) {
+    out->assign(n_total, 0);
+    return zg_engine_generate_sample(engine_, inputs.data(), inputs.size(), n_total, temp, seed, 0, out->data());
+  }
   int generate_greedy(const std::vector<size_t> &inputs, size_t n_total, std::vector<size_t> *out) {
     out->assign(n_total, 0);
     return zg_engine_generate_greedy(engine_, inputs.data(), inputs.size(), n_total, out->data());
@@ -69,19 +74,6 @@ class GPT {  // main.zig:149-208; owns the device model, the preallocated State 
   bool loaded_ = false;
 };
 
-// xoshiro-free, seedable uniform source (the reference seeds std.rand.DefaultPrng from wall-clock seconds on
-// every call, main.zig:204, which cannot be reproduced; splitmix64 with --seed can)
-struct SplitMix64 {
-  uint64_t s;
-  double next() {
-    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
-  }
-};
-
 // generate (main.zig:322-342): prompt tokens one at a time without logits, then sampling up to n_total; the last
 // prompt token is forwarded twice, as in the reference.  Every token (prompt included) is decoded and emitted.
 // `decode` turns one token id into its bytes: Encoder::decode (bpe.zig:99-118) or the fidelity tokenizer's.
@@ -89,27 +81,14 @@ inline void generate(GPT &gpt, const std::function<void(size_t, std::string *)> 
                      const std::vector<size_t> &inputs, size_t n_total, bool greedy, uint64_t seed,
                      const std::function<void(const std::string &)> &emit) {
   std::string piece;
-  if (greedy) {  // one persistent-kernel launch for the whole loop
-    std::vector<size_t> toks;
-    if (gpt.generate_greedy(inputs, n_total, &toks) != 0) return;
-    for (size_t t : toks) {
-      piece.clear();
-      decode(t, &piece);
-      emit(piece);
-    }
-    return;
-  }
-  SplitMix64 rng{seed};
-  size_t token = 0;
-  for (size_t s = 0; s < n_total; ++s) {
-    if (s < inputs.size()) {
-      token = inputs[s];
-      gpt.forward(s + 1, token, false);
-    } else {
-      token = gpt.sample(s + 1, temp, token, rng.next());
-    }
+  // greedy: one persistent-kernel launch for the whole loop; sampling: one launch + one sampling kernel per token,
+  // still without a host round trip (GPT.sample's draw comes from the counter-based generator, main.zig:198-207)
+  std::vector<size_t> toks;
+  const int rc = greedy ? gpt.generate_greedy(inputs, n_total, &toks) : gpt.generate_sample(inputs, n_total, temp, seed, &toks);
+  if (rc != 0) return;
+  for (size_t t : toks) {
     piece.clear();
-    decode(token, &piece);
+    decode(t, &piece);
     emit(piece);
   }
 }

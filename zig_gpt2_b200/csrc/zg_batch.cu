@@ -19,6 +19,8 @@
 #include "zg_skinny.cuh"
 
 namespace zg {
+void launch_sample_rows(const float *logits, size_t pitch, int V, const void *sample_params_dev, const int *step_dev, int step,
+                        unsigned long long *tok, unsigned long long *hist, int B, unsigned long long *host_ring);
 
 namespace {
 
@@ -266,6 +268,8 @@ struct zg_batch {
   std::vector<SkinnyLayerPlans> sk_plans;  // decode step with <= 128 sequences: swapped-operand stream-K GEMMs
   SkinnyPlan sk_head;                      // tied lm_head with the argmax in its epilogue (no logits leave the kernel)
   unsigned long long *best = nullptr;      // [B][2] packed (orderable logit, ~column) words of the fused argmax
+  void *samp = nullptr;                    // device {temp, seed, seq_base} of the sampling generate loop
+  cudaGraphExec_t graph_sampling = nullptr;
   bool skinny = false;
   GemmPlan dec_head, pre_head;
   std::vector<AttnPrefillPlan> pre_attn;
@@ -383,7 +387,7 @@ bool build_prefill_plans(zg_batch *e, int T) {
 
 // One decode step for every sequence at position *pos: GPT.forward(seq_len = *pos + 1, tok[b]) (main.zig:178-195).
 // head: 0 = no logits, 1 = logits in e->logits + argmax over them, 2 = argmax only, fused into the lm_head GEMM when the
-// stream-K path is active (greedy generate / run_steps never need the logits themselves)
+// stream-K path is active (greedy generate / run_steps never need the logits themselves), 3 = logits + sampled token
 void enqueue_step(zg_batch *e, bool from_prompt, int n_inputs, int head) {
   cudaStream_t s = ctx().stream;
   const int B = e->B, E = (int)e->cfg.n_embed, H = (int)e->cfg.n_heads, V = (int)e->cfg.vocab_size;
@@ -424,8 +428,12 @@ void enqueue_step(zg_batch *e, bool from_prompt, int n_inputs, int head) {
   } else if (head) {
     launch_ln_rows<false>(e->x, E, e->h, e->lnf_g, e->lnf_b, E, B, s);  // main.zig:189
     gemm_launch(e->dec_head);  // tied lm_head (main.zig:192-194)
-    argmax_rows_kernel<<<B, 256, 0, s>>>(e->logits, (size_t)e->Vp, V, e->tok, e->hist, B, e->pos);
-    ZG_LAUNCH_CHECK();
+    if (head == 3) {  // GPT.sample (main.zig:198-207): temperature softmax + inverse-CDF draw per sequence, on the device
+      launch_sample_rows(e->logits, (size_t)e->Vp, V, e->samp, e->pos, 0, e->tok, e->hist, B, nullptr);
+    } else {
+      argmax_rows_kernel<<<B, 256, 0, s>>>(e->logits, (size_t)e->Vp, V, e->tok, e->hist, B, e->pos);
+      ZG_LAUNCH_CHECK();
+    }
   }
   set_pos_kernel<<<1, 1, 0, s>>>(e->pos, 1, 1);
   ZG_LAUNCH_CHECK();
@@ -541,6 +549,7 @@ zg_batch *zg_batch_create(const zg_gpt *gpt, size_t n_seqs, size_t cache_rows, s
   note_alloc();
   e->pos = balloc<int>(e, 4);
   e->best = balloc<unsigned long long>(e, 2 * B);
+  e->samp = balloc<unsigned long long>(e, 8);
   if (e->f16_prefill) {
     const size_t M = B * max_prompt;
     e->px = balloc<float>(e, M * E);
@@ -578,6 +587,7 @@ void zg_batch_destroy(zg_batch *e) {
   if (ctx().ready) cudaStreamSynchronize(ctx().stream);
   if (e->graph_sample) cudaGraphExecDestroy(e->graph_sample);
   if (e->graph_prompt) cudaGraphExecDestroy(e->graph_prompt);
+  if (e->graph_sampling) cudaGraphExecDestroy(e->graph_sampling);
   for (void *p : e->owned) zg_free(p);
   if (e->hist_host) cudaFreeHost(e->hist_host);
   delete e;
@@ -633,9 +643,8 @@ int zg_batch_prefill_resident(zg_batch *e, size_t T, int compute_logits) {
 // Steps s < n_inputs forward the prompt (one token at a time like the reference, or all at once when use_prefill);
 // step n_inputs forwards the last prompt token again (the reference's duplicate, main.zig:329-338); every step's
 // token goes to out_tokens[b*n_total + s] (HOST).  Asynchronous until the final copy.
-int zg_batch_generate_greedy(zg_batch *e, const size_t *prompts, size_t n_inputs, size_t n_total, size_t *out_tokens,
-                             int use_prefill) {
-  if (!require_ready("zg_batch_generate_greedy")) return 1;
+static int batch_generate(zg_batch *e, const size_t *prompts, size_t n_inputs, size_t n_total, size_t *out_tokens,
+                          int use_prefill, bool sample) {
   const int B = e->B;
   if (n_inputs == 0 || n_inputs > n_total || n_total > (size_t)e->cap || n_total > e->hist_cap) {
     set_error(1, "zg_batch_generate_greedy: need 1 <= n_inputs <= n_total <= cache rows", __FILE__, __LINE__);
@@ -663,7 +672,8 @@ int zg_batch_generate_greedy(zg_batch *e, const size_t *prompts, size_t n_inputs
     ZG_LAUNCH_CHECK();
   }
   if (e->use_graph) {
-    if (!e->graph_sample && !capture(e, &e->graph_sample, false, 0, 2)) e->use_graph = false;
+    if (!sample && !e->graph_sample && !capture(e, &e->graph_sample, false, 0, 2)) e->use_graph = false;
+    if (sample && !e->graph_sampling && !capture(e, &e->graph_sampling, false, 0, 3)) e->use_graph = false;
     if (e->use_graph && first < n_inputs && (e->graph_n_inputs != (int)n_inputs || !e->graph_prompt)) {
       if (e->graph_prompt) cudaGraphExecDestroy(e->graph_prompt);
       e->graph_prompt = nullptr;
@@ -674,10 +684,10 @@ int zg_batch_generate_greedy(zg_batch *e, const size_t *prompts, size_t n_inputs
   for (size_t st = first; st < n_total; ++st) {
     const bool prompt_step = st < n_inputs;
     if (e->use_graph) {
-      ZG_CUDA(cudaGraphLaunch(prompt_step ? e->graph_prompt : e->graph_sample, s));
+      ZG_CUDA(cudaGraphLaunch(prompt_step ? e->graph_prompt : (sample ? e->graph_sampling : e->graph_sample), s));
       ctx().launches += prompt_step ? 2 + 7 * e->layers.size() + 1 : 1 + 7 * e->layers.size() + 4;
     } else {
-      enqueue_step(e, prompt_step, (int)n_inputs, prompt_step ? 0 : 2);
+      enqueue_step(e, prompt_step, (int)n_inputs, prompt_step ? 0 : (sample ? 3 : 2));
     }
   }
   e->host_pos = (int)n_total;
@@ -688,6 +698,26 @@ int zg_batch_generate_greedy(zg_batch *e, const size_t *prompts, size_t n_inputs
     for (int b = 0; b < B; ++b) out_tokens[(size_t)b * n_total + st] = (size_t)e->hist_host[st * B + b];
   if (zg_tc_error()) set_error(1, "tensor-core kernel watchdog tripped", __FILE__, __LINE__);
   return zg_last_error();
+}
+
+int zg_batch_generate_greedy(zg_batch *e, const size_t *prompts, size_t n_inputs, size_t n_total, size_t *out_tokens,
+                             int use_prefill) {
+  if (!require_ready("zg_batch_generate_greedy")) return 1;
+  return batch_generate(e, prompts, n_inputs, n_total, out_tokens, use_prefill, false);
+}
+
+// generate() with temperature sampling for every sequence: sequence b of this engine draws its step-s uniform as
+// philox_uniform(seed, s, seq_base + b), so a sequence's tokens do not depend on which GPU / batch slot it runs in.
+int zg_batch_generate_sample(zg_batch *e, const size_t *prompts, size_t n_inputs, size_t n_total, float temp,
+                             unsigned long long seed, unsigned long long seq_base, size_t *out_tokens, int use_prefill) {
+  if (!require_ready("zg_batch_generate_sample")) return 1;
+  if (!(temp > 0.0f)) {
+    set_error(1, "zg_batch_generate_sample: temp must be > 0", __FILE__, __LINE__);
+    return 1;
+  }
+  struct { float temp; unsigned long long seed, seq_base; } sp = {temp, seed, seq_base};
+  ZG_CUDA(cudaMemcpyAsync(e->samp, &sp, sizeof(sp), cudaMemcpyHostToDevice, ctx().stream));
+  return batch_generate(e, prompts, n_inputs, n_total, out_tokens, use_prefill, true);
 }
 
 // Device-resident stepping for timing: run n_steps sampling steps from the current position (no host copies).

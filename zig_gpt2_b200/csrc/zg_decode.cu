@@ -45,6 +45,8 @@
 #include "zg_ptx.cuh"
 
 namespace zg {
+void launch_sample_rows(const float *logits, size_t pitch, int V, const void *sample_params_dev, const int *step_dev, int step,
+                        unsigned long long *tok, unsigned long long *hist, int B, unsigned long long *host_ring);
 void launch_softmax_temp(float *x, size_t n, float temp);
 void launch_weighted_index(const float *p, size_t n, float u, unsigned long long *out);
 
@@ -1417,6 +1419,7 @@ struct zg_engine {
   u64 *last_token_dev;
   u64 *prof_dev;
   unsigned *err_dev;
+  void *samp_dev;  // {temp, seed, sequence} of the sampling generate loop (zg_engine_generate_sample)
   unsigned epoch_count;  // host mirror of the phase epoch (monotonic across launches)
   int grid;
   size_t smem_bytes;
@@ -1525,6 +1528,7 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
   e->last_token_dev = (u64 *)zg_alloc(8);
   e->prof_dev = (u64 *)zg_alloc((2 * PROF_MAX + 4) * 8);
   e->err_dev = (unsigned *)zg_alloc(256);
+  e->samp_dev = zg_alloc(64);
   ZG_CUDA(cudaHostAlloc(&e->tokens_host, C * 8, cudaHostAllocMapped));
   note_alloc();
   ZG_CUDA(cudaHostGetDevicePointer((void **)&e->tokens_host_devptr, e->tokens_host, 0));
@@ -1566,7 +1570,7 @@ void zg_engine_destroy(zg_engine *e) {
   zg_sync();
   if (g_table_owner == e) g_table_owner = nullptr;
   zg_free(e->exchange_dev); zg_free(e->derived_dev); zg_free(e->prompt_dev); zg_free(e->tokens_dev); zg_free(e->last_token_dev);
-  zg_free(e->prof_dev); zg_free(e->err_dev);
+  zg_free(e->prof_dev); zg_free(e->err_dev); zg_free(e->samp_dev);
   cudaFreeHost(e->tokens_host);
   free(e->layers_host);
   free(e);
@@ -1691,6 +1695,38 @@ int zg_engine_generate_greedy(zg_engine *e, const size_t *inputs, size_t n_input
   if (zg_engine_set_prompt(e, inputs, n_inputs)) return zg_last_error();
   zg_engine_run_steps(e, 0, n_total);
   // tokens were streamed into the pinned ring as they were produced; one wait for the whole call
+  ZG_CUDA(cudaStreamSynchronize(ctx().stream));
+  for (size_t i = 0; i < n_total; ++i) out_tokens[i] = (size_t)e->tokens_host[i];
+  return engine_check_watchdog(e);
+}
+
+// generate() with temperature sampling (main.zig:322-342 with GPT.sample, :198-207), device resident: every sampling step is
+// one persistent-kernel launch that leaves the logits in state.logits plus one sampling kernel (logits / temp, softmax,
+// inverse-CDF draw with u = philox_uniform(seed, step, sequence)) that writes the token where the next launch reads it.
+// No host round trip per token; the host waits once.  Greedy semantics otherwise: prompt tokens are forwarded without
+// logits, the last prompt token is forwarded twice.
+int zg_engine_generate_sample(zg_engine *e, const size_t *inputs, size_t n_inputs, size_t n_total, float temp,
+                              unsigned long long seed, unsigned long long sequence, size_t *out_tokens) {
+  if (!require_ready("zg_engine_generate_sample")) return 1;
+  if (n_inputs == 0 || n_total > e->cfg.context_size || n_inputs > n_total || !(temp > 0.0f)) {
+    set_error(1, "zg_engine_generate_sample: need 1 <= n_inputs <= n_total <= context_size and temp > 0", __FILE__, __LINE__);
+    return 1;
+  }
+  if (zg_engine_set_prompt(e, inputs, n_inputs)) return zg_last_error();
+  struct { float temp; unsigned long long seed, seq_base; } sp = {temp, seed, sequence};
+  ZG_CUDA(cudaMemcpyAsync(e->samp_dev, &sp, sizeof(sp), cudaMemcpyHostToDevice, ctx().stream));
+  zg_engine_run_steps(e, 0, n_inputs);
+  for (size_t s = n_inputs; s < n_total; ++s) {
+    DecodeParams p = e->base;
+    p.prompt = e->prompt_dev;
+    p.n_prompt = e->n_prompt;
+    p.first_step = (int)s;
+    p.n_steps = 1;
+    p.store_logits = 1;
+    engine_launch(e, p);
+    launch_sample_rows(e->state.logits, e->cfg.vocab_size, (int)e->cfg.vocab_size, e->samp_dev, nullptr, (int)s,
+                       e->tokens_dev + s, nullptr, 1, e->tokens_host_devptr + s);
+  }
   ZG_CUDA(cudaStreamSynchronize(ctx().stream));
   for (size_t i = 0; i < n_total; ++i) out_tokens[i] = (size_t)e->tokens_host[i];
   return engine_check_watchdog(e);

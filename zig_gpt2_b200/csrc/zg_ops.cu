@@ -2,6 +2,7 @@
 // through the C-ABI of include/zg_b200.h.  fp32 storage, fp32 accumulation (the reference's arithmetic
 // type).  All pointers are device pointers unless stated otherwise; every call enqueues on ctx().stream.
 #include "zg_common.cuh"
+#include "zg_philox.cuh"
 
 namespace zg {
 
@@ -309,6 +310,55 @@ __global__ void __launch_bounds__(1024) weighted_index_kernel(const float *__res
   }
 }
 
+
+// GPT.sample's tail for B rows at once (main.zig:200-206): logits / temp, softmax, weightedIndex -- without writing the
+// probabilities back.  Row b draws u = philox_uniform(seed, step, seq_base + b).  One CTA per row: pass 1 the row
+// maximum, pass 2 per-thread chunk sums of e^((x - max) / temp), then thread 0 walks the 1,024 chunk sums to the chunk
+// that brackets u * total and scans inside it sequentially in fp32, like the reference's loop.
+struct SampleParams { float temp; unsigned long long seed, seq_base; };
+__global__ void __launch_bounds__(1024) sample_rows_kernel(const float *__restrict__ logits, size_t pitch, int V,
+                                                           const SampleParams *__restrict__ sp, const int *step_dev, int step,
+                                                           unsigned long long *__restrict__ tok, unsigned long long *__restrict__ hist,
+                                                           int B, unsigned long long *__restrict__ host_ring) {
+  __shared__ float chunk_sum[1024];
+  __shared__ float red[32];
+  const float *row = logits + (size_t)blockIdx.x * pitch;
+  const float inv_t = 1.0f / sp->temp;
+  const int st = step_dev ? *step_dev : step;
+  const int per = (V + blockDim.x - 1) / blockDim.x;
+  const int lo = threadIdx.x * per, hi = min(lo + per, V);
+  float m = -INFINITY;
+  for (int i = lo; i < hi; ++i) m = fmaxf(m, row[i] * inv_t);
+  m = block_max(m, red);
+  __syncthreads();
+  float s = 0.0f;
+  for (int i = lo; i < hi; ++i) s += expf(row[i] * inv_t - m);
+  chunk_sum[threadIdx.x] = s;
+  const float total = block_sum(s, red);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float u = philox_uniform(sp->seed, (unsigned long long)st, sp->seq_base + blockIdx.x);
+    const float point = u * total;
+    float acc = 0.0f;
+    int ans = V - 1;
+    bool found = false;
+    for (unsigned c = 0; c < blockDim.x && !found; ++c) {
+      if (point < acc + chunk_sum[c]) {
+        const int clo = c * per, chi = min(clo + per, V);
+        for (int i = clo; i < chi; ++i) {
+          acc += expf(row[i] * inv_t - m);
+          if (point < acc) { ans = i; found = true; break; }
+        }
+      } else {
+        acc += chunk_sum[c];
+      }
+    }
+    tok[blockIdx.x] = (unsigned long long)ans;
+    if (hist) hist[(size_t)st * B + blockIdx.x] = (unsigned long long)ans;
+    if (host_ring) host_ring[blockIdx.x] = (unsigned long long)ans;
+  }
+}
+
 }  // namespace zg
 
 // =================================================================================================
@@ -452,6 +502,12 @@ void launch_argmax(const float *logits, size_t n, unsigned long long *out) {
 }
 void launch_softmax_temp(float *x, size_t n, float temp) {
   softmax_kernel<<<1, 1024, 0, ctx().stream>>>(x, n, temp);
+  ZG_LAUNCH_CHECK();
+}
+void launch_sample_rows(const float *logits, size_t pitch, int V, const void *sample_params_dev, const int *step_dev, int step,
+                        unsigned long long *tok, unsigned long long *hist, int B, unsigned long long *host_ring) {
+  sample_rows_kernel<<<B, 1024, 0, ctx().stream>>>(logits, pitch, V, (const SampleParams *)sample_params_dev, step_dev, step, tok,
+                                                   hist, B, host_ring);
   ZG_LAUNCH_CHECK();
 }
 void launch_weighted_index(const float *p, size_t n, float u, unsigned long long *out) {

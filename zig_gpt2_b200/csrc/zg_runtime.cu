@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "zg_common.cuh"
+#include "zg_philox.cuh"
 
 namespace zg {
 
@@ -192,6 +193,15 @@ int zg_set_stream(void *s) {
   if (!require_ready("zg_set_stream")) return 1;
   ctx().stream = s ? (cudaStream_t)s : ctx().own_stream;
   return 0;
+}
+
+// the uniform draw of sampling step `step` of sequence `sequence` (host copy of the device function: no device needed)
+double zg_philox_uniform(unsigned long long seed, unsigned long long step, unsigned long long sequence) {
+  return (double)philox_uniform(seed, step, sequence);
+}
+void zg_philox4x32_10(const unsigned counter[4], const unsigned key[2], unsigned out[4]) {
+  const Philox4 r = philox4x32_10(counter[0], counter[1], counter[2], counter[3], key[0], key[1]);
+  for (int i = 0; i < 4; ++i) out[i] = r.v[i];
 }
 
 unsigned long long zg_launch_count(void) { return ctx().launches; }

@@ -125,6 +125,19 @@ class GPT:  # main.zig:149-208
             raise _lib.ZgError(f"zg_engine_generate_greedy -> {rc}")
         return out.astype(np.int64)
 
+    def generate_sample(self, inputs: Sequence[int], n_total: int, state: State, temp: float, seed: int,
+                        sequence: int = 0) -> np.ndarray:
+        """generate() with GPT.sample (main.zig:198-207): temperature softmax + inverse-CDF draw on the device, the
+        uniform of step s being zg_philox_uniform(seed, s, sequence); no host round trip per token."""
+        p = np.ascontiguousarray(inputs, np.uint64)
+        out = np.zeros(n_total, np.uint64)
+        rc = _lib.load().zg_engine_generate_sample(self.engine(state), p.ctypes.data_as(_lib.c_size_p), p.size, n_total,
+                                                   temp, seed, sequence, out.ctypes.data_as(_lib.c_size_p))
+        _lib.check()
+        if rc:
+            raise _lib.ZgError(f"zg_engine_generate_sample -> {rc}")
+        return out.astype(np.int64)
+
     def close(self):
         if self._engine is not None:
             _lib.load().zg_engine_destroy(self._engine)
@@ -182,7 +195,7 @@ def gpt_from_numpy(config: GPTConfig, weights: "Dict[str, np.ndarray]") -> GPT:
 
 
 def generate(gpt: GPT, encoder, temp: float, inputs: Sequence[int], state: State, n_total: Optional[int] = None,
-             greedy: bool = False, emit: Callable[[bytes], None] = lambda b: None, rng=None) -> List[int]:
+             greedy: bool = False, emit: Callable[[bytes], None] = lambda b: None, rng=None, seed: Optional[int] = None) -> List[int]:
     """generate (main.zig:322-342): prompt tokens are forwarded one at a time without logits, then tokens are
     sampled up to context_size; the LAST PROMPT TOKEN IS FORWARDED TWICE (main.zig:329-338), as in the
     reference.  Every token (prompt included) is decoded and emitted (main.zig:339-340)."""
@@ -190,6 +203,13 @@ def generate(gpt: GPT, encoder, temp: float, inputs: Sequence[int], state: State
     out: List[int] = []
     if greedy:
         toks = gpt.generate_greedy(inputs, n_total, state)
+        for t in toks:
+            out.append(int(t))
+            if encoder is not None:
+                emit(encoder.decode([int(t)]))
+        return out
+    if seed is not None:  # device-resident sampling loop, reproducible: u(step) = Philox(seed, step, 0)
+        toks = gpt.generate_sample(inputs, n_total, state, temp, seed)
         for t in toks:
             out.append(int(t))
             if encoder is not None:

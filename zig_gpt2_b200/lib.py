@@ -63,6 +63,8 @@ SIGNATURES = {
     "zg_upload": (I, [P, P, Z]), "zg_download": (I, [P, P, Z]), "zg_sync": (I, []),
     "zg_last_error": (I, []), "zg_last_error_string": (C.c_char_p, []), "zg_clear_error": (V, []),
     "zg_set_stream": (I, [P]), "zg_launch_count": (C.c_ulonglong, []), "zg_alloc_count": (C.c_ulonglong, []),
+    "zg_philox_uniform": (C.c_double, [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong]),
+    "zg_philox4x32_10": (V, [C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "zg_timer_begin": (I, []), "zg_timer_end_ms": (C.c_float, []),
     "zg_linear_forward": (V, [C.POINTER(ZgLinear), P, Z, P]),
     "zg_linear_forward_tc": (V, [C.POINTER(ZgLinear), P, Z, P, I, P, I, P, I]),
@@ -89,6 +91,7 @@ SIGNATURES = {
     "zg_engine_forward": (V, [P, Z, Z, I]), "zg_engine_sample_greedy": (Z, [P, Z, Z]),
     "zg_engine_sample": (Z, [P, Z, C.c_float, Z, C.c_double]),
     "zg_engine_generate_greedy": (I, [P, c_size_p, Z, Z, c_size_p]),
+    "zg_engine_generate_sample": (I, [P, c_size_p, Z, Z, C.c_float, C.c_ulonglong, C.c_ulonglong, c_size_p]),
     "zg_engine_set_prompt": (I, [P, c_size_p, Z]), "zg_engine_run_steps": (V, [P, Z, Z]),
     "zg_engine_read_tokens": (I, [P, Z, Z, c_size_p]),
     "zg_engine_read_profile": (Z, [P, C.POINTER(C.c_ulonglong), Z]),
@@ -96,6 +99,7 @@ SIGNATURES = {
     "zg_batch_forward": (V, [P, Z, c_size_p, I]), "zg_batch_logits": (P, [P]), "zg_batch_logits_pitch": (Z, [P]),
     "zg_batch_prefill": (I, [P, c_size_p, Z, I]), "zg_batch_prefill_resident": (I, [P, Z, I]),
     "zg_batch_generate_greedy": (I, [P, c_size_p, Z, Z, c_size_p, I]),
+    "zg_batch_generate_sample": (I, [P, c_size_p, Z, Z, C.c_float, C.c_ulonglong, C.c_ulonglong, c_size_p, I]),
     "zg_batch_set_position": (V, [P, Z]), "zg_batch_run_steps": (V, [P, Z]),
     "zg_batch_read_tokens": (I, [P, c_size_p]), "zg_batch_fused_argmax": (I, [P]),
     "zg_batch_k_cache": (P, [P, Z]), "zg_batch_v_cache": (P, [P, Z]),
