@@ -227,7 +227,9 @@ size_t zg_engine_read_profile(zg_engine *e, unsigned long long *out, size_t max_
 typedef struct zg_batch zg_batch;
 /* start-up: caches for n_seqs sequences of up to cache_rows positions, activation sets, plans (tensor maps), f16
  * weight copies when max_prompt > 0 (prefill enabled for prompts up to max_prompt tokens).  flags bit 0: no CUDA graph;
- * bit 1: single-pass TF32 decode GEMMs instead of the error-compensated 3xTF32 default; bit 3: never the swapped-operand
+ * bit 1: single-pass TF32 decode GEMMs instead of the error-compensated 3xTF32 default; bit 2: fp32-class prefill (3xTF32
+ * GEMMs on fp32 activations + fp32 causal attention) instead of the f16 pipeline -- the prefilled generate() is then
+ * token-identical to the reference's token-at-a-time prompt loop, at about a third of the f16 prefill's speed; bit 3: never the swapped-operand
  * stream-K GEMMs (the default decode step for n_seqs <= 128, zg_linear_forward_skinny), always the general kernel. */
 zg_batch *zg_batch_create(const zg_gpt *gpt, size_t n_seqs, size_t cache_rows, size_t max_prompt, int flags);
 void zg_batch_destroy(zg_batch *e);

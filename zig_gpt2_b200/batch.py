@@ -14,13 +14,14 @@ from .gpt import GPT
 
 class BatchEngine:
     def __init__(self, gpt: GPT, n_seqs: int, cache_rows: Optional[int] = None, max_prompt: int = 0, graph: bool = True,
-                 tf32_single_pass: bool = False, general_gemm_only: bool = False):
+                 tf32_single_pass: bool = False, general_gemm_only: bool = False, exact_prefill: bool = False):
         self.gpt, self.n_seqs = gpt, int(n_seqs)
         self.cache_rows = int(cache_rows or gpt.config.context_size)
         self.max_prompt = int(max_prompt)
         L = _lib.load()
         self._h = L.zg_batch_create(C.byref(gpt.c), self.n_seqs, self.cache_rows, self.max_prompt,
-                                    (0 if graph else 1) | (2 if tf32_single_pass else 0) | (8 if general_gemm_only else 0))
+                                    (0 if graph else 1) | (2 if tf32_single_pass else 0) | (4 if exact_prefill else 0) |
+                                    (8 if general_gemm_only else 0))
         _lib.check()
         if not self._h:
             raise _lib.ZgError("zg_batch_create failed")

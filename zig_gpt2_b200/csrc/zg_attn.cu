@@ -274,16 +274,21 @@ constexpr int DEC_WARPS = 8;
 
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 attn_decode_batch_kernel(const float *__restrict__ q, int ldq, const float *k_cache, const float *v_cache, long long seq_stride, int E, float *__restrict__ out, int ldo,
-                         const int *pos_dev, int pos_base, const float *knew, const float *vnew, int trigger) {
+                         const int *pos_dev, int pos_base, const float *knew, const float *vnew, int trigger,
+                         int rows_per_seq) {
   __shared__ float s_m[DEC_WARPS], s_l[DEC_WARPS];
   __shared__ float s_o[DEC_WARPS][HD];
-  const int h = blockIdx.x, b = blockIdx.y;
+  // rows_per_seq == 0: decode step, row blockIdx.y = sequence b at the common position.  rows_per_seq = T_prompt > 0:
+  // fp32-class causal prefill -- row blockIdx.y = (b, t) attends to cache rows [0, t] of sequence b, which is what t + 1
+  // calls of CausalSelfAttention.forward leave in _q (ops.zig:129-173; tests.zig:245-334 proves the equivalence).
+  const int h = blockIdx.x, qrow = blockIdx.y;
+  const int b = rows_per_seq ? qrow / rows_per_seq : qrow;
   if (trigger) pdl_trigger();  // the c_proj GEMM that follows fills its ring with weights while the caches stream
   pdl_wait();  // q / the new K,V row are the c_attn GEMM's output (no-op for an ordinary launch)
-  const int T = pos_base + (pos_dev ? *pos_dev : 0) + 1;
+  const int T = rows_per_seq ? (qrow % rows_per_seq) + 1 : pos_base + (pos_dev ? *pos_dev : 0) + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = lane >> 4, l16 = lane & 15;  // a half-warp covers one 256-byte head row with float4 loads
-  const float4 qv = *reinterpret_cast<const float4 *>(q + (size_t)b * ldq + h * HD + 4 * l16);
+  const float4 qv = *reinterpret_cast<const float4 *>(q + (size_t)qrow * ldq + h * HD + 4 * l16);
   const float *kb = k_cache + (size_t)b * seq_stride + h * HD + 4 * l16;
   const float *vb = v_cache + (size_t)b * seq_stride + h * HD + 4 * l16;
   float4 k_last = make_float4(0.f, 0.f, 0.f, 0.f), v_last = k_last;
@@ -372,7 +377,7 @@ attn_decode_batch_kernel(const float *__restrict__ q, int ldq, const float *k_ca
       num = fmaf(f, s_o[w][threadIdx.x], num);
       den = fmaf(f, s_l[w], den);
     }
-    out[(size_t)b * ldo + h * HD + threadIdx.x] = num / den;
+    out[(size_t)qrow * ldo + h * HD + threadIdx.x] = num / den;
   }
 }
 
@@ -406,9 +411,11 @@ void attn_prefill_launch(const AttnPrefillPlan &p) {
 
 void attn_decode_batch_launch(const float *q, int ldq, const float *k_cache, const float *v_cache, long long seq_stride,
                               int B, int H, int E, float *out, int ldo, const int *pos_dev, int pos_base,
-                              const float *knew, const float *vnew) {
-  ZG_CUDA(launch_pdl(PDL_ATTN_DEP, attn_decode_batch_kernel, dim3(H, B), dim3(DEC_WARPS * 32), 0, ctx().stream, q, ldq, k_cache, v_cache,
-                     seq_stride, E, out, ldo, pos_dev, pos_base, knew, vnew, (knew && (pdl_mask() & PDL_ATTN_TRIGGER)) ? 1 : 0));
+                              const float *knew, const float *vnew, int rows_per_seq) {
+  // rows_per_seq > 0 (causal prefill): B * rows_per_seq query rows
+  ZG_CUDA(launch_pdl(PDL_ATTN_DEP, attn_decode_batch_kernel, dim3(H, rows_per_seq ? B * rows_per_seq : B), dim3(DEC_WARPS * 32), 0,
+                     ctx().stream, q, ldq, k_cache, v_cache, seq_stride, E, out, ldo, pos_dev, pos_base, knew, vnew,
+                     (knew && (pdl_mask() & PDL_ATTN_TRIGGER)) ? 1 : 0, rows_per_seq));
   ZG_LAUNCH_CHECK();
 }
 

@@ -14,6 +14,6 @@ void attn_init_attrs();
 void attn_prefill_launch(const AttnPrefillPlan &p);
 void attn_decode_batch_launch(const float *q, int ldq, const float *k_cache, const float *v_cache, long long seq_stride,
                               int B, int H, int E, float *out, int ldo, const int *pos_dev, int pos_base,
-                              const float *knew = nullptr, const float *vnew = nullptr);
+                              const float *knew = nullptr, const float *vnew = nullptr, int rows_per_seq = 0);
 
 }  // namespace zg

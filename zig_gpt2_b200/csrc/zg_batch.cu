@@ -247,7 +247,8 @@ using namespace zg;
 struct zg_batch {
   zg_config cfg;
   int B = 0, cap = 0, max_prompt = 0, Vp = 0;
-  bool f16_prefill = false;
+  bool f16_prefill = false;   // prefill enabled (max_prompt > 0)
+  bool exact_prefill = false;  // ... with 3xTF32 GEMMs on fp32 activations and fp32 causal attention instead of the f16 pipeline
   const float *wte = nullptr, *wpe = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
   const __half *wte16 = nullptr;
   std::vector<LayerW> layers;
@@ -259,6 +260,7 @@ struct zg_batch {
   // prefill activations (rows = B * max_prompt)
   float *px = nullptr, *plast = nullptr;
   __half *ph = nullptr, *pqkv = nullptr, *patt = nullptr, *ph4 = nullptr, *plast16 = nullptr;
+  float *ph32 = nullptr, *pqkv32 = nullptr, *patt32 = nullptr, *ph4_32 = nullptr;  // exact_prefill
   u64 *tok = nullptr, *hist = nullptr, *prompts = nullptr, *ptok = nullptr;
   u64 *hist_host = nullptr;  // pinned [hist_cap][B]: generate() reads the token history back through it
   size_t hist_cap = 0;
@@ -355,8 +357,36 @@ bool build_skinny_plans(zg_batch *e) {
   return skinny_plan(&e->sk_head, e->dec_mode, e->h, E, e->wte, a);
 }
 
+// fp32-class prefill: the same four GEMMs per layer in the 3xTF32 mode on fp32 activations; logits through the decode
+// head (e->h -> e->logits).  Token-identical to the reference's token-at-a-time prompt loop wherever the decode step is.
+bool build_exact_prefill_plans(zg_batch *e, int T) {
+  const int B = e->B, E = (int)e->cfg.n_embed, M = B * T;
+  e->pre_plans.resize(e->layers.size());
+  for (size_t l = 0; l < e->layers.size(); ++l) {
+    const LayerW &w = e->layers[l];
+    LayerPlans &p = e->pre_plans[l];
+    GemmArgs a = base_args(M, 3 * E, E, w.attn_b, e->pqkv32, 3 * E, 0);
+    a.k_cache = e->k_cache + l * e->layer_stride;
+    a.v_cache = e->v_cache + l * e->layer_stride;
+    a.E = E; a.rows_per_seq = T; a.cache_seq_stride = (long long)e->seq_stride; a.pos_dev = nullptr; a.pos_base = 0; a.cache_rows = e->cap;
+    if (!gemm_plan(&p.attn, 2, e->ph32, E, w.attn_w, a, 0)) return false;
+    a = base_args(M, E, E, w.proj_b, e->px, E, 0);
+    a.epi = TC_EPI_RESIDUAL; a.resid = e->px; a.ldr = E;
+    if (!gemm_plan(&p.proj, 2, e->patt32, E, w.proj_w, a, 0)) return false;
+    a = base_args(M, 4 * E, E, w.fc_b, e->ph4_32, 4 * E, 0);
+    a.epi = TC_EPI_GELU;
+    if (!gemm_plan(&p.fc, 2, e->ph32, E, w.fc_w, a, 0)) return false;
+    a = base_args(M, E, 4 * E, w.proj2_b, e->px, E, 0);
+    a.epi = TC_EPI_RESIDUAL; a.resid = e->px; a.ldr = E;
+    if (!gemm_plan(&p.proj2, 2, e->ph4_32, 4 * E, w.proj2_w, a, 0)) return false;
+  }
+  e->pre_T = T;
+  return true;
+}
+
 bool build_prefill_plans(zg_batch *e, int T) {
   if (e->pre_T == T) return true;
+  if (e->exact_prefill) return build_exact_prefill_plans(e, T);
   const int B = e->B, E = (int)e->cfg.n_embed, V = (int)e->cfg.vocab_size, M = B * T, H = (int)e->cfg.n_heads;
   e->pre_plans.resize(e->layers.size());
   e->pre_attn.resize(e->layers.size());
@@ -444,6 +474,26 @@ void enqueue_prefill(zg_batch *e, int T, bool with_logits) {
   const int B = e->B, E = (int)e->cfg.n_embed, M = B * T;
   embed_rows_kernel<<<M, 128, 0, s>>>(e->wte, e->wpe, e->ptok, T, nullptr, E, (int)e->cfg.vocab_size, e->px);
   ZG_LAUNCH_CHECK();
+  if (e->exact_prefill) {
+    const int H = (int)e->cfg.n_heads;
+    for (size_t l = 0; l < e->layers.size(); ++l) {
+      const LayerW &w = e->layers[l];
+      const LayerPlans &p = e->pre_plans[l];
+      launch_ln_rows<false>(e->px, E, e->ph32, w.ln1_g, w.ln1_b, E, M, s);
+      gemm_launch(p.attn);  // c_attn + K/V rows [0, T) of every sequence into the caches
+      attn_decode_batch_launch(e->pqkv32, 3 * E, e->k_cache + l * e->layer_stride, e->v_cache + l * e->layer_stride,
+                               (long long)e->seq_stride, B, H, E, e->patt32, E, nullptr, 0, nullptr, nullptr, T);
+      gemm_launch(p.proj);
+      launch_ln_rows<false>(e->px, E, e->ph32, w.ln2_g, w.ln2_b, E, M, s);
+      gemm_launch(p.fc);
+      gemm_launch(p.proj2);
+    }
+    if (with_logits) {  // last position of every prompt only (main.zig:192), through the decode head
+      launch_ln_rows<false>(e->px + (size_t)(T - 1) * E, (size_t)T * E, e->h, e->lnf_g, e->lnf_b, E, B, s);
+      gemm_launch(e->dec_head);
+    }
+    return;
+  }
   for (size_t l = 0; l < e->layers.size(); ++l) {
     const LayerW &w = e->layers[l];
     const LayerPlans &p = e->pre_plans[l];
@@ -501,6 +551,7 @@ zg_batch *zg_batch_create(const zg_gpt *gpt, size_t n_seqs, size_t cache_rows, s
   e->max_prompt = (int)max_prompt;
   e->Vp = (int)((V + 3) & ~(size_t)3);
   e->f16_prefill = max_prompt > 0;
+  e->exact_prefill = e->f16_prefill && (flags & 4);
   e->use_graph = !(flags & 1);
   e->dec_mode = (flags & 2) ? 1 : 2;
   e->wte = gpt->wte.weight;
@@ -518,14 +569,14 @@ zg_batch *zg_batch_create(const zg_gpt *gpt, size_t n_seqs, size_t cache_rows, s
     w.fc_w = b.mlp.c_fc.weight; w.fc_b = b.mlp.c_fc.bias;
     w.proj2_w = b.mlp.c_proj.weight; w.proj2_b = b.mlp.c_proj.bias;
     w.attn_w16 = w.proj_w16 = w.fc_w16 = w.proj2_w16 = nullptr;
-    if (e->f16_prefill) {
+    if (e->f16_prefill && !e->exact_prefill) {
       w.attn_w16 = f16_copy(e, w.attn_w, 3 * E * E);
       w.proj_w16 = f16_copy(e, w.proj_w, E * E);
       w.fc_w16 = f16_copy(e, w.fc_w, 4 * E * E);
       w.proj2_w16 = f16_copy(e, w.proj2_w, 4 * E * E);
     }
   }
-  if (e->f16_prefill) e->wte16 = f16_copy(e, e->wte, V * E);
+  if (e->f16_prefill && !e->exact_prefill) e->wte16 = f16_copy(e, e->wte, V * E);
   const size_t B = n_seqs;
   e->seq_stride = cache_rows * E;
   e->layer_stride = B * e->seq_stride;
@@ -550,7 +601,15 @@ zg_batch *zg_batch_create(const zg_gpt *gpt, size_t n_seqs, size_t cache_rows, s
   e->pos = balloc<int>(e, 4);
   e->best = balloc<unsigned long long>(e, 2 * B);
   e->samp = balloc<unsigned long long>(e, 8);
-  if (e->f16_prefill) {
+  if (e->exact_prefill) {
+    const size_t M = B * max_prompt;
+    e->px = balloc<float>(e, M * E);
+    e->ph32 = balloc<float>(e, M * E);
+    e->pqkv32 = balloc<float>(e, M * 3 * E);
+    e->patt32 = balloc<float>(e, M * E);
+    e->ph4_32 = balloc<float>(e, M * 4 * E);
+    e->ptok = balloc<u64>(e, M);
+  } else if (e->f16_prefill) {
     const size_t M = B * max_prompt;
     e->px = balloc<float>(e, M * E);
     e->ph = balloc<__half>(e, M * E);
