@@ -75,7 +75,7 @@ def test_host_tokenizer_loads_json_vocab_files(tmp_path):
 
 # ---- GPU -----------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-def test_load_gpt_from_raw_files_matches_in_memory_model(tmp_path):
+def test_load_gpt_from_raw_files_matches_in_memory_model(tmp_path, monkeypatch):
     from zig_gpt2_b200 import gpt, lib
 
     L = lib.init(0)
@@ -93,7 +93,9 @@ def test_load_gpt_from_raw_files_matches_in_memory_model(tmp_path):
         m2.forward(s + 1, t, s == len(prompt) - 1, s2)
     assert np.array_equal(s2.logits.download(), want)
 
-    # (2) zg_load_gpt: file -> pinned staging -> device, then the same engine
+    # (2) zg_load_gpt: mmap -> two pinned staging buffers -> async H2D, then the same engine.  A 4 KB chunk forces
+    # hundreds of chunks per tensor through the double-buffered path.
+    monkeypatch.setenv("ZG_LOAD_CHUNK_KB", "4")
     g = lib.ZgGPT()
     c = lib.ZgConfig(CFG.vocab_size, CFG.context_size, CFG.n_layer, CFG.n_heads, CFG.n_embed)
     assert L.zg_load_gpt(C.byref(g), C.byref(c), str(tmp_path / "raw").encode()) == 0

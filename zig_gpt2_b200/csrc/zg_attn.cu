@@ -55,9 +55,6 @@ __device__ __forceinline__ float max3(float a, float b, float c) {  // three-inp
 // Row maximum of one 128-key score tile (this thread's query row r lives in TMEM lane r).  DIAG: the tile crosses the
 // causal boundary and keys c > r are masked; every other tile runs the mask-free instantiation (the per-element
 // compare / select pairs were a third of the kernel's instructions when the mask was evaluated for all tiles).
-// Row maximum of one 128-key score tile (this thread's query row r lives in TMEM lane r).  DIAG: the tile crosses the
-// causal boundary and keys c > r are masked; every other tile runs the mask-free instantiation (the per-element
-// compare / select pairs were a third of the kernel's instructions when the mask was evaluated for all tiles).
 // (Measured and rejected: 16-column tcgen05.ld kept one load ahead of the arithmetic -- 2 % slower end to end.)
 template <bool DIAG>
 __device__ __forceinline__ float tile_row_max(uint32_t ts_row, int r) {

@@ -55,29 +55,14 @@ typedef unsigned long long u64;
 constexpr int NTHREADS = NCT + 32;  // + producer warp
 constexpr int MAXSLOTS = 32;
 constexpr int MAX_LAYERS = 64;
-#ifndef ZG_ATT_ROWS
-#define ZG_ATT_ROWS (ZG_NCW > 7 ? 8 : 16)  // rows per warp of an attention work item before the head is split across CTAs
-#endif
-constexpr int ATT_CHUNK = ZG_ATT_ROWS * NCW;  // KV rows per attention work item before splitting (one register round)
-#ifndef ZG_ATT_SMAX
-#define ZG_ATT_SMAX 8
-#endif
-constexpr int ATT_SMAX = ZG_ATT_SMAX;          // at most this many splits per head; longer contexts loop over rounds inside a split
+constexpr int ATT_ROWS = 16;  // rows per warp of an attention work item before the head is split across CTAs
+constexpr int ATT_CHUNK = ATT_ROWS * NCW;  // KV rows per attention work item before splitting (one register round)
+constexpr int ATT_SMAX = 8;          // at most this many splits per head; longer contexts loop over rounds inside a split
 constexpr int PROF_MAX = 16384;
 // sm.red layout: per-warp attention (m, l), per-warp argmax (value, index), the reduced token
 constexpr int RED_M = 0, RED_L = 16, RED_B = 32, RED_I = 48, RED_TOK = 64, RED_FLOATS = 96;
 static_assert(NCW <= 16, "sm.red and sm.part hold 16 per-warp entries");
 constexpr int MAXNE = 16;        // elements of the stream a CTA owns in the reduce phase: ceil(E / SMs) <= 16
-// Replicas of the broadcast vectors of the flagged exchange (the stream after each half of a block, the attention
-// output, the argmax partials).  Every one of the G CTAs gathers these vectors at the same moment, so with one copy
-// the 48 L2 lines of a 768-element vector serve 148 requests each per poll round (and the producers' stores queue
-// behind them); a producer writes XREP copies (lanes 0..XREP-1 of the 8-lane group that holds a finished row) and CTA
-// c reads copy c mod XREP.  q and the new K/V row are read by the attention CTAs only and are not replicated.
-#ifndef ZG_XREP
-#define ZG_XREP 1
-#endif
-constexpr int XREP = ZG_XREP;
-static_assert(XREP >= 1 && XREP <= 8, "one replica per lane of an 8-lane row group");
 
 struct LayerDesc {
   const float *wq, *c1q, *c2q;    // LN1-folded c_attn: W diag(g) [3E,E], its row sums, W b + bias
@@ -122,18 +107,15 @@ struct DecodeParams {
 };
 
 // Cycle-level breakdown of a phase (zg_engine_read_profile): thread 0 of one chosen CTA keeps up to 12 %clock readings
-// in registers and dumps them as (tag = 512 + 16 * phase kind + point, cycles) pairs when the phase ends.  Compiled
-// in by default: with profiling off every hook is one not-taken uniform branch.  (Measured on B200: the build WITH
-// the hooks decodes ~5% faster than -DZG_NO_PROF -- a ptxas scheduling artefact, recorded in DESIGN.md, not relied on.)
-#ifndef ZG_NO_PROF
+// in registers and dumps them as (tag = 512 + 16 * phase kind + point, cycles) pairs when the phase ends.  Always
+// compiled in: with profiling off every hook is one not-taken uniform branch.  (Round 1 measured builds without the
+// hooks 5-8 % slower -- the never-taken dump block at the end of every phase changes ptxas's schedule; the A/B log is
+// profiles/r01_ab_experiments.txt.  The kernel is sensitive to code layout at this level: every change is re-timed.)
 struct Clk {
   unsigned t[12];
   u64 *buf;
   int i;
   __device__ __forceinline__ void at(int k) {
-#ifdef ZG_PROF_MASK  // experiment: compile in only the hooks whose bit is set
-    if (!((ZG_PROF_MASK >> k) & 1)) return;
-#endif
     if (buf) {
       if (k == 0) {
 #pragma unroll
@@ -143,12 +125,6 @@ struct Clk {
     }
   }
   __device__ __forceinline__ void dump(int kind) {
-#ifdef ZG_SYNCWARP_END  // experiment: force warp reconvergence at the end of every phase
-    __syncwarp();
-#endif
-#ifdef ZG_PROF_NODUMP
-    return;
-#endif
     if (buf && i + 12 < PROF_MAX) {
 #pragma unroll
       for (int k = 0; k < 12; ++k) {
@@ -160,33 +136,7 @@ struct Clk {
     }
   }
 };
-#else
-struct Clk {
-  u64 *buf;
-#if defined(ZG_PIN_BARRIER)  // experiment: keep only the compiler-level ordering point of a hook
-  __device__ __forceinline__ void at(int) { asm volatile("" ::: "memory"); }
-#elif defined(ZG_PIN_CLOCK)  // experiment: keep one unconditional volatile clock read per hook
-  __device__ __forceinline__ void at(int) {
-    unsigned t;
-    asm volatile("mov.u32 %0, %%clock;" : "=r"(t));
-  }
-#else
-  __device__ __forceinline__ void at(int) {}
-#endif
-  __device__ __forceinline__ void dump(int) {}
-};
-#endif
 
-// optional back-off between polls of the flagged exchange (experiment: -DZG_POLL_NS=n)
-__device__ __forceinline__ void poll_backoff() {
-#ifdef ZG_POLL_NS
-  __nanosleep(ZG_POLL_NS);
-#endif
-#ifdef ZG_POLL_CYCLES  // experiment: clock-spin between polls (finer than nanosleep)
-  const long long t0 = clock64();
-  while (clock64() - t0 < ZG_POLL_CYCLES) {}
-#endif
-}
 
 // Hold-off before the first poll of a phase.  A CTA that finishes a phase early starts to poll the flagged words of the
 // next phase's input at once; 148 CTAs x 224 threads polling the very L2 lines that the slower CTAs are still storing
@@ -280,7 +230,6 @@ __device__ __noinline__ ulonglong2 spin_pair(const u64 *p, unsigned ep, Watchdog
   const long long t0 = clock64();
   unsigned spins = 0;
   while (!pair_ok(v, ep)) {
-    poll_backoff();
     v = ld_pair(p);
     if ((++spins & 255u) == 0 && clock64() - t0 > WATCHDOG_CYCLES) {
       wd_trip(wd, 3u);
@@ -303,59 +252,12 @@ __device__ __noinline__ u64 spin_word(const u64 *p, unsigned ep, Watchdog wd) {
   }
   return v;
 }
-// gather n floats (n even) whose words must carry epoch `ep` into shared memory; all loads of a thread are
-// issued before the first check, so the common case costs one L2 round trip; late pairs are re-polled together
-// GB = flagged pairs a thread keeps in flight per pass: 2 cover E <= 896 in one pass (half the code of 4 -- every phase
-// executes its code once, so straight-line code size is instruction-cache misses), 4 cover E <= 1792.
-template <int GB, int NT = NCT>
-__device__ __forceinline__ void gather_flagged(float *dst_smem, const u64 *src, int n, unsigned ep, Watchdog wd) {
-  const int npairs = n >> 1;
-#pragma unroll 1
-  for (int base = 0; base < npairs; base += GB * NT) {
-    ulonglong2 v[GB];
-    bool all_ok = true;
-#pragma unroll
-    for (int j = 0; j < GB; ++j) {
-      const int idx = base + j * NT + (int)threadIdx.x;
-      if (idx < npairs) v[j] = ld_pair(src + 2 * idx);
-    }
-#pragma unroll
-    for (int j = 0; j < GB; ++j) {
-      const int idx = base + j * NT + (int)threadIdx.x;
-      if (idx < npairs) all_ok = all_ok && pair_ok(v[j], ep);
-    }
-    if (!all_ok && !wd_tripped(wd)) {
-      const long long t0 = clock64();
-      do {
-        poll_backoff();
-        all_ok = true;
-#pragma unroll
-        for (int j = 0; j < GB; ++j) {
-          const int idx = base + j * NT + (int)threadIdx.x;
-          if (idx < npairs && !pair_ok(v[j], ep)) v[j] = ld_pair(src + 2 * idx);
-        }
-#pragma unroll
-        for (int j = 0; j < GB; ++j) {
-          const int idx = base + j * NT + (int)threadIdx.x;
-          if (idx < npairs) all_ok = all_ok && pair_ok(v[j], ep);
-        }
-        if (!all_ok && clock64() - t0 > WATCHDOG_CYCLES) {
-          wd_trip(wd, 3u);
-          break;
-        }
-      } while (!all_ok);
-    }
-#pragma unroll
-    for (int j = 0; j < GB; ++j) {
-      const int idx = base + j * NT + (int)threadIdx.x;
-      if (idx < npairs) reinterpret_cast<float2 *>(dst_smem)[idx] = make_float2(lo_f(v[j].x), lo_f(v[j].y));
-    }
-  }
-}
-// The same gather with ONE 256-bit load per thread and pass (LDG.E.ENL2.256.STRONG.GPU: four flagged words = one 32-byte
-// sector).  A thread's strong loads do not overlap well -- every additional flagged load per thread and pass was measured
-// at +100..200 cycles on the gather's critical path (one polling warp with 12 pairs per lane: 207 us/token against 144.5
-// for seven warps with 2 pairs per lane) -- so the widest load wins: E = 768 needs 192 loads, one per thread.
+// Gather n floats (n % 4 == 0) whose words must carry epoch `ep` into shared memory: all loads of a thread are issued
+// before the first check, so the common case costs one L2 round trip; late quads are re-polled together.  ONE 256-bit load
+// per thread and pass (LDG.E.ENL2.256.STRONG.GPU: four flagged words = one 32-byte sector): a thread's strong loads do not
+// overlap well -- every additional flagged load per thread and pass was measured at +100..200 cycles on the gather's
+// critical path (one polling warp with 12 128-bit pairs per lane: 207 us/token; seven warps with 2 pairs per lane: 145.3;
+// one 256-bit quad per thread: 143.3) -- so the widest load wins: E = 768 needs 192 loads, one per thread.
 struct Quad { u64 a, b, c, d; };
 __device__ __forceinline__ Quad ld_quad(const u64 *p) {
   Quad v;
@@ -481,11 +383,8 @@ __device__ __forceinline__ float packed_reduce(float (&v)[N], int lane) {
 // waited for (cache rows do not depend on this step), so a split that fits one round costs no exposed L2 latency
 // after q lands.  Scores: per-lane partial dot over the lane's 2 dims, packed butterfly (AR + 5 - log2 AR shuffles
 // for AR rows), one exp per lane, p broadcast by shuffle for the PV accumulation.
-#ifndef ZG_ATT_INLINE
-#define ZG_ATT_INLINE __forceinline__
-#endif
 template <int AR>
-__device__ ZG_ATT_INLINE void attention_item(const DecodeParams &p, const Smem &sm, int l, int h, int s, int S, int T,
+__device__ __forceinline__ void attention_item(const DecodeParams &p, const Smem &sm, int l, int h, int s, int S, int T,
                                                unsigned ep_in, unsigned ep_out, Clk &ck) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int hd = 64;
@@ -591,9 +490,7 @@ __device__ ZG_ATT_INLINE void attention_item(const DecodeParams &p, const Smem &
       o = fmaf(po[w * hd + tid], sc, o);
     }
     if (S == 1) {
-      const float ov = fdiv(o, lsum);
-#pragma unroll
-      for (int rep = 0; rep < XREP; ++rep) st_flag(p.att_f + (size_t)rep * E + h * hd + tid, ov, ep_out);
+      st_flag(p.att_f + h * hd + tid, fdiv(o, lsum), ep_out);
     } else {  // flash-decoding partial (m, l, unnormalised o): every consumer of the attention output combines the S
               // partials of a head itself while it gathers the vector (gather_att_partials), so no fence, no counter
       u64 *mine = p.attp_f + ((size_t)h * ATT_SMAX + s) * (hd + 2);
@@ -605,10 +502,7 @@ __device__ ZG_ATT_INLINE void attention_item(const DecodeParams &p, const Smem &
 
 // Attention output vector from S (2..ATT_SMAX) flagged partials per head: out = sum_s o_s e^(m_s - M) / sum_s l_s e^(m_s - M).
 // A thread handles pairs of adjacent elements; all 2 S loads of a pair are in flight before the first check.
-#ifndef ZG_GAP_INLINE
-#define ZG_GAP_INLINE __forceinline__
-#endif
-__device__ ZG_GAP_INLINE void gather_att_partials(float *dst_smem, const u64 *attp, int E, int S, unsigned ep, Watchdog wd) {
+__device__ __forceinline__ void gather_att_partials(float *dst_smem, const u64 *attp, int E, int S, unsigned ep, Watchdog wd) {
   constexpr int hd = 64;
   const int npairs = E >> 1;
 #pragma unroll 1
@@ -711,11 +605,7 @@ __device__ __forceinline__ void ln_finish(float s, float ss, float inv_E, float 
     ss += __shfl_xor_sync(0xffffffffu, ss, o);
   }
   mean = s * inv_E;
-#ifdef ZG_SLOW_RSTD
-  rstd = 1.0f / sqrtf(ss * inv_E - mean * mean + 1e-5f);
-#else
   rstd = rsqrtf(fmaf(ss, inv_E, -mean * mean) + 1e-5f);
-#endif
 }
 // explicit LayerNorm output (only needed when GPT.forward has to leave ln_f(x) in state.x, main.zig:189)
 template <int NJ>
@@ -779,16 +669,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
     e.r0 = 0; e.nrows = 0; e.mode = M_ATTN;
     int N = 0, rot = 0;
     if (g == L5) {
-      e.W = p.wte_f; e.bias = p.c2h; e.c1 = p.c1h; e.src = p.xnew_f + (size_t)(cta % XREP) * E; e.mode = M_LMHEAD; N = p.V;
+      e.W = p.wte_f; e.bias = p.c2h; e.c1 = p.c1h; e.src = p.xnew_f; e.mode = M_LMHEAD; N = p.V;
     } else {
       const LayerDesc &ld = c_layers[l];
       rot = phase_rot(l, ph, G);
       if (ph == 0) {
-        e.W = ld.wq; e.bias = ld.c2q; e.c1 = ld.c1q; e.src = p.xnew_f + (size_t)(cta % XREP) * E; e.mode = M_QKV; N = 3 * E;
+        e.W = ld.wq; e.bias = ld.c2q; e.c1 = ld.c1q; e.src = p.xnew_f; e.mode = M_QKV; N = 3 * E;
       } else if (ph == 2) {
-        e.W = ld.w_proj; e.bias = ld.b_proj; e.src = p.att_f + (size_t)(cta % XREP) * E; e.mode = M_RESID; N = E;
+        e.W = ld.w_proj; e.bias = ld.b_proj; e.src = p.att_f; e.mode = M_RESID; N = E;
       } else if (ph == 3) {
-        e.W = ld.wfc; e.W2 = ld.w2t; e.bias = ld.c2f; e.c1 = ld.c1f; e.src = p.xres_f + (size_t)(cta % XREP) * E; e.mode = M_MLP; N = 4 * E;
+        e.W = ld.wfc; e.W2 = ld.w2t; e.bias = ld.c2f; e.c1 = ld.c1f; e.src = p.xres_f; e.mode = M_MLP; N = 4 * E;
       } else if (ph == 4) {
         e.bias = ld.b_proj2; e.mode = M_REDUCE; N = E;
       }
@@ -860,15 +750,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
 
   // ================================= consumer warps =================================
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#ifndef ZG_NO_PROF
   Clk ck;
   ck.buf = (p.prof && cta == p.prof_cta && tid == 0) ? p.prof : nullptr;
   ck.i = 0;
 #pragma unroll
   for (int k = 0; k < 12; ++k) ck.t[k] = 0u;
-#else
-  Clk ck{nullptr};
-#endif
   u64 prev_token = 0;
   int bslot = 0;               // ring slot of the first unit of the next batch
   uint32_t fpar = 0;           // bit s: parity the next wait on full barrier s expects
@@ -896,7 +782,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
       ++ep;
       const PhaseEnt ent = table[g];
       const bool is_head = (g == L5);
-      const int tag = is_head ? 96 : 16 * (g % 5 + 1);
       const int mode = ent.mode;
       ck.at(0);
 
@@ -907,11 +792,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           const int chunk = (T + S - 1) / S;
           if (chunk <= 4 * NCW) attention_item<4>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep, ck);
           else if (chunk <= 8 * NCW) attention_item<8>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep, ck);
-#if defined(ZG_ATT_MAX8) || ZG_NCW > 7  // never the 16-row instantiation (64 registers of K/V): 8-row rounds
-          else attention_item<8>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep, ck);
-#else
           else attention_item<16>(p, sm, g / 5, cta / S, cta % S, S, T, ep - 1, ep, ck);
-#endif
         }
         ck.at(11);
         ck.dump(1);
@@ -948,8 +829,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         if (!all_ok && !wd_tripped(sm.wd)) {
           const long long t0 = clock64();
           do {
-            poll_backoff();
-            all_ok = true;
+                all_ok = true;
 #pragma unroll
             for (int q = 0; q < NP; ++q)
               if ((unsigned)(w[q] >> 32) != ep - 1) w[q] = ld_word(col + (size_t)(sgrp + q * nsg) * E);
@@ -976,9 +856,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           float v = 0.0f;
 #pragma unroll
           for (int w2 = 0; w2 < NCW; ++w2) v += sm.part[tid * 16 + w2];
-          v += xmid[ent.r0 + tid] + bmine;
-#pragma unroll
-          for (int rep = 0; rep < XREP; ++rep) st_flag(p.xnew_f + (size_t)rep * E + ent.r0 + tid, v, ep);
+          st_flag(p.xnew_f + ent.r0 + tid, v + (xmid[ent.r0 + tid] + bmine), ep);
         }
         ck.at(11);
         ck.dump(4);
@@ -993,11 +871,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
       // ---------------- phase top: issue every load whose address is known before the activation arrives ----
       // lanes 0/8/16/24 of warp w finish rows w, w + NCW, w + 2 NCW, w + 3 NCW of a batch
       // the weights of the first batch are almost always in the ring already: test its barrier now, off the critical path
-#ifdef ZG_NO_EARLY_TRY
-      bool wready = false;
-#else
       bool wready = mbar_try(sm.full0 + 8u * bslot, (fpar >> bslot) & 1u);
-#endif
       float bias_v = 0.0f, c1_v = 0.0f;
       if (elane && iloc < min(rb, ent.nrows)) {
         const int r = ent.r0 + iloc;
@@ -1023,11 +897,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
       } else if (mode == M_RESID && att_splits(T, G, p.H) > 1) {
         gather_att_partials(vec, p.attp_f, E, att_splits(T, G, p.H), ep - 1, sm.wd);
       } else {
-#ifdef ZG_GATHER128  // the previous form: 128-bit loads, two (wide models: four) flagged pairs per thread and pass
-        gather_flagged<(NJ <= 7 ? 2 : 4)>(vec, ent.src, E, ep - 1, sm.wd);
-#else
         gather_flagged256<(NJ <= 7 ? 1 : 2)>(vec, ent.src, E, ep - 1, sm.wd);
-#endif
       }
       ck.at(2);
       consumer_sync();
@@ -1124,9 +994,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
               st_flag(p.kvn_f + E + (r - 2 * E), v, ep);
             }
           } else if (mode == M_RESID) {  // residual 1, main.zig:136-139: the stream is this CTA's own copy
-            const float xv = v + vprev[r];
-#pragma unroll
-            for (int rep = 0; rep < XREP; ++rep) st_flag(p.xres_f + (size_t)rep * E + r, xv, ep);
+            st_flag(p.xres_f + r, v + vprev[r], ep);
           } else if (mode == M_MLP) {  // main.zig:79-80
             sm.fbuf[b0 + iloc] = gelu_dec(v);
           } else {  // tied lm_head (main.zig:193) + running argmax; this lane sees increasing r, so strict >
@@ -1141,11 +1009,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         // ---------------- mlp c_proj, main.zig:81: out += f_j * c_proj^T[j, :] over the hidden units j this CTA owns.
         // Thread t accumulates output float4 t (and t + 224 for wide models); no shuffles. ----------------
         // test the barrier of the first c_proj^T batch before the CTA sync
-#ifdef ZG_NO_EARLY_TRY
-        bool w2ready = false;
-#else
         bool w2ready = mbar_try(sm.full0 + 8u * bslot, (fpar >> bslot) & 1u);
-#endif
         consumer_sync();  // fbuf complete
         ck.at(9);
         constexpr int NK = (NJ * 32 > NCT) ? 2 : 1;  // output float4 per thread
@@ -1159,7 +1023,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           if (!w2ready) mbar_wait(sm.full0 + 8u * bslot, (fpar >> bslot) & 1u, sm.wd);
           w2ready = false;
           fpar ^= 1u << bslot;
-#ifndef ZG_PASS2_V1
           // One ring unit (4 rows of c_proj^T) per trip: one broadcast LDS.128 for the unit's four GELU factors, four
           // LDS.128 for this thread's column of the four rows, 16 FMAs.  Rows past the batch re-read row 0 of their unit
           // (always valid) with a zero factor.  Two trips are unrolled together so that the loads of unit q + 1 are in
@@ -1190,65 +1053,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
               if (++sl == nslot) sl = 0;
             }
           }
-#else
-          // Software-pipelined over the ring units of the batch, two units per trip of a ROLLED loop (A / B register
-          // sets ping-pong): unit q + 1 is loaded while unit q is multiplied.  Rows past the batch re-read a valid row
-          // with a zero factor.  Rolled on purpose: a phase runs its code once, so the 7-unit unrolled form was 7 KB of
-          // straight-line code to fetch per layer for 6 units of work.
-#pragma unroll
-          for (int k = 0; k < NK; ++k) {
-            const int i4 = min(tid + k * NCT, Eq - 1);
-            const bool live = tid + k * NCT < Eq;
-            float4 wa[4], wb[4];
-            {
-              const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)bslot * slotf);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) wa[j] = w4[(j < nbr ? j : 0) * Eq + i4];
-            }
-#pragma unroll 1
-            for (int q = 0; q < nun; q += 2) {
-              {  // load unit q + 1 (clamped) into B
-                const int qn = min(q + 1, nun - 1);
-                int sl = bslot + qn;
-                if (sl >= nslot) sl -= nslot;
-                const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)sl * slotf);
-                const int nvn = nbr - 4 * qn;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) wb[j] = w4[(j < nvn ? j : 0) * Eq + i4];
-              }
-              {  // multiply unit q from A
-                const float4 f4 = *reinterpret_cast<const float4 *>(sm.fbuf + b0 + 4 * q);
-                const int nv = live ? nbr - 4 * q : 0;
-                const float fj[4] = {nv > 0 ? f4.x : 0.0f, nv > 1 ? f4.y : 0.0f, nv > 2 ? f4.z : 0.0f, nv > 3 ? f4.w : 0.0f};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  o4[k].x = fmaf(fj[j], wa[j].x, o4[k].x); o4[k].y = fmaf(fj[j], wa[j].y, o4[k].y);
-                  o4[k].z = fmaf(fj[j], wa[j].z, o4[k].z); o4[k].w = fmaf(fj[j], wa[j].w, o4[k].w);
-                }
-              }
-              {  // load unit q + 2 (clamped) into A
-                const int qn = min(q + 2, nun - 1);
-                int sl = bslot + qn;
-                if (sl >= nslot) sl -= nslot;
-                const float4 *w4 = reinterpret_cast<const float4 *>(sm.ring + (size_t)sl * slotf);
-                const int nvn = nbr - 4 * qn;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) wa[j] = w4[(j < nvn ? j : 0) * Eq + i4];
-              }
-              {  // multiply unit q + 1 from B (zero factors when the batch has no such unit)
-                const int q1 = min(q + 1, nun - 1);
-                const float4 f4 = *reinterpret_cast<const float4 *>(sm.fbuf + b0 + 4 * q1);
-                const int nv = (live && q + 1 < nun) ? nbr - 4 * (q + 1) : 0;
-                const float fj[4] = {nv > 0 ? f4.x : 0.0f, nv > 1 ? f4.y : 0.0f, nv > 2 ? f4.z : 0.0f, nv > 3 ? f4.w : 0.0f};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  o4[k].x = fmaf(fj[j], wb[j].x, o4[k].x); o4[k].y = fmaf(fj[j], wb[j].y, o4[k].y);
-                  o4[k].z = fmaf(fj[j], wb[j].z, o4[k].z); o4[k].w = fmaf(fj[j], wb[j].w, o4[k].w);
-                }
-              }
-            }
-          }
-#endif
           __syncwarp();
           if (lane < nun) {
             int sl = bslot + lane;
@@ -1290,19 +1094,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
           best = (lane < NCW) ? sm.red[RED_B + lane] : -INFINITY;
           best_i = (lane < NCW) ? __float_as_uint(sm.red[RED_I + lane]) : 0xffffffffu;
 #pragma unroll
-          for (int o = (NCW > 8 ? 8 : 4); o > 0; o >>= 1) {
+          for (int o = 4; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, best, o);
             const unsigned oi = __shfl_xor_sync(0xffffffffu, best_i, o);
             if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
           }
-          if (tid < XREP) st_flag2(p.amax_f + 2 * ((size_t)tid * G + cta), best, __uint_as_float(best_i), ep);
+          if (tid == 0) st_flag2(p.amax_f + 2 * cta, best, __uint_as_float(best_i), ep);
           predelay(ZG_PD_AMAX);
           float bv = -INFINITY;
           unsigned bi = 0xffffffffu;
-          const u64 *amax_mine = p.amax_f + 2 * (size_t)(cta % XREP) * G;
           for (int i = tid; i < G; i += 32) {
-            ulonglong2 w = ld_pair(amax_mine + 2 * i);
-            if (!pair_ok(w, ep)) w = spin_pair(amax_mine + 2 * i, ep, sm.wd);
+            ulonglong2 w = ld_pair(p.amax_f + 2 * i);
+            if (!pair_ok(w, ep)) w = spin_pair(p.amax_f + 2 * i, ep, sm.wd);
             const float ov = lo_f(w.x);
             const unsigned oi = (unsigned)w.y;
             if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
@@ -1327,7 +1130,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
       // GPT.forward(compute_logits = false) still leaves ln_f(x) in state.x (main.zig:189)
       vsel ^= 1;
       float *vec = sm.vec + vsel * E;
-      gather_flagged<(NJ <= 7 ? 2 : 4)>(vec, p.xnew_f, E, ep, sm.wd);
+      gather_flagged256<(NJ <= 7 ? 1 : 2)>(vec, p.xnew_f, E, ep, sm.wd);
       consumer_sync();
       if (warp == 0) {
         float4 xs[NJ];
@@ -1520,8 +1323,8 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
 
   const size_t C = cfg.context_size, hd = 64;
   const size_t n_attp = cfg.n_heads * (size_t)ATT_SMAX * (hd + 2);
-  const size_t n_amax = (XREP * 2 * (size_t)e->grid + 3) & ~(size_t)3;  // keeps the vectors behind it 32-byte aligned (256-bit loads)
-  const size_t n_exchange = XREP * E + E + 2 * E + XREP * E + n_amax + XREP * E + n_attp + (size_t)e->grid * E;
+  const size_t n_amax = (2 * (size_t)e->grid + 3) & ~(size_t)3;  // keeps the vectors behind it 32-byte aligned (256-bit loads)
+  const size_t n_exchange = E + E + 2 * E + E + n_amax + E + n_attp + (size_t)e->grid * E;
   e->exchange_dev = (u64 *)zg_alloc(n_exchange * 8);
   e->prompt_dev = (u64 *)zg_alloc(C * 8);
   e->tokens_dev = (u64 *)zg_alloc(C * 8);
@@ -1550,12 +1353,12 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
   p.wte = gpt->wte.weight; p.wpe = gpt->wpe.weight; p.lnf_g = gpt->ln_f.weight; p.lnf_b = gpt->ln_f.bias;
   p.wte_f = wte_f; p.c1h = c1h; p.c2h = c2h;
   u64 *x = e->exchange_dev;
-  p.xres_f = x; x += XREP * E;
+  p.xres_f = x; x += E;
   p.q_f = x; x += E;
   p.kvn_f = x; x += 2 * E;
-  p.att_f = x; x += XREP * E;
+  p.att_f = x; x += E;
   p.amax_f = x; x += n_amax;
-  p.xnew_f = x; x += XREP * E;
+  p.xnew_f = x; x += E;
   p.attp_f = x; x += n_attp;
   p.part_f = x;
   p.xres_out = state->o; p.xout = state->x; p.logits = state->logits;

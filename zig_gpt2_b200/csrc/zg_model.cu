@@ -1,8 +1,12 @@
 // zg_model.cu -- src/main.zig's State / MLP / Block / GPT composed op by op from the kernels of zg_ops.cu
 // (one kernel per reference op, with the GELU and residual adds folded into the Linear epilogues), plus
 // model assembly and the raw-file loader.  The fused persistent path lives in zg_decode.cu.
+#include <fcntl.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "zg_common.cuh"
 
@@ -191,26 +195,46 @@ void zg_gpt_free(zg_gpt *g) {
   memset(g, 0, sizeof(*g));
 }
 
-// ---- load_gpt, main.zig:304-314 with load_tensor (ops.zig:309-320) reading straight into pinned staging ----
+// ---- load_gpt, main.zig:304-314 with load_tensor (ops.zig:309-320) ----
 static const char *const kBlockKinds[12] = {"ln_1-g",        "ln_1-b",     "attn-c_attn-w", "attn-c_attn-b",
                                             "attn-c_proj-w", "attn-c_proj-b", "ln_2-g",     "ln_2-b",
                                             "mlp-c_fc-w",    "mlp-c_fc-b", "mlp-c_proj-w",  "mlp-c_proj-b"};
 
+// Files are mapped (mmap) and streamed through TWO pinned staging buffers: while the H2D copy of chunk i runs on the
+// stream (cudaMemcpyAsync from pinned memory, a real DMA), the host copies chunk i + 1 out of the page cache into the
+// other buffer -- disk/page-cache reads, the staging memcpy and the PCIe transfer overlap, and a 6 GB checkpoint needs
+// 2 x 64 MB of pinned memory instead of a buffer as large as the largest tensor.  A file shorter than its tensor is an
+// error (the reference reads with readAll and ignores the count, ops.zig:318: a short file silently leaves garbage).
 int zg_load_gpt(zg_gpt *g, const zg_config *c, const char *raw_dir) {
   if (!require_ready("zg_load_gpt")) return 1;
   const size_t nw = zg_weight_count(c);
   float **w = (float **)calloc(nw, sizeof(float *));
   if (!w) return 2;
-  size_t max_elems = 0;
-  for (size_t i = 0; i < nw; ++i) max_elems = zg_weight_elems(c, i) > max_elems ? zg_weight_elems(c, i) : max_elems;
-  float *staging = nullptr;
-  cudaError_t e = cudaHostAlloc(&staging, max_elems * sizeof(float), cudaHostAllocDefault);
+  size_t chunk = (size_t)64 << 20;
+  if (const char *kb = getenv("ZG_LOAD_CHUNK_KB")) {  // tests: exercise the multi-chunk path on small tensors
+    const long v = atol(kb);
+    if (v > 0) chunk = (size_t)v << 10;
+  }
+  char *staging[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaHostAlloc((void **)&staging[i], chunk, cudaHostAllocDefault);
+    note_alloc();
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) {
     set_error((int)e, "zg_load_gpt staging", __FILE__, __LINE__);
+    for (int i = 0; i < 2; ++i) {
+      if (staging[i]) cudaFreeHost(staging[i]);
+      if (done[i]) cudaEventDestroy(done[i]);
+    }
     free(w);
     return (int)e;
   }
-  int rc = 0;
+  cudaStream_t s = ctx().stream;
+  int rc = 0, buf = 0;
+  bool used[2] = {false, false};
   for (size_t i = 0; i < nw && rc == 0; ++i) {
     char name[64], path[1024];
     if (i == 0) snprintf(name, sizeof(name), "wte");
@@ -218,17 +242,39 @@ int zg_load_gpt(zg_gpt *g, const zg_config *c, const char *raw_dir) {
     else if (i >= 2 + 12 * c->n_layer) snprintf(name, sizeof(name), (i - 2 - 12 * c->n_layer) == 0 ? "ln_f-g" : "ln_f-b");
     else snprintf(name, sizeof(name), "h%zu-%s", (i - 2) / 12, kBlockKinds[(i - 2) % 12]);
     snprintf(path, sizeof(path), "%s/model-%s", raw_dir, name);
-    const size_t n = zg_weight_elems(c, i);
-    FILE *f = fopen(path, "rb");
-    if (!f) { rc = 3; set_error(1, "zg_load_gpt: cannot open tensor file", path, 0); break; }
-    const size_t got = fread(staging, sizeof(float), n, f);
-    fclose(f);
-    if (got != n) { rc = 4; set_error(1, "zg_load_gpt: short read (the reference accepts it silently, ops.zig:318; we do not)", path, 0); break; }
-    w[i] = (float *)zg_alloc(n * sizeof(float));
-    if (!w[i]) { rc = zg_last_error(); break; }
-    rc = zg_upload(w[i], staging, n * sizeof(float));
+    const size_t bytes = zg_weight_elems(c, i) * sizeof(float);
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { rc = 3; set_error(1, "zg_load_gpt: cannot open tensor file", path, 0); break; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || (size_t)st.st_size < bytes) {
+      close(fd);
+      rc = 4;
+      set_error(1, "zg_load_gpt: short read (the reference accepts it silently, ops.zig:318; we do not)", path, 0);
+      break;
+    }
+    const char *map = (const char *)mmap(nullptr, bytes, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (map == MAP_FAILED) { rc = 5; set_error(1, "zg_load_gpt: mmap failed", path, 0); break; }
+    madvise((void *)map, bytes, MADV_SEQUENTIAL);
+    w[i] = (float *)zg_alloc(bytes);
+    if (!w[i]) { rc = zg_last_error(); munmap((void *)map, bytes); break; }
+    for (size_t off = 0; off < bytes && rc == 0; off += chunk) {
+      const size_t n = bytes - off < chunk ? bytes - off : chunk;
+      if (used[buf]) ZG_CUDA(cudaEventSynchronize(done[buf]));  // the copy that last used this buffer has drained
+      memcpy(staging[buf], map + off, n);
+      ZG_CUDA(cudaMemcpyAsync((char *)w[i] + off, staging[buf], n, cudaMemcpyHostToDevice, s));
+      ZG_CUDA(cudaEventRecord(done[buf], s));
+      used[buf] = true;
+      buf ^= 1;
+      rc = zg_last_error();
+    }
+    munmap((void *)map, bytes);
   }
-  cudaFreeHost(staging);
+  ZG_CUDA(cudaStreamSynchronize(s));
+  for (int i = 0; i < 2; ++i) {
+    cudaFreeHost(staging[i]);
+    cudaEventDestroy(done[i]);
+  }
   if (rc == 0) rc = zg_gpt_init(g, c, (const float *const *)w);
   free(w);  // the device tensors stay alive for the life of the process, like the reference's arena (main.zig:349-350)
   return rc;

@@ -5,10 +5,7 @@
 
 namespace zg {
 
-#ifndef ZG_NCW
-#define ZG_NCW 7
-#endif
-constexpr int NCW = ZG_NCW;        // consumer warps of the persistent decode kernel (+ 1 producer warp = 8 warps:
+constexpr int NCW = 7;             // consumer warps of the persistent decode kernel (+ 1 producer warp = 8 warps:
                                    // two per scheduler, so a thread may use up to 255 registers)
 constexpr int NCT = NCW * 32;      // consumer threads
 
