@@ -91,11 +91,12 @@ void zg_linear_forward_tc(const zg_linear *self, const void *inputs, size_t inpu
 /* Linear.forward for 1 <= M <= 128 rows (the batched decode step) on the tensor cores with the operands swapped: 128
  * weight rows are the UMMA M operand, the whole batch is N, the (weight tile, k-block) grid is split evenly over the SMs
  * (stream-K) and partial sums are reduced into `outputs` with fp32 atomics.  `outputs` must hold zeros (plain Linear) or
- * the residual (x += Linear(h), main.zig:136-145) on entry; in_features % 32 == 0.  precision 0 = TF32, 2 = 3xTF32.
+ * the residual (x += Linear(h), main.zig:136-145) on entry; in_features % 32 == 0.  precision 0 = TF32, 2 = 3xTF32,
+ * 1 = f16 operands (`inputs` and `weight_lowp` are f16 copies made with zg_to_f16; in_features % 64 == 0; no xform).
  * xform bit 0 applies GELU (ops.zig:221-228) to `inputs` on the fly (mlp c_proj reading c_fc's pre-activation,
  * main.zig:80); bit 1 is a test hook (element-wise fp32 atomics instead of TMA reduce-adds in the epilogue). */
-void zg_linear_forward_skinny(const zg_linear *self, const float *inputs, size_t inputs_len, float *outputs, int precision,
-                              int xform);
+void zg_linear_forward_skinny(const zg_linear *self, const void *inputs, size_t inputs_len, float *outputs, int precision,
+                              int xform, const void *weight_lowp);
 /* Greedy sampling through a Linear without materialising its outputs (the tied lm_head + argmax, main.zig:193): for every
  * row m of `inputs`, tokens_dev[m] (DEVICE, 64-bit) = index of the first maximum of inputs[m,:] . W^T + bias.  The argmax
  * runs in the GEMM epilogue (whole weight tiles per CTA, packed atomicMax per row); `best_scratch` is 2 * M 64-bit words
@@ -230,7 +231,10 @@ typedef struct zg_batch zg_batch;
  * bit 1: single-pass TF32 decode GEMMs instead of the error-compensated 3xTF32 default; bit 2: fp32-class prefill (3xTF32
  * GEMMs on fp32 activations + fp32 causal attention) instead of the f16 pipeline -- the prefilled generate() is then
  * token-identical to the reference's token-at-a-time prompt loop, at about a third of the f16 prefill's speed; bit 3: never the swapped-operand
- * stream-K GEMMs (the default decode step for n_seqs <= 128, zg_linear_forward_skinny), always the general kernel. */
+ * stream-K GEMMs (the default decode step for n_seqs <= 128, zg_linear_forward_skinny), always the general kernel;
+ * bit 4: 16-bit storage for the decode step: f16 copies of every weight (made here, once), f16 KV
+ * caches, f16 operands, fp32 residual stream and accumulation -- half the bytes per step, tensor-core tolerance (<= 2e-2 on
+ * logits).  Needs n_seqs <= 128 and max_prompt == 0; zg_batch_k_cache / v_cache then return f16 data. */
 zg_batch *zg_batch_create(const zg_gpt *gpt, size_t n_seqs, size_t cache_rows, size_t max_prompt, int flags);
 void zg_batch_destroy(zg_batch *e);
 /* GPT.forward(seq_len, tokens[b], compute_logits) for every sequence b (tokens: HOST, n_seqs entries).  compute_logits:
@@ -251,6 +255,7 @@ int zg_batch_generate_sample(zg_batch *e, const size_t *prompts, size_t n_inputs
                              unsigned long long seed, unsigned long long seq_base, size_t *out_tokens, int use_prefill);
 void zg_batch_set_position(zg_batch *e, size_t pos); /* next step attends to cache rows [0, pos] (timing at a given context) */
 void zg_batch_run_steps(zg_batch *e, size_t n_steps); /* n greedy steps from the current position, device resident, async */
+int zg_batch_storage_bits(const zg_batch *e); /* 32 (the reference's fp32 weights and caches) or 16 */
 int zg_batch_fused_argmax(const zg_batch *e); /* 1 when the decode step runs the stream-K GEMMs (n_seqs <= 128) and fuses the argmax */
 int zg_batch_read_tokens(zg_batch *e, size_t *out_tokens); /* argmax token of every sequence's last step (HOST, n_seqs ids); synchronises */
 const float *zg_batch_k_cache(const zg_batch *e, size_t layer); /* device, [n_seqs, cache_rows, n_embed] */

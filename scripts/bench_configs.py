@@ -157,8 +157,9 @@ def measure_cfg4(L, lib, trials: int = 5, steps: int = 8, small: bool = False, d
     out = {}
     tok_host = np.random.default_rng(1237).integers(0, cfg.vocab_size, B).astype(np.uint64)
     got = np.zeros(B, np.uint64)
-    for mode_name, single in (("3xtf32", False), ("tf32", True)):
-        eng = BatchEngine(model, B, cache_rows=T, tf32_single_pass=single)
+    for mode_name, single in (("3xtf32", False), ("tf32", True), ("f16", None)):
+        eng = (BatchEngine(model, B, cache_rows=T, tf32_single_pass=single) if single is not None
+               else BatchEngine(model, B, cache_rows=T, storage16=True))
         for Tctx in (1024, 512):
             for _ in range(3):
                 eng.set_position(Tctx - 1)
@@ -190,7 +191,9 @@ def measure_cfg4(L, lib, trials: int = 5, steps: int = 8, small: bool = False, d
             ach = bytes_step / (ms * 1e-3) / 1e9
             out[f"cfg4_{mode_name}_t{Tctx}"] = {
                 "metric": "decode_tokens_per_sec", "value": B / (ms * 1e-3), "unit": "tok/s", "n_gpus": 1, "steps": steps,
-                "ms_per_step": ms, "higher_is_better": True, "dtype": f"f32 storage, {mode_name} tensor-core GEMMs", "data": "synthetic",
+                "ms_per_step": ms, "higher_is_better": True, "data": "synthetic",
+                "dtype": (f"f32 storage, {mode_name} tensor-core GEMMs" if single is not None
+                          else "f16 weight + KV storage (one-time copies), f16 tensor-core GEMMs, f32 accumulate"),
                 "config": {"workload": f"GPT-2 {size}{' (4 layers)' if small else ''} batched decode, batch {B}, context {Tctx} "
                                        "(BASELINE configs[3])", "trials": trials,
                            "l2": "weights + KV read per step (46 GB at context 1024) far exceed L2"},
@@ -209,7 +212,8 @@ def eng_step_bytes(cfg, seq_len: int, batch: int, eng) -> int:
     """Algorithmic bytes of one batched decode step: weights once, KV rows, and the logits round trip
     unless the engine fuses the argmax into the lm_head epilogue."""
     fused = bool(getattr(eng, "fused_argmax", False))
-    b = cfg.decode_bytes(seq_len=seq_len, batch=batch, fused_argmax=fused)
+    elem = 2 if getattr(eng, "storage_bits", 32) == 16 else 4
+    b = cfg.decode_bytes(seq_len=seq_len, batch=batch, elem=elem, fused_argmax=fused)
     if not fused:
         b += 4 * batch * cfg.vocab_size  # logits written by the lm_head GEMM, read again by the argmax kernel
     return b

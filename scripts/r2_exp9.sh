@@ -1,14 +1,14 @@
 #!/bin/bash
 mkdir -p gpurun_out
 {
-for lvl in 15 47 31; do
+for lvl in 47; do
 echo "ZG_PDL=$lvl"
 env ZG_PDL=$lvl timeout 900 python scripts/bench_configs.py cfg4 --trials 3 --steps 4 2>&1 | python -c "
 import sys, json
 for ln in sys.stdin:
     if ln.startswith('{'):
         r = json.loads(ln); print(r['record'], round(r['value']), round(r['ms_per_step'],3), round(r['roofline']['frac'],3), round(r['e2e']['value']))
-" | grep tf32_t1024
+" | grep t1024
 done
 echo "cfg5 small (128 sequences on one GPU)"
 timeout 900 python scripts/bench_configs.py cfg5 --small --trials 3 2>&1 | python -c "

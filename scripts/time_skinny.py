@@ -37,7 +37,7 @@ for M, E in ((64, 1600), (128, 768), (32, 1600)):
         row = f"M={M:4d} {name:11s} N={N:6d} K={K:5d} {N*K*4/1e6:7.1f} MB |"
         for prec, pname in ((0, "tf32"), (2, "3xtf32")):
             t_old = timeit(lambda: L.zg_linear_forward_tc(C.byref(lin), dx.ptr, M * K, out.ptr, prec, None, 0, None, 0))
-            t_new = timeit(lambda: L.zg_linear_forward_skinny(C.byref(lin), dx.ptr, M * K, out.ptr, prec, 0))
+            t_new = timeit(lambda: L.zg_linear_forward_skinny(C.byref(lin), dx.ptr, M * K, out.ptr, prec, 0, None))
             lib.check()
             row += f" {pname}: old {t_old:7.1f} us  skinny {t_new:7.1f} us ({N*K*4/t_new/1e3:6.0f} GB/s) |"
         print(row, flush=True)

@@ -494,3 +494,48 @@ def test_exact_prefill_small_model_ragged(small_model):
     assert np.array_equal(eng.generate_greedy(prompts, n_total, use_prefill=True), toks)
     assert np.array_equal(eng.generate_greedy(prompts, n_total, use_prefill=False), toks)
     eng.close()
+
+
+def test_16bit_storage_decode_step(small_model):
+    """16-bit weight / KV storage for the batched decode step: logits and caches within the tensor-core
+    tolerance (<= 2e-2, north_star) of the fp32 oracle, greedy tokens leave the oracle's sequence only at a near-tie."""
+    from zig_gpt2_b200.batch import BatchEngine
+
+    cfg, w, model = small_model
+    B, n_in, n_total = 5, 8, 40
+    prompts = np.random.RandomState(0).randint(0, cfg.vocab_size, (B, n_in))
+    toks, logits, kvs = _oracle_runs(cfg, w, prompts, n_total)
+    eng = BatchEngine(model, B, cache_rows=64, storage16=True)
+    assert eng.storage_bits == 16 and eng.fused_argmax
+    for s in range(n_total):  # teacher-forced with the oracle's tokens
+        sampling = s >= n_in
+        feed = toks[:, s] if not sampling else (toks[:, s - 1] if s > n_in else prompts[:, -1])
+        eng.forward(s + 1, feed, 1 if sampling else 0)
+        if sampling:
+            got = eng.logits()
+            for b in range(B):
+                assert rel(got[b], logits[b][s - n_in]) <= TC_RTOL, (s, b)
+            assert np.array_equal(eng.read_tokens(), got.argmax(axis=1))
+    k, v = eng.kv(cfg.n_layer - 1, n_total)
+    for b in range(B):
+        assert rel(k[b].astype(np.float32), kvs[b][0]) <= TC_RTOL and rel(v[b].astype(np.float32), kvs[b][1]) <= TC_RTOL
+    got = eng.generate_greedy(prompts, n_total)
+    eng.close()
+    assert np.array_equal(got[:, :n_in], prompts)
+    for b in range(B):
+        diff = np.nonzero(got[b] != toks[b])[0]
+        if diff.size:
+            s = int(diff[0])
+            lg = np.sort(logits[b][s - n_in])
+            assert lg[-1] - lg[-2] <= TC_RTOL * float(np.abs(lg).max()), (b, s)
+
+
+def test_16bit_storage_rejects_unsupported_shapes(small_model):
+    from zig_gpt2_b200 import lib
+    from zig_gpt2_b200.batch import BatchEngine
+
+    cfg, w, model = small_model
+    with pytest.raises(lib.ZgError):
+        BatchEngine(model, 129, cache_rows=16, storage16=True)
+    with pytest.raises(lib.ZgError):
+        BatchEngine(model, 4, cache_rows=16, max_prompt=8, storage16=True)

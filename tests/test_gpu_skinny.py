@@ -43,7 +43,7 @@ def test_skinny_linear_matches_oracle(M, N, K, precision, tol, variant):
     out = DeviceBuffer.from_numpy(r if variant == "residual" else np.zeros((M, N), np.float32))
     lin = ZgLinear(K, N, dw.ptr, db.ptr)
     xform = 1 if variant == "gelu" else (2 if variant == "plain-atomics" else 0)  # bit 1: scalar-atomic epilogue
-    L.zg_linear_forward_skinny(C.byref(lin), dx.ptr, M * K, out.ptr, precision, xform)
+    L.zg_linear_forward_skinny(C.byref(lin), dx.ptr, M * K, out.ptr, precision, xform, None)
     lib.check()
     assert L.zg_tc_error() == 0
     e = rel(out.download().reshape(M, N), want)
@@ -58,7 +58,7 @@ def test_skinny_refuses_unsupported_shapes():
     buf = DeviceBuffer(256 * 256)
     for M, N, K in ((129, 64, 64), (4, 64, 48)):  # too many rows; in_features not a multiple of 32
         lin = ZgLinear(K, N, buf.ptr, None)
-        L.zg_linear_forward_skinny(C.byref(lin), buf.ptr, M * K, buf.ptr, 2, 0)
+        L.zg_linear_forward_skinny(C.byref(lin), buf.ptr, M * K, buf.ptr, 2, 0, None)
         with pytest.raises(lib.ZgError):
             lib.check()
 
@@ -95,3 +95,33 @@ def test_fused_argmax_picks_the_first_maximum(M, N, K):
     assert np.array_equal(got[clear], want[clear])
     picked = logits[np.arange(M), got]
     assert np.all(srt[:, -1] - picked <= 1e-4 * np.abs(logits).max())
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 4800, 1600), (128, 768, 3072), (9, 200, 64)])
+def test_skinny_f16_operands(M, N, K):
+    """16-bit weight storage: f16 copies of inputs and weights, kind::f16 MMAs, fp32 accumulation and fp32 output."""
+    import zg_oracle as zo
+    from zig_gpt2_b200 import lib
+    from zig_gpt2_b200.lib import DeviceBuffer, ZgLinear
+
+    L = lib.init(0)
+    rs = np.random.RandomState(K)
+    x = rs.randn(M, K).astype(np.float32)
+    w = (rs.randn(N, K) * 0.05).astype(np.float32)
+    b = rs.randn(N).astype(np.float32)
+    zo.use_openblas()
+    want = zo.linear(x.astype(np.float16).astype(np.float32), w.astype(np.float16).astype(np.float32), b)
+    full = zo.linear(x, w, b)
+    zo.use_scalar_blas()
+    dx, dw, db = DeviceBuffer.from_numpy(x), DeviceBuffer.from_numpy(w), DeviceBuffer.from_numpy(b)
+    x16, w16 = DeviceBuffer(M * K, np.uint16), DeviceBuffer(N * K, np.uint16)
+    L.zg_to_f16(dx.ptr, x16.ptr, M * K)
+    L.zg_to_f16(dw.ptr, w16.ptr, N * K)
+    out = DeviceBuffer.from_numpy(np.zeros((M, N), np.float32))
+    lin = ZgLinear(K, N, dw.ptr, db.ptr)
+    L.zg_linear_forward_skinny(C.byref(lin), x16.ptr, M * K, out.ptr, 1, 0, w16.ptr)
+    lib.check()
+    assert L.zg_tc_error() == 0
+    got = out.download().reshape(M, N)
+    assert rel(got, want) <= 1e-4   # against the same f16-rounded operands: only the accumulation order differs
+    assert rel(got, full) <= 2e-2   # against the fp32 Linear: the f16 rounding of the operands

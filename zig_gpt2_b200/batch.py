@@ -14,18 +14,20 @@ from .gpt import GPT
 
 class BatchEngine:
     def __init__(self, gpt: GPT, n_seqs: int, cache_rows: Optional[int] = None, max_prompt: int = 0, graph: bool = True,
-                 tf32_single_pass: bool = False, general_gemm_only: bool = False, exact_prefill: bool = False):
+                 tf32_single_pass: bool = False, general_gemm_only: bool = False, exact_prefill: bool = False,
+                 storage16: bool = False):
         self.gpt, self.n_seqs = gpt, int(n_seqs)
         self.cache_rows = int(cache_rows or gpt.config.context_size)
         self.max_prompt = int(max_prompt)
         L = _lib.load()
         self._h = L.zg_batch_create(C.byref(gpt.c), self.n_seqs, self.cache_rows, self.max_prompt,
                                     (0 if graph else 1) | (2 if tf32_single_pass else 0) | (4 if exact_prefill else 0) |
-                                    (8 if general_gemm_only else 0))
+                                    (8 if general_gemm_only else 0) | (16 if storage16 else 0))
         _lib.check()
         if not self._h:
             raise _lib.ZgError("zg_batch_create failed")
         self.pitch = int(L.zg_batch_logits_pitch(self._h))
+        self.storage_bits = int(L.zg_batch_storage_bits(self._h))
         self.fused_argmax = bool(L.zg_batch_fused_argmax(self._h))  # greedy steps never write logits (stream-K path)
 
     def _tok(self, a, n) -> np.ndarray:
@@ -62,7 +64,7 @@ class BatchEngine:
     def kv(self, layer: int, rows: int):
         L = _lib.load()
         E = self.gpt.config.n_embed
-        k = np.empty((self.n_seqs, self.cache_rows, E), np.float32)
+        k = np.empty((self.n_seqs, self.cache_rows, E), np.float16 if self.storage_bits == 16 else np.float32)
         v = np.empty_like(k)
         L.zg_download(k.ctypes.data, L.zg_batch_k_cache(self._h, layer), k.nbytes)
         L.zg_download(v.ctypes.data, L.zg_batch_v_cache(self._h, layer), v.nbytes)

@@ -269,8 +269,35 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_qkv, __half *__restri
 // -------------------------------------------------------------------------------------------------------------------
 constexpr int DEC_WARPS = 8;
 
+// four consecutive cache elements: the caches are fp32 (the reference's storage) or f16 (16-bit KV storage).  Loaded raw
+// (rows in flight stay in their storage format: an f16 row costs half the registers) and widened at the point of use.
+template <typename CT> struct Raw4;
+template <> struct Raw4<float> { typedef float4 type; };
+template <> struct Raw4<__half> { typedef uint2 type; };
+__device__ __forceinline__ float4 ld_raw4(const float *p) { return ld_stream(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ uint2 ld_raw4(const __half *p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 widen(float4 v) { return v; }
+__device__ __forceinline__ float4 widen(uint2 r) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&r.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void narrow(float4 v, float4 *o) { *o = v; }
+__device__ __forceinline__ void narrow(float4 v, uint2 *o) {
+  __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  o->x = *reinterpret_cast<uint32_t *>(&a);
+  o->y = *reinterpret_cast<uint32_t *>(&b);
+}
+__device__ __forceinline__ void st_out(float *p, float v) { *p = v; }
+__device__ __forceinline__ void st_out(__half *p, float v) { *p = __float2half_rn(v); }
+
+// CT: cache element type; OT: output element type (f16 when the c_proj GEMM that follows reads f16 operands)
+template <typename CT, typename OT>
 __global__ void __launch_bounds__(DEC_WARPS * 32)
-attn_decode_batch_kernel(const float *__restrict__ q, int ldq, const float *k_cache, const float *v_cache, long long seq_stride, int E, float *__restrict__ out, int ldo,
+attn_decode_batch_kernel(const float *__restrict__ q, int ldq, const CT *k_cache, const CT *v_cache, long long seq_stride, int E, OT *__restrict__ out, int ldo,
                          const int *pos_dev, int pos_base, const float *knew, const float *vnew, int trigger,
                          int rows_per_seq) {
   __shared__ float s_m[DEC_WARPS], s_l[DEC_WARPS];
@@ -286,60 +313,66 @@ attn_decode_batch_kernel(const float *__restrict__ q, int ldq, const float *k_ca
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = lane >> 4, l16 = lane & 15;  // a half-warp covers one 256-byte head row with float4 loads
   const float4 qv = *reinterpret_cast<const float4 *>(q + (size_t)qrow * ldq + h * HD + 4 * l16);
-  const float *kb = k_cache + (size_t)b * seq_stride + h * HD + 4 * l16;
-  const float *vb = v_cache + (size_t)b * seq_stride + h * HD + 4 * l16;
-  float4 k_last = make_float4(0.f, 0.f, 0.f, 0.f), v_last = k_last;
+  const CT *kb = k_cache + (size_t)b * seq_stride + h * HD + 4 * l16;
+  const CT *vb = v_cache + (size_t)b * seq_stride + h * HD + 4 * l16;
+  typedef typename Raw4<CT>::type RawT;
+  RawT k_last, v_last;  // row T-1 in storage format, from the c_attn output (knew != null)
+  narrow(make_float4(0.f, 0.f, 0.f, 0.f), &k_last);
+  v_last = k_last;
   if (knew) {
-    k_last = *reinterpret_cast<const float4 *>(knew + (size_t)b * ldq + h * HD + 4 * l16);
-    v_last = *reinterpret_cast<const float4 *>(vnew + (size_t)b * ldq + h * HD + 4 * l16);
-    if (threadIdx.x < 16) {  // cache append: 16 lanes x float4 = this head's 64 floats of row T-1
-      *reinterpret_cast<float4 *>(const_cast<float *>(kb) + (size_t)(T - 1) * E) = k_last;
-      *reinterpret_cast<float4 *>(const_cast<float *>(vb) + (size_t)(T - 1) * E) = v_last;
+    narrow(*reinterpret_cast<const float4 *>(knew + (size_t)b * ldq + h * HD + 4 * l16), &k_last);
+    narrow(*reinterpret_cast<const float4 *>(vnew + (size_t)b * ldq + h * HD + 4 * l16), &v_last);
+    if (threadIdx.x < 16) {  // cache append: 16 lanes x 4 elements = this head's 64 values of row T-1
+      *reinterpret_cast<RawT *>(const_cast<CT *>(kb) + (size_t)(T - 1) * E) = k_last;
+      *reinterpret_cast<RawT *>(const_cast<CT *>(vb) + (size_t)(T - 1) * E) = v_last;
     }
   }
   const float scale = 0.125f;
   float m = -INFINITY, l = 0.0f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  // each half-warp walks rows t = 2 * (warp + DEC_WARPS * i) + half, four rows in flight
+  // each half-warp walks rows t = 2 * (warp + DEC_WARPS * i) + half; U rows in flight per half-warp -- 4 KB per warp
+  // whatever the storage width (an f16 row is half as long, so twice as many are kept in flight)
+  constexpr int U = sizeof(CT) == 2 ? 8 : 4;
   constexpr int STEP = 2 * DEC_WARPS;
-  for (int tb = 2 * warp; tb < T; tb += 4 * STEP) {  // warp-uniform trip count: the shuffles below need all 32 lanes
+  for (int tb = 2 * warp; tb < T; tb += U * STEP) {  // warp-uniform trip count: the shuffles below need all 32 lanes
     const int t0 = tb + half;
-    float4 kk[4], vv[4];
-    float s[4];
+    RawT kk[U], vv[U];
+    float s[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int t = t0 + u * STEP;
-      if (t < T) {
-        if (knew && t == T - 1) {
-          kk[u] = k_last;
-          vv[u] = v_last;
-        } else {
-          kk[u] = ld_stream(reinterpret_cast<const float4 *>(kb + (size_t)t * E));
-          vv[u] = ld_stream(reinterpret_cast<const float4 *>(vb + (size_t)t * E));
-        }
+      kk[u] = k_last;
+      vv[u] = v_last;
+      if (t < T && !(knew && t == T - 1)) {
+        kk[u] = ld_raw4(kb + (size_t)t * E);
+        vv[u] = ld_raw4(vb + (size_t)t * E);
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int t = t0 + u * STEP;
-      float d = (t < T) ? (qv.x * kk[u].x + qv.y * kk[u].y + qv.z * kk[u].z + qv.w * kk[u].w) : 0.0f;
+      const float4 kf = widen(kk[u]);
+      float d = (t < T) ? (qv.x * kf.x + qv.y * kf.y + qv.z * kf.z + qv.w * kf.w) : 0.0f;
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
       s[u] = (t < T) ? d * scale : -INFINITY;
     }
-    float mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
+    float mx = s[0];
+#pragma unroll
+    for (int u = 1; u < U; ++u) mx = fmaxf(mx, s[u]);
     const float m_new = fmaxf(m, mx);
     if (m_new > -INFINITY) {
       const float a = __expf(m - m_new);
       acc.x *= a; acc.y *= a; acc.z *= a; acc.w *= a;
       l *= a;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         if (s[u] > -INFINITY) {
           const float p = __expf(s[u] - m_new);
+          const float4 vf = widen(vv[u]);
           l += p;
-          acc.x = fmaf(p, vv[u].x, acc.x); acc.y = fmaf(p, vv[u].y, acc.y);
-          acc.z = fmaf(p, vv[u].z, acc.z); acc.w = fmaf(p, vv[u].w, acc.w);
+          acc.x = fmaf(p, vf.x, acc.x); acc.y = fmaf(p, vf.y, acc.y);
+          acc.z = fmaf(p, vf.z, acc.z); acc.w = fmaf(p, vf.w, acc.w);
         }
       }
       m = m_new;
@@ -374,7 +407,7 @@ attn_decode_batch_kernel(const float *__restrict__ q, int ldq, const float *k_ca
       num = fmaf(f, s_o[w][threadIdx.x], num);
       den = fmaf(f, s_l[w], den);
     }
-    out[(size_t)qrow * ldo + h * HD + threadIdx.x] = num / den;
+    st_out(out + (size_t)qrow * ldo + h * HD + threadIdx.x, num / den);
   }
 }
 
@@ -410,9 +443,18 @@ void attn_decode_batch_launch(const float *q, int ldq, const float *k_cache, con
                               int B, int H, int E, float *out, int ldo, const int *pos_dev, int pos_base,
                               const float *knew, const float *vnew, int rows_per_seq) {
   // rows_per_seq > 0 (causal prefill): B * rows_per_seq query rows
-  ZG_CUDA(launch_pdl(PDL_ATTN_DEP, attn_decode_batch_kernel, dim3(H, rows_per_seq ? B * rows_per_seq : B), dim3(DEC_WARPS * 32), 0,
-                     ctx().stream, q, ldq, k_cache, v_cache, seq_stride, E, out, ldo, pos_dev, pos_base, knew, vnew,
-                     (knew && (pdl_mask() & PDL_ATTN_TRIGGER)) ? 1 : 0, rows_per_seq));
+  ZG_CUDA(launch_pdl(PDL_ATTN_DEP, attn_decode_batch_kernel<float, float>, dim3(H, rows_per_seq ? B * rows_per_seq : B),
+                     dim3(DEC_WARPS * 32), 0, ctx().stream, q, ldq, k_cache, v_cache, seq_stride, E, out, ldo, pos_dev, pos_base, knew,
+                     vnew, (knew && (pdl_mask() & PDL_ATTN_TRIGGER)) ? 1 : 0, rows_per_seq));
+  ZG_LAUNCH_CHECK();
+}
+
+// the same step over f16 caches, f16 output (16-bit KV storage: half the bytes the step has to stream)
+void attn_decode_batch_launch_f16(const float *q, int ldq, const void *k_cache, const void *v_cache, long long seq_stride, int B,
+                                  int H, int E, void *out_f16, int ldo, const int *pos_dev, const float *knew, const float *vnew) {
+  ZG_CUDA(launch_pdl(PDL_ATTN_DEP, attn_decode_batch_kernel<__half, __half>, dim3(H, B), dim3(DEC_WARPS * 32), 0, ctx().stream, q, ldq,
+                     (const __half *)k_cache, (const __half *)v_cache, seq_stride, E, (__half *)out_f16, ldo, pos_dev, 0, knew, vnew,
+                     (knew && (pdl_mask() & PDL_ATTN_TRIGGER)) ? 1 : 0, 0));
   ZG_LAUNCH_CHECK();
 }
 

@@ -16,4 +16,7 @@ void attn_decode_batch_launch(const float *q, int ldq, const float *k_cache, con
                               int B, int H, int E, float *out, int ldo, const int *pos_dev, int pos_base,
                               const float *knew = nullptr, const float *vnew = nullptr, int rows_per_seq = 0);
 
+void attn_decode_batch_launch_f16(const float *q, int ldq, const void *k_cache, const void *v_cache, long long seq_stride, int B,
+                                  int H, int E, void *out_f16, int ldo, const int *pos_dev, const float *knew, const float *vnew);
+
 }  // namespace zg

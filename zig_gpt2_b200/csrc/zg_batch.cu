@@ -117,8 +117,8 @@ void launch_ln_rows(const float *in, size_t in_stride, void *out, const float *g
 // four warps per row -- the decode step has <= 128 rows, so the row is split over 128 threads instead of giving a single
 // warp ~2,000 dependent instructions (the one-warp-per-row kernel took 11-12 us per call at E = 1600).
 constexpr int LNZ_THREADS = 128;
-template <int LN_MAXV>  // float4 per thread: n_embed <= 4 * LNZ_THREADS * LN_MAXV
-__global__ void __launch_bounds__(LNZ_THREADS) ln_zero_rows_kernel(const float *__restrict__ in, float *__restrict__ out,
+template <int LN_MAXV, bool OUT_F16>  // float4 per thread: n_embed <= 4 * LNZ_THREADS * LN_MAXV
+__global__ void __launch_bounds__(LNZ_THREADS) ln_zero_rows_kernel(const float *__restrict__ in, void *__restrict__ out,
                                                                    const float *__restrict__ g, const float *__restrict__ b,
                                                                    int E, float eps, float *__restrict__ zero, int zero_n,
                                                                    int trigger) {
@@ -162,17 +162,40 @@ __global__ void __launch_bounds__(LNZ_THREADS) ln_zero_rows_kernel(const float *
       y.y = (v[i].y - mean) / std_ * gg.y + bb.y;
       y.z = (v[i].z - mean) / std_ * gg.z + bb.z;
       y.w = (v[i].w - mean) / std_ * gg.w + bb.w;
-      reinterpret_cast<float4 *>(out + (size_t)row * E)[c] = y;
+      if (OUT_F16) {
+        __half2 lo = __floats2half2_rn(y.x, y.y), hi = __floats2half2_rn(y.z, y.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t *>(&lo);
+        pk.y = *reinterpret_cast<uint32_t *>(&hi);
+        reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(out) + (size_t)row * E)[c] = pk;
+      } else {
+        reinterpret_cast<float4 *>(reinterpret_cast<float *>(out) + (size_t)row * E)[c] = y;
+      }
     }
   }
 }
-void launch_ln_zero_rows(const float *in, float *out, const float *g, const float *b, int E, int rows, float *zero, int zero_n,
+template <bool OUT_F16>
+void launch_ln_zero_rows(const float *in, void *out, const float *g, const float *b, int E, int rows, float *zero, int zero_n,
                          cudaStream_t s) {
-  if (E <= 1024) ZG_CUDA(launch_pdl(PDL_LN_DEP, ln_zero_rows_kernel<2>, dim3(rows), dim3(LNZ_THREADS), 0, s, in, out, g, b, E, 1e-5f, zero, zero_n,
-                                    (pdl_mask() & PDL_LN_TRIGGER) ? 1 : 0));
-  else ZG_CUDA(launch_pdl(PDL_LN_DEP, ln_zero_rows_kernel<4>, dim3(rows), dim3(LNZ_THREADS), 0, s, in, out, g, b, E, 1e-5f, zero, zero_n,
-                                    (pdl_mask() & PDL_LN_TRIGGER) ? 1 : 0));
+  const int trig = (pdl_mask() & PDL_LN_TRIGGER) ? 1 : 0;
+  if (E <= 1024) ZG_CUDA(launch_pdl(PDL_LN_DEP, ln_zero_rows_kernel<2, OUT_F16>, dim3(rows), dim3(LNZ_THREADS), 0, s, in, out, g, b, E, 1e-5f, zero, zero_n, trig));
+  else ZG_CUDA(launch_pdl(PDL_LN_DEP, ln_zero_rows_kernel<4, OUT_F16>, dim3(rows), dim3(LNZ_THREADS), 0, s, in, out, g, b, E, 1e-5f, zero, zero_n, trig));
   ZG_LAUNCH_CHECK();
+}
+
+// h16 = f16(gelu(pre)): the GELU between c_fc and mlp c_proj (main.zig:80) of the 16-bit decode step, where c_proj's f16
+// operand cannot be produced by c_fc's epilogue (stream-K partial sums).  Exact tanhf GELU (ops.zig:225).
+__global__ void __launch_bounds__(256) gelu_to_f16_kernel(const float *__restrict__ pre, __half *__restrict__ out, size_t n4) {
+  pdl_trigger();
+  pdl_wait();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4 *>(pre)[i];
+    __half2 a = __floats2half2_rn(gelu_ref(v.x), gelu_ref(v.y)), b = __floats2half2_rn(gelu_ref(v.z), gelu_ref(v.w));
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t *>(&a);
+    pk.y = *reinterpret_cast<uint32_t *>(&b);
+    reinterpret_cast<uint2 *>(out)[i] = pk;
+  }
 }
 
 // greedy argmax per row (first maximum wins, like the oracle); writes the next token and the history row
@@ -273,6 +296,12 @@ struct zg_batch {
   void *samp = nullptr;                    // device {temp, seed, seq_base} of the sampling generate loop
   cudaGraphExec_t graph_sampling = nullptr;
   bool skinny = false;
+  // 16-bit storage (flags bit 4): f16 copies of every weight, f16 KV caches, f16 operands between the kernels of the
+  // stream-K decode step; fp32 residual stream and fp32 accumulation throughout
+  bool store16 = false;
+  __half *h16 = nullptr, *att16 = nullptr, *h4_16 = nullptr;
+  void *k_cache16 = nullptr, *v_cache16 = nullptr;
+  SkinnyPlan sk_head_logits;  // lm_head into a zeroed logits buffer (compute_logits = 1)
   GemmPlan dec_head, pre_head;
   std::vector<AttnPrefillPlan> pre_attn;
   int pre_T = -1;
@@ -333,7 +362,35 @@ bool build_decode_plans(zg_batch *e) {
 // Decode step with <= 128 sequences: every layer GEMM through the stream-K kernel.  c_attn reduces into a zeroed qkv
 // (its K/V columns are appended to the caches by the attention kernel), c_fc into a zeroed pre-activation buffer whose
 // GELU is applied by mlp c_proj's operand load, both c_proj's into the residual stream in place.
+bool build_skinny_plans16(zg_batch *e) {
+  const int B = e->B, E = (int)e->cfg.n_embed;
+  e->sk_plans.resize(e->layers.size());
+  for (size_t l = 0; l < e->layers.size(); ++l) {
+    const LayerW &w = e->layers[l];
+    SkinnyLayerPlans &p = e->sk_plans[l];
+    SkinnyArgs a;
+    a.M = B; a.N = 3 * E; a.K = E; a.bias = w.attn_b; a.out = e->qkv; a.ldo = 3 * E;
+    if (!skinny_plan(&p.attn, 0, e->h16, E, w.attn_w16, a)) return false;
+    a = SkinnyArgs();
+    a.M = B; a.N = E; a.K = E; a.bias = w.proj_b; a.out = e->x; a.ldo = E;
+    if (!skinny_plan(&p.proj, 0, e->att16, E, w.proj_w16, a)) return false;
+    a = SkinnyArgs();
+    a.M = B; a.N = 4 * E; a.K = E; a.bias = w.fc_b; a.out = e->h4; a.ldo = 4 * E;
+    if (!skinny_plan(&p.fc, 0, e->h16, E, w.fc_w16, a)) return false;
+    a = SkinnyArgs();
+    a.M = B; a.N = E; a.K = 4 * E; a.bias = w.proj2_b; a.out = e->x; a.ldo = E;
+    if (!skinny_plan(&p.proj2, 0, e->h4_16, 4 * E, w.proj2_w16, a)) return false;
+  }
+  SkinnyArgs a;
+  a.M = B; a.N = (int)e->cfg.vocab_size; a.K = E; a.best = e->best;
+  if (!skinny_plan(&e->sk_head, 0, e->h16, E, e->wte16, a)) return false;
+  a = SkinnyArgs();
+  a.M = B; a.N = (int)e->cfg.vocab_size; a.K = E; a.out = e->logits; a.ldo = e->Vp;
+  return skinny_plan(&e->sk_head_logits, 0, e->h16, E, e->wte16, a);
+}
+
 bool build_skinny_plans(zg_batch *e) {
+  if (e->store16) return build_skinny_plans16(e);
   const int B = e->B, E = (int)e->cfg.n_embed;
   e->sk_plans.resize(e->layers.size());
   for (size_t l = 0; l < e->layers.size(); ++l) {
@@ -427,15 +484,31 @@ void enqueue_step(zg_batch *e, bool from_prompt, int n_inputs, int head) {
   }
   embed_rows_kernel<<<B, 128, 0, s>>>(e->wte, e->wpe, e->tok, 1, e->pos, E, V, e->x);
   ZG_LAUNCH_CHECK();
-  for (size_t l = 0; e->skinny && l < e->layers.size(); ++l) {
+  for (size_t l = 0; e->store16 && l < e->layers.size(); ++l) {  // 16-bit storage: same step, f16 operands and caches
     const LayerW &w = e->layers[l];
     const SkinnyLayerPlans &p = e->sk_plans[l];
-    launch_ln_zero_rows(e->x, e->h, w.ln1_g, w.ln1_b, E, B, e->qkv, 3 * E, s);  // main.zig:121-123; qkv := 0
+    launch_ln_zero_rows<true>(e->x, e->h16, w.ln1_g, w.ln1_b, E, B, e->qkv, 3 * E, s);
+    skinny_launch(p.attn);
+    attn_decode_batch_launch_f16(e->qkv, 3 * E, (const __half *)e->k_cache16 + l * e->layer_stride,
+                                 (const __half *)e->v_cache16 + l * e->layer_stride, (long long)e->seq_stride, B, H, E, e->att16, E,
+                                 e->pos, e->qkv + E, e->qkv + 2 * E);
+    skinny_launch(p.proj);
+    launch_ln_zero_rows<true>(e->x, e->h16, w.ln2_g, w.ln2_b, E, B, e->h4, 4 * E, s);
+    skinny_launch(p.fc);
+    ZG_CUDA(launch_pdl(PDL_LN_DEP, gelu_to_f16_kernel, dim3(2 * ctx().sm_count), dim3(256), 0, s, (const float *)e->h4, e->h4_16,
+                       (size_t)B * E));  // B * 4E / 4 float4
+    ZG_LAUNCH_CHECK();
+    skinny_launch(p.proj2);
+  }
+  for (size_t l = 0; e->skinny && !e->store16 && l < e->layers.size(); ++l) {
+    const LayerW &w = e->layers[l];
+    const SkinnyLayerPlans &p = e->sk_plans[l];
+    launch_ln_zero_rows<false>(e->x, e->h, w.ln1_g, w.ln1_b, E, B, e->qkv, 3 * E, s);  // main.zig:121-123; qkv := 0
     skinny_launch(p.attn);                                                       // c_attn (ops.zig:143)
     attn_decode_batch_launch(e->qkv, 3 * E, e->k_cache + l * e->layer_stride, e->v_cache + l * e->layer_stride,
                              (long long)e->seq_stride, B, H, E, e->att, E, e->pos, 0, e->qkv + E, e->qkv + 2 * E);
     skinny_launch(p.proj);                                                       // x += c_proj(att) (ops.zig:172, main.zig:136-139)
-    launch_ln_zero_rows(e->x, e->h, w.ln2_g, w.ln2_b, E, B, e->h4, 4 * E, s);    // main.zig:140; h4 := 0
+    launch_ln_zero_rows<false>(e->x, e->h, w.ln2_g, w.ln2_b, E, B, e->h4, 4 * E, s);    // main.zig:140; h4 := 0
     skinny_launch(p.fc);                                                         // c_fc pre-activation (main.zig:79)
     skinny_launch(p.proj2);                                                      // x += c_proj(gelu(.)) (main.zig:80-81,142-145)
   }
@@ -451,8 +524,23 @@ void enqueue_step(zg_batch *e, bool from_prompt, int n_inputs, int head) {
     gemm_launch(p.fc);     // c_fc + GELU (main.zig:79-80)
     gemm_launch(p.proj2);  // c_proj + residual (main.zig:81,142-145)
   }
-  if (head == 2 && e->skinny) {
-    launch_ln_zero_rows(e->x, e->h, e->lnf_g, e->lnf_b, E, B, reinterpret_cast<float *>(e->best), 4, s);  // main.zig:189; best := 0
+  if (head && e->store16) {
+    if (head == 2) {
+      launch_ln_zero_rows<true>(e->x, e->h16, e->lnf_g, e->lnf_b, E, B, reinterpret_cast<float *>(e->best), 4, s);
+      skinny_launch(e->sk_head);
+      skinny_finish_argmax(e->best, e->tok, e->hist, B, e->pos);
+    } else {
+      launch_ln_zero_rows<true>(e->x, e->h16, e->lnf_g, e->lnf_b, E, B, e->logits, e->Vp, s);  // logits := 0
+      skinny_launch(e->sk_head_logits);
+      if (head == 3) {
+        launch_sample_rows(e->logits, (size_t)e->Vp, V, e->samp, e->pos, 0, e->tok, e->hist, B, nullptr);
+      } else {
+        argmax_rows_kernel<<<B, 256, 0, s>>>(e->logits, (size_t)e->Vp, V, e->tok, e->hist, B, e->pos);
+        ZG_LAUNCH_CHECK();
+      }
+    }
+  } else if (head == 2 && e->skinny) {
+    launch_ln_zero_rows<false>(e->x, e->h, e->lnf_g, e->lnf_b, E, B, reinterpret_cast<float *>(e->best), 4, s);  // main.zig:189; best := 0
     skinny_launch(e->sk_head);                                         // tied lm_head + argmax (main.zig:192-194)
     skinny_finish_argmax(e->best, e->tok, e->hist, B, e->pos);
   } else if (head) {
@@ -552,6 +640,13 @@ zg_batch *zg_batch_create(const zg_gpt *gpt, size_t n_seqs, size_t cache_rows, s
   e->Vp = (int)((V + 3) & ~(size_t)3);
   e->f16_prefill = max_prompt > 0;
   e->exact_prefill = e->f16_prefill && (flags & 4);
+  e->store16 = (flags & 16) != 0;
+  if (e->store16 && (max_prompt > 0 || n_seqs > 128 || E % 64 != 0 || getenv("ZG_NO_SPLIT_K") != nullptr)) {
+    set_error(1, "zg_batch_create: 16-bit storage needs n_seqs <= 128, n_embed % 64 == 0, max_prompt == 0 (prompts go token by token)",
+              __FILE__, __LINE__);
+    delete e;
+    return nullptr;
+  }
   e->use_graph = !(flags & 1);
   e->dec_mode = (flags & 2) ? 1 : 2;
   e->wte = gpt->wte.weight;
@@ -569,19 +664,28 @@ zg_batch *zg_batch_create(const zg_gpt *gpt, size_t n_seqs, size_t cache_rows, s
     w.fc_w = b.mlp.c_fc.weight; w.fc_b = b.mlp.c_fc.bias;
     w.proj2_w = b.mlp.c_proj.weight; w.proj2_b = b.mlp.c_proj.bias;
     w.attn_w16 = w.proj_w16 = w.fc_w16 = w.proj2_w16 = nullptr;
-    if (e->f16_prefill && !e->exact_prefill) {
+    if ((e->f16_prefill && !e->exact_prefill) || e->store16) {
       w.attn_w16 = f16_copy(e, w.attn_w, 3 * E * E);
       w.proj_w16 = f16_copy(e, w.proj_w, E * E);
       w.fc_w16 = f16_copy(e, w.fc_w, 4 * E * E);
       w.proj2_w16 = f16_copy(e, w.proj2_w, 4 * E * E);
     }
   }
-  if (e->f16_prefill && !e->exact_prefill) e->wte16 = f16_copy(e, e->wte, V * E);
+  if ((e->f16_prefill && !e->exact_prefill) || e->store16) e->wte16 = f16_copy(e, e->wte, V * E);
   const size_t B = n_seqs;
   e->seq_stride = cache_rows * E;
   e->layer_stride = B * e->seq_stride;
-  e->k_cache = balloc<float>(e, L * e->layer_stride);
-  e->v_cache = balloc<float>(e, L * e->layer_stride);
+  if (e->store16) {
+    e->k_cache16 = balloc<__half>(e, L * e->layer_stride);
+    e->v_cache16 = balloc<__half>(e, L * e->layer_stride);
+    e->h16 = balloc<__half>(e, B * E);
+    e->att16 = balloc<__half>(e, B * E);
+    e->h4_16 = balloc<__half>(e, B * 4 * E);
+    e->k_cache = e->v_cache = balloc<float>(e, 4);  // placeholders: the fp32 caches do not exist in this mode
+  } else {
+    e->k_cache = balloc<float>(e, L * e->layer_stride);
+    e->v_cache = balloc<float>(e, L * e->layer_stride);
+  }
   e->x = balloc<float>(e, B * E);
   e->h = balloc<float>(e, B * E);
   e->qkv = balloc<float>(e, B * 3 * E);
@@ -623,8 +727,13 @@ zg_batch *zg_batch_create(const zg_gpt *gpt, size_t n_seqs, size_t cache_rows, s
     zg_batch_destroy(e);
     return nullptr;
   }
-  zg_memset(e->k_cache, 0, L * e->layer_stride * sizeof(float));
-  zg_memset(e->v_cache, 0, L * e->layer_stride * sizeof(float));
+  if (e->store16) {
+    zg_memset(e->k_cache16, 0, L * e->layer_stride * sizeof(__half));
+    zg_memset(e->v_cache16, 0, L * e->layer_stride * sizeof(__half));
+  } else {
+    zg_memset(e->k_cache, 0, L * e->layer_stride * sizeof(float));
+    zg_memset(e->v_cache, 0, L * e->layer_stride * sizeof(float));
+  }
   zg_memset(e->pos, 0, 4 * sizeof(int));
   zg_memset(e->tok, 0, B * sizeof(u64));
   gemm_init_attrs();
@@ -633,7 +742,7 @@ zg_batch *zg_batch_create(const zg_gpt *gpt, size_t n_seqs, size_t cache_rows, s
   // ZG_NO_SPLIT_K=1 asks for run-to-run bit-reproducible steps: no reduction in arrival order anywhere, i.e. no split-K
   // in the general kernel and no stream-K kernel at all
   e->skinny = !(flags & 8) && getenv("ZG_NO_SPLIT_K") == nullptr && skinny_supported(e->B, (int)E, (int)E);
-  if (!build_decode_plans(e) || (e->skinny && !build_skinny_plans(e))) {
+  if ((!e->store16 && !build_decode_plans(e)) || (e->skinny && !build_skinny_plans(e))) {
     zg_batch_destroy(e);
     return nullptr;
   }
@@ -799,6 +908,7 @@ void zg_batch_run_steps(zg_batch *e, size_t n_steps) {
   }
 }
 int zg_batch_fused_argmax(const zg_batch *e) { return e->skinny ? 1 : 0; }
+int zg_batch_storage_bits(const zg_batch *e) { return e->store16 ? 16 : 32; }
 // Set the common position (and so the attended length) directly: timing a step at T = 1024 needs no 1023 real steps.
 void zg_batch_set_position(zg_batch *e, size_t pos) {
   if (!require_ready("zg_batch_set_position")) return;
@@ -815,7 +925,13 @@ int zg_batch_read_tokens(zg_batch *e, size_t *out_tokens) {
   for (int b = 0; b < e->B; ++b) out_tokens[b] = (size_t)e->hist_host[b];
   return zg_last_error();
 }
-const float *zg_batch_k_cache(const zg_batch *e, size_t layer) { return e->k_cache + layer * e->layer_stride; }
-const float *zg_batch_v_cache(const zg_batch *e, size_t layer) { return e->v_cache + layer * e->layer_stride; }
+const float *zg_batch_k_cache(const zg_batch *e, size_t layer) {  // f16 data when zg_batch_storage_bits() == 16
+  if (e->store16) return reinterpret_cast<const float *>((const __half *)e->k_cache16 + layer * e->layer_stride);
+  return e->k_cache + layer * e->layer_stride;
+}
+const float *zg_batch_v_cache(const zg_batch *e, size_t layer) {
+  if (e->store16) return reinterpret_cast<const float *>((const __half *)e->v_cache16 + layer * e->layer_stride);
+  return e->v_cache + layer * e->layer_stride;
+}
 
 }  // extern "C"

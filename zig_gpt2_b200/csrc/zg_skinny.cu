@@ -27,8 +27,7 @@ namespace zg {
 namespace {
 
 constexpr int WM = 128;          // weight rows per tile = UMMA M = TMEM lanes
-constexpr int ROW_BYTES = 128;   // one swizzle row = 32 fp32 of K
-constexpr int BK = 32;
+constexpr int ROW_BYTES = 128;   // one swizzle row = 32 fp32 (or 64 f16) of K
 constexpr int W_STAGE = WM * ROW_BYTES;
 constexpr int SK_THREADS = 6 * 32;
 constexpr int SK_SMEM_BUDGET = 196 * 1024;
@@ -50,13 +49,16 @@ struct SkCfg {
 };
 
 // SPLIT: 3xTF32.  MB: batch columns of the accumulator (64 or 128).  XF: the transform warps touch every landed tile
-// (always when SPLIT; otherwise only when X needs the GELU).
-template <bool SPLIT, int MB, bool XF>
+// (always when SPLIT; otherwise only when X needs the GELU).  F16: both operands are f16 copies (16-bit weight storage:
+// half the bytes per weight), kind::f16 with fp32 accumulation; partial sums still leave as fp32.
+template <bool SPLIT, int MB, bool XF, bool F16>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                    const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ SkinnyArgs g) {
   using C = SkCfg<SPLIT, MB>;
   static_assert(!SPLIT || XF, "the 3xTF32 split is done by the transform warps");
+  static_assert(!F16 || (!SPLIT && !XF), "f16 operands are neither split nor transformed");
+  constexpr int BK = F16 ? 64 : 32;  // elements per 128-byte swizzle row
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = tc::smem_addr(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -127,7 +129,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc = tc::umma_idesc(2u, WM, MB, 0, 0);
+      constexpr uint32_t idesc = tc::umma_idesc(F16 ? 0u : 2u, WM, MB, 0, 0);
       const uint32_t ready_bar = XF ? xf_bar : full_bar;
       uint32_t stage = 0, phase = 0, tphase = 0;
       bool ok = true;
@@ -152,7 +154,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
               tc::umma<true>(tmem, da, db_lo, idesc, 1u);
               tc::umma<true>(tmem, da, db, idesc, 1u);
             } else {
-              tc::umma<true>(tmem, da, db, idesc, acc);
+              tc::umma<!F16>(tmem, da, db, idesc, acc);
             }
           }
           tc::umma_commit(empty_bar + 8 * stage);
@@ -277,14 +279,14 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
   if (warp == 1) tc::tmem_dealloc<MB>(tmem);
 }
 
-template <bool SPLIT, int MB, bool XF>
+template <bool SPLIT, int MB, bool XF, bool F16 = false>
 void launch_skinny(const SkinnyPlan &p) {
   static unsigned attr_gen = 0;  // per device: redone after every zg_init
   if (attr_gen != ctx().generation) {
-    ZG_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<SPLIT, MB, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<SPLIT, MB>::SMEM));
+    ZG_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<SPLIT, MB, XF, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<SPLIT, MB>::SMEM));
     attr_gen = ctx().generation;
   }
-  ZG_CUDA(launch_pdl(PDL_GEMM_DEP, gemm_skinny_kernel<SPLIT, MB, XF>, dim3(p.grid), dim3(SK_THREADS), (size_t)SkCfg<SPLIT, MB>::SMEM, ctx().stream,
+  ZG_CUDA(launch_pdl(PDL_GEMM_DEP, gemm_skinny_kernel<SPLIT, MB, XF, F16>, dim3(p.grid), dim3(SK_THREADS), (size_t)SkCfg<SPLIT, MB>::SMEM, ctx().stream,
                      p.tm_w, p.tm_x, p.tm_out, p.args));
   ZG_LAUNCH_CHECK();
 }
@@ -293,11 +295,13 @@ void launch_skinny(const SkinnyPlan &p) {
 
 bool g_skinny_scalar_atomics = false;  // test hook: element-wise fp32 atomics instead of TMA reduce-adds
 
-bool skinny_supported(int M, int N, int K) { return M >= 1 && M <= 128 && N >= 1 && K >= BK && K % BK == 0; }
+bool skinny_supported(int M, int N, int K) { return M >= 1 && M <= 128 && N >= 1 && K >= 64 && K % 64 == 0; }
 
-bool skinny_plan(SkinnyPlan *p, int mode, const float *X, size_t ldx, const float *W, const SkinnyArgs &args) {
-  if (!skinny_supported(args.M, args.N, args.K)) {
-    set_error(1, "skinny_plan: needs 1 <= M <= 128 and in_features a multiple of 32", __FILE__, __LINE__);
+bool skinny_plan(SkinnyPlan *p, int mode, const void *X, size_t ldx, const void *W, const SkinnyArgs &args) {
+  const bool f16 = mode == 0;
+  const int BK = f16 ? 64 : 32, es = f16 ? 2 : 4;
+  if (args.M < 1 || args.M > 128 || args.N < 1 || args.K < BK || args.K % BK != 0 || (f16 && args.xform != SK_XFORM_NONE)) {
+    set_error(1, "skinny_plan: needs 1 <= M <= 128 and in_features a multiple of 32 (f16 operands: 64, no transform)", __FILE__, __LINE__);
     return false;
   }
   p->args = args;
@@ -311,8 +315,8 @@ bool skinny_plan(SkinnyPlan *p, int mode, const float *X, size_t ldx, const floa
   long long grid = units / 4;
   if (grid < 1) grid = 1;
   p->grid = (int)(grid < sms ? grid : sms);
-  if (!make_tmap_2d(&p->tm_w, W, 0, (uint64_t)args.N, (uint64_t)args.K, (uint64_t)args.K * 4, WM, BK)) return false;
-  if (!make_tmap_2d(&p->tm_x, X, 0, (uint64_t)args.M, (uint64_t)args.K, (uint64_t)ldx * 4, (uint32_t)p->mb, BK)) return false;
+  if (!make_tmap_2d(&p->tm_w, W, f16 ? 1 : 0, (uint64_t)args.N, (uint64_t)args.K, (uint64_t)args.K * es, WM, BK)) return false;
+  if (!make_tmap_2d(&p->tm_x, X, f16 ? 1 : 0, (uint64_t)args.M, (uint64_t)args.K, (uint64_t)ldx * es, (uint32_t)p->mb, BK)) return false;
   p->tm_out = p->tm_x;  // valid placeholder
   p->args.tma_out = 0;
   if (args.best) {
@@ -327,6 +331,11 @@ bool skinny_plan(SkinnyPlan *p, int mode, const float *X, size_t ldx, const floa
 
 void skinny_launch(const SkinnyPlan &p) {
   const bool split = p.mode == 2, xf = split || p.args.xform != SK_XFORM_NONE;
+  if (p.mode == 0) {
+    if (p.mb == 64) launch_skinny<false, 64, false, true>(p);
+    else launch_skinny<false, 128, false, true>(p);
+    return;
+  }
   if (p.mb == 64) {
     if (split) launch_skinny<true, 64, true>(p);
     else if (xf) launch_skinny<false, 64, true>(p);
@@ -356,12 +365,14 @@ void skinny_init_attrs() {  // outside any stream capture: cudaFuncSetAttribute 
   static unsigned gen = 0;
   if (gen == ctx().generation) return;
   gen = ctx().generation;
-  ZG_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<true, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<true, 64>::SMEM));
-  ZG_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<false, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<false, 64>::SMEM));
-  ZG_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<false, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<false, 64>::SMEM));
-  ZG_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<true, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<true, 128>::SMEM));
-  ZG_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<false, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<false, 128>::SMEM));
-  ZG_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<false, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<false, 128>::SMEM));
+  ZG_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<true, 64, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<true, 64>::SMEM));
+  ZG_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<false, 64, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<false, 64>::SMEM));
+  ZG_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<false, 64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<false, 64>::SMEM));
+  ZG_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<true, 128, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<true, 128>::SMEM));
+  ZG_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<false, 128, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<false, 128>::SMEM));
+  ZG_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<false, 128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<false, 128>::SMEM));
+  ZG_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<false, 64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<false, 64>::SMEM));
+  ZG_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<false, 128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<false, 128>::SMEM));
 }
 
 }  // namespace zg
@@ -373,8 +384,8 @@ extern "C" {
 // Linear.forward for M <= 128 rows through the swapped-operand stream-K kernel: outputs[M,N] += bias + inputs . W^T.
 // `outputs` must hold zeros (plain Linear) or the residual (x += Linear(h)) on entry.  precision: 0 = TF32, 2 = 3xTF32.
 // xform: 0 none, 1 = inputs := gelu(inputs) on the fly (the GELU between c_fc and mlp c_proj, main.zig:80).
-void zg_linear_forward_skinny(const zg_linear *self, const float *inputs, size_t inputs_len, float *outputs, int precision,
-                              int xform) {
+void zg_linear_forward_skinny(const zg_linear *self, const void *inputs, size_t inputs_len, float *outputs, int precision,
+                              int xform, const void *weight_lowp) {
   if (!require_ready("zg_linear_forward_skinny")) return;
   g_skinny_scalar_atomics = (xform & 2) != 0;  // test hook (bit 1): the scalar-atomic epilogue
   xform &= 1;
@@ -387,7 +398,8 @@ void zg_linear_forward_skinny(const zg_linear *self, const float *inputs, size_t
   a.ldo = a.N;
   a.xform = xform;
   SkinnyPlan p;
-  const bool planned = skinny_plan(&p, precision == 2 ? 2 : 1, inputs, self->in_features, self->weight, a);
+  const bool planned = precision == 1 ? skinny_plan(&p, 0, inputs, self->in_features, weight_lowp, a)
+                                      : skinny_plan(&p, precision == 2 ? 2 : 1, inputs, self->in_features, self->weight, a);
   g_skinny_scalar_atomics = false;
   if (planned) skinny_launch(p);
 }

@@ -28,14 +28,14 @@ struct SkinnyArgs {
 struct SkinnyPlan {
   CUtensorMap tm_w, tm_x, tm_out;
   SkinnyArgs args;
-  int mode = 1;  // 1 = fp32 operands as tf32, 2 = 3xTF32 error-compensated
+  int mode = 1;  // 0 = f16 operands (16-bit weight storage), 1 = fp32 operands as tf32, 2 = 3xTF32 error-compensated
   int mb = 64;   // batch columns of the accumulator
   int grid = 0;
 };
 
 bool skinny_supported(int M, int N, int K);
-// X: [M, K] row-major with pitch ldx elements; W: [N, K] row-major (Linear.weight, ops.zig:9)
-bool skinny_plan(SkinnyPlan *p, int mode, const float *X, size_t ldx, const float *W, const SkinnyArgs &args);
+// X: [M, K] row-major with pitch ldx elements; W: [N, K] row-major (Linear.weight, ops.zig:9); fp32, or f16 for mode 0
+bool skinny_plan(SkinnyPlan *p, int mode, const void *X, size_t ldx, const void *W, const SkinnyArgs &args);
 void skinny_launch(const SkinnyPlan &p);
 void skinny_init_attrs();
 // after a fused-argmax launch: unpack best[2 m] into tok[m] (and hist[*pos_dev][m] when hist != null)

@@ -68,7 +68,7 @@ SIGNATURES = {
     "zg_timer_begin": (I, []), "zg_timer_end_ms": (C.c_float, []),
     "zg_linear_forward": (V, [C.POINTER(ZgLinear), P, Z, P]),
     "zg_linear_forward_tc": (V, [C.POINTER(ZgLinear), P, Z, P, I, P, I, P, I]),
-    "zg_linear_forward_skinny": (V, [C.POINTER(ZgLinear), P, Z, P, I, I]),
+    "zg_linear_forward_skinny": (V, [C.POINTER(ZgLinear), P, Z, P, I, I, P]),
     "zg_linear_argmax_skinny": (V, [C.POINTER(ZgLinear), P, Z, I, P, P]),
     "zg_to_f16": (V, [P, P, Z]), "zg_tc_error": (I, []), "zg_tc_set_direct_epilogue": (V, [I]),
     "zg_embedding_forward": (V, [C.POINTER(ZgEmbedding), c_size_p, Z, P]),
@@ -101,7 +101,7 @@ SIGNATURES = {
     "zg_batch_generate_greedy": (I, [P, c_size_p, Z, Z, c_size_p, I]),
     "zg_batch_generate_sample": (I, [P, c_size_p, Z, Z, C.c_float, C.c_ulonglong, C.c_ulonglong, c_size_p, I]),
     "zg_batch_set_position": (V, [P, Z]), "zg_batch_run_steps": (V, [P, Z]),
-    "zg_batch_read_tokens": (I, [P, c_size_p]), "zg_batch_fused_argmax": (I, [P]),
+    "zg_batch_read_tokens": (I, [P, c_size_p]), "zg_batch_fused_argmax": (I, [P]), "zg_batch_storage_bits": (I, [P]),
     "zg_batch_k_cache": (P, [P, Z]), "zg_batch_v_cache": (P, [P, Z]),
     "zg_attention_prefill": (V, [P, P, Z, Z, Z, Z]),
     "zg_attention_decode_batch": (V, [P, P, P, Z, Z, Z, Z, Z, P]),
