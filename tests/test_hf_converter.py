@@ -100,3 +100,22 @@ def test_gpu_paths_reproduce_hf_logits(converted, fused):
         fwd(s + 1, int(t), True, state)
         assert float(np.abs(state.logits.download() - logits[s]).max()) <= 1e-4 * scale, s
     model.close()
+
+
+def test_convert_a_local_hf_checkpoint_directory(tmp_path):
+    """`python -m zig_gpt2_b200.convert <hf_dir> <out_dir>`: save_pretrained() directory -> raw/model-* files + vocab JSONs."""
+    import json
+
+    from zig_gpt2_b200.convert import convert_hf_dir
+
+    m = hf_model(n_layer=1, n_head=2, n_embd=128, vocab=300, ctx=32, seed=3)
+    hf_dir, out_dir = tmp_path / "hf", tmp_path / "model"
+    m.save_pretrained(str(hf_dir))
+    json.dump({"a": 0, "b": 1}, open(hf_dir / "vocab.json", "w"))
+    cfg = convert_hf_dir(str(hf_dir), str(out_dir))
+    assert cfg == GPTConfig(300, 32, 1, 2, 128)
+    back = load_raw(cfg, str(out_dir / "raw"))
+    want = from_hf_state_dict(m.state_dict(), cfg)
+    assert all(np.array_equal(back[n], want[n]) for n in want)
+    assert json.load(open(out_dir / "encoder.json")) == {"a": 0, "b": 1}
+    assert len(json.load(open(out_dir / "byte_encoder.json"))) == 256

@@ -250,6 +250,16 @@ pub fn generate(gpt: GPT, encoder: bpe.Encoder, temp: f32, inputs: []usize, stat
 }
 
 /// Greedy variant: the whole loop is one persistent-kernel launch; tokens stream into a pinned host ring.
+/// generate with GPT.sample run entirely on the device: the draw of step s is Philox4x32-10(seed; s, sequence)
+/// (zg_philox_uniform), so a run is reproducible and needs no host round trip per token.
+pub fn generate_sample(gpt: GPT, encoder: bpe.Encoder, temp: f32, seed: u64, inputs: []usize, out_tokens: []usize, state: State) !void {
+    if (c.zg_engine_generate_sample(gpt.engine, inputs.ptr, inputs.len, out_tokens.len, temp, seed, 0, out_tokens.ptr) != 0) return ops.DeviceError.CudaFailure;
+    for (out_tokens) |token| {
+        const decoded = encoder.decode(&[1]usize{token}, state.decoded);
+        std.debug.print("{s}", .{decoded});
+    }
+}
+
 pub fn generate_greedy(gpt: GPT, encoder: bpe.Encoder, inputs: []usize, out_tokens: []usize, state: State) !void {
     if (c.zg_engine_generate_greedy(gpt.engine, inputs.ptr, inputs.len, out_tokens.len, out_tokens.ptr) != 0) return ops.DeviceError.CudaFailure;
     for (out_tokens) |token| {
