@@ -255,8 +255,8 @@ pub fn generate(gpt: GPT, encoder: bpe.Encoder, temp: f32, inputs: []usize, stat
 pub fn generate_sample(gpt: GPT, encoder: bpe.Encoder, temp: f32, seed: u64, inputs: []usize, out_tokens: []usize, state: State) !void {
     if (c.zg_engine_generate_sample(gpt.engine, inputs.ptr, inputs.len, out_tokens.len, temp, seed, 0, out_tokens.ptr) != 0) return ops.DeviceError.CudaFailure;
     for (out_tokens) |token| {
-        const decoded = encoder.decode(&[1]usize{token}, state.decoded);
-        std.debug.print("{s}", .{decoded});
+        const decoded_len = encoder.decode(&[_]usize{token}, state.decoded);
+        std.debug.print("{s}", .{state.decoded[0..decoded_len]});
     }
 }
 
