@@ -13,6 +13,8 @@
 // (2) attn_decode_batch_kernel: one new token per sequence against that sequence's fp32 KV cache (ops.zig:249-307,
 //     query length 1, no mask) for B sequences at once; one CTA per (head, sequence), each K/V row read exactly once
 //     with 128-bit loads straight from the time-major cache (no transposed copies), online softmax across warps.
+#include <stdlib.h>
+
 #include "zg_attn.cuh"
 
 namespace zg {
@@ -258,6 +260,259 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_qkv, __half *__restri
   if (warp == 1) tc::tmem_dealloc<ATT_TMEM_COLS>(tmem);
 }
 
+// ---- version 2 of the prefill kernel (round 2): P and O never leave tensor memory, two threads per query row ---------------
+//   * P = 2^(S scale - m) goes back to TMEM as packed f16 (tcgen05.st, columns [192, 256)) and the P V product reads its A
+//     operand straight from TMEM (tcgen05.mma, A-from-TMEM form): no shared-memory round trip, no swizzle arithmetic, no
+//     generic->async proxy fence, 32 KB less shared memory per CTA;
+//   * O accumulates in TMEM across the key tiles (P V with accumulate) instead of being pulled into registers and
+//     folded with 64 FMAs per thread and tile.  The running maximum is LAZY: a row keeps scaling by the maximum it
+//     last committed to until a tile exceeds it by more than 2^8 (P then still fits f16 with room to spare); only then
+//     is O rescaled in TMEM (ld, multiply, st), for the whole warp at once because tcgen05.ld / st are warp-collective.
+//     l and O are always scaled by the same reference, so the final O / l is exact;
+//   * EIGHT softmax warps: the two threads (warp w, warp w + 4, same lane) share a query row and split its 128 key
+//     columns, 64 each (and the 64 output columns, 32 each); the row maximum of a tile is exchanged through shared
+//     memory (double-buffered by tile parity, one named barrier per tile).  With 83 registers per thread two such CTAs
+//     (20 warps) fit an SM: five warps per scheduler hide the tcgen05.ld and MUFU latencies that four could not.
+//   tcgen05.commit semantics order everything: s_full(j) arrives only after every earlier MMA of the issuing thread --
+//   including P V of tile j-1 -- has completed, so a softmax thread that has seen s_full(j) may rescale O and overwrite P.
+constexpr int ATT2_THREADS = (2 + 8) * 32;
+constexpr int ATT2_SMEM = TILE_BYTES * (1 + 2 + 2) + 128 + 2 * 2 * QT * 4;  // Q, K x2, V x2, barriers, row maxima [parity][half][row]
+#ifndef ZG_ATTN_POLY_EVERY
+#define ZG_ATTN_POLY_EVERY 0  // 2: every other element takes the FMA-pipe polynomial (round 1), 4 / 8: every fourth / eighth,
+                              // 0: MUFU.EX2 only -- measured 112.5 / 104.7 / 101.3 / 99.3 us per layer at 355M, 16 x 1024
+#endif
+constexpr float LAZY_RESCALE = 8.0f;                                         // log2 domain
+
+// 64 key columns [c0, c0 + 64) of this thread's row: running maximum
+template <bool DIAG>
+__device__ __forceinline__ float half_row_max(uint32_t ts_row, int r, int c0) {
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = c0; c < c0 + 64; c += 32) {
+    uint32_t sr[32];
+    tc::tmem_ld32(ts_row + c, sr);
+    tc::tmem_ld_wait();
+    if (DIAG) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c + i <= r) mx = fmaxf(mx, __uint_as_float(sr[i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]));  // FMNMX3
+    }
+  }
+  return mx;
+}
+// the same 64 columns: P as packed f16 into TMEM columns tp_row + c/2 .., returns the partial row sum
+template <bool DIAG>
+__device__ __forceinline__ float half_row_exp(uint32_t ts_row, uint32_t tp_row, int r, int c0, float scale2, float m_ref,
+                                              float &tile_max) {
+  float sum = 0.0f, mx = -INFINITY;
+#pragma unroll 1
+  for (int c = c0; c < c0 + 64; c += 32) {
+    uint32_t sr[32];
+    tc::tmem_ld32(ts_row + c, sr);
+    tc::tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      // one element in ZG_ATTN_POLY_EVERY takes the FMA-pipe polynomial, the others MUFU.EX2: with eight softmax warps
+      // per CTA the kernel is bound by instruction issue (ncu: issue slots 54 % busy, XU 18 %), and the polynomial costs
+      // ~10 instructions against 2
+      const float x0 = fmaf(__uint_as_float(sr[i]), scale2, -m_ref);
+      const float x1 = fmaf(__uint_as_float(sr[i + 1]), scale2, -m_ref);
+      float p0 = fast_exp2(x0);
+      float p1 = (ZG_ATTN_POLY_EVERY > 0 && ((i >> 1) % (ZG_ATTN_POLY_EVERY / 2 > 0 ? ZG_ATTN_POLY_EVERY / 2 : 1)) == 0) ? exp2_poly(x1) : fast_exp2(x1);
+      if (DIAG) {
+        if (c + i > r) p0 = 0.0f; else mx = fmaxf(mx, x0);
+        if (c + i + 1 > r) p1 = 0.0f; else mx = fmaxf(mx, x1);
+      } else {
+        mx = max3(mx, x0, x1);  // how far this tile rises above the reference (log2 domain)
+      }
+      sum += p0 + p1;
+      __half2 t = __floats2half2_rn(p0, p1);
+      pk[i >> 1] = *reinterpret_cast<uint32_t *>(&t);
+    }
+    tc::tmem_st16(tp_row + (c >> 1), pk);  // keys c .. c+31 -> 16 packed columns
+  }
+  tc::tmem_st_wait();
+  tile_max = mx;
+  return sum;
+}
+
+__global__ void __launch_bounds__(ATT2_THREADS, 2)
+attn_prefill_kernel_v2(const __grid_constant__ CUtensorMap tm_qkv, __half *__restrict__ out, int T, int H, int E,
+                       int n_bh, unsigned *err) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = tc::smem_addr(smem_raw);
+  const uint32_t sQ = base, sK = base + TILE_BYTES, sV = sK + 2 * TILE_BYTES;
+  const uint32_t bars = sV + 2 * TILE_BYTES;
+  const uint32_t q_full = bars, kv_full = bars + 8, kv_empty = bars + 24, s_full = bars + 40, p_full = bars + 48,
+                 pv_full = bars + 56, slot = bars + 64, abort_flag = bars + 68;
+  float *rowx = reinterpret_cast<float *>(smem_raw + (bars + 128 - base));  // [2 parity][2 half][128 rows]
+  const tc::Guard guard{err, abort_flag};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int num_qt = (T + QT - 1) / QT;
+  const int qt = num_qt - 1 - (int)(blockIdx.x / n_bh);  // heavy (late) query tiles first
+  const int bh = blockIdx.x % n_bh, b = bh / H, h = bh % H;
+  const int q0 = qt * QT, n_kv = qt + 1;
+  const int row_base = b * T;
+
+  if (threadIdx.x == 0) {
+    if (base & 1023u) atomicExch(err, 4u);
+    tc::mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(kv_full + 8 * s, 1);
+      tc::mbar_init(kv_empty + 8 * s, 1);
+    }
+    tc::mbar_init(s_full, 1);
+    tc::mbar_init(p_full, 8);
+    tc::mbar_init(pv_full, 1);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(abort_flag), "r"(0u));
+    tc::fence_mbar_init();
+    tc::prefetch_tmap(&tm_qkv);
+  }
+  if (warp == 1) tc::tmem_alloc<ATT_TMEM_COLS>(slot);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *reinterpret_cast<uint32_t *>(smem_raw + (slot - base));
+  const uint32_t tS = tmem, tO = tmem + 128, tP = tmem + 192;
+
+  // warps 0 and 1 run their loops with all 32 lanes and warp-uniform operands; one elected lane issues (zg_tc.cuh, *_u)
+  if (warp == 0) {  // ---------------- TMA producer ----------------
+    tc::mbar_expect_tx_u(q_full, TILE_BYTES);
+    tc::tma_load_2d_u(sQ, &tm_qkv, h * HD, row_base + q0, q_full);
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j & 1;
+      if (!tc::mbar_wait_u(kv_empty + 8 * s, ((j >> 1) & 1) ^ 1, guard)) break;
+      tc::mbar_expect_tx_u(kv_full + 8 * s, 2 * TILE_BYTES);
+      tc::tma_load_2d_u(sK + s * TILE_BYTES, &tm_qkv, E + h * HD, row_base + j * KT, kv_full + 8 * s);
+      tc::tma_load_2d_u(sV + s * TILE_BYTES, &tm_qkv, 2 * E + h * HD, row_base + j * KT, kv_full + 8 * s);
+    }
+  } else if (warp == 1) {  // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc_s = tc::umma_idesc(0, QT, KT, 0, 0);  // Q (K-major) x K (K-major)
+    constexpr uint32_t idesc_o = tc::umma_idesc(0, QT, HD, 0, 1);  // P (TMEM, K-major) x V (MN-major: head dim contiguous)
+    // descriptors differ only in the 14-bit start-address field (bits 0..13, units of 16 bytes): built once, then an add
+    // on the low word per MMA (shared memory ends below 256 KB, so the field never carries)
+    const uint64_t dq0 = tc::umma_desc_sw128(sQ, 16, 1024), dk0 = tc::umma_desc_sw128(sK, 16, 1024),
+                   dv0 = tc::umma_desc_sw128(sV, 1024, 1024);
+    bool ok = tc::mbar_wait_u(q_full, 0, guard);
+    for (int j = 0; j < n_kv && ok; ++j) {
+      const int s = j & 1;
+      if (!tc::mbar_wait_u(kv_full + 8 * s, (j >> 1) & 1, guard)) break;
+      tc::fence_after_sync();
+      const uint64_t dk = dk0 + (uint64_t)(s * (TILE_BYTES >> 4)), dv = dv0 + (uint64_t)(s * (TILE_BYTES >> 4));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tc::umma_u<false>(tS, dq0 + 2 * k, dk + 2 * k, idesc_s, (uint32_t)(k != 0));
+      tc::umma_commit_u(s_full);
+      if (!tc::mbar_wait_u(p_full, j & 1, guard)) break;
+      tc::fence_after_sync();
+#pragma unroll
+      for (int i = 0; i < 8; ++i)  // 16 keys per MMA = 8 packed columns of P; V rows 16 i .. 16 i + 15
+        tc::umma_ts_f16_u(tO, tP + 8 * i, dv + 128 * i, idesc_o, (uint32_t)((j | i) != 0));
+      tc::umma_commit_u(kv_empty + 8 * s);
+      if (j == n_kv - 1) tc::umma_commit_u(pv_full);
+    }
+  } else {  // ---------------- softmax warps: two threads per query row ----------------
+    const int quad = warp & 3, r = quad * 32 + lane;  // TMEM lane == tile row (tcgen05.ld: warp w touches lanes 32 (w % 4) ..)
+    const int hf = (warp - 2) >> 2;                   // which 64 key columns / 32 output columns of the row
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const float scale2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    // S is read from TMEM ONCE per tile: tcgen05.ld moves 64 bytes per clock and SM, so the classic two passes (row
+    // maximum, then exponentials) cost 2 x 64 KB = 2,048 cycles per 128 x 128 tile -- more than everything else together.
+    // The exponentials are taken against the reference maximum the row already has and the tile's own maximum is
+    // tracked on the side; the reference moves (and O is rescaled) BEFORE THE NEXT tile when the tile rose more than
+    // 2^8 above it, and only a rise above 2^15 (P would leave the f16 range) makes the row pair redo the tile at once.
+    // The very first tile has no reference yet and takes the two passes.
+    float m_ref = -INFINITY, l = 0.0f, m_next = 0.0f;
+    bool pending = false;  // the reference moves to m_next before the next tile
+    bool ok = true;
+    for (int j = 0; j < n_kv; ++j) {
+      if (!tc::mbar_wait(s_full, j & 1, guard)) { ok = false; break; }
+      tc::fence_after_sync();
+      const bool diag = (j == qt);  // only the last key tile crosses the causal boundary
+      float *xb = rowx + (j & 1) * 2 * QT;
+      auto rescale_o = [&](float alpha) {  // warp-collective: this warp's 32 rows x this half's 32 columns of O
+        uint32_t pr[32];
+        tc::tmem_ld32(tO + lane_base + 32 * hf, pr);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pr[i] = __float_as_uint(__uint_as_float(pr[i]) * alpha);
+        tc::tmem_st32(tO + lane_base + 32 * hf, pr);
+        tc::tmem_st_wait();
+      };
+      if (j == 0) {
+        float mx = (diag ? half_row_max<true>(tS + lane_base, r, 64 * hf) : half_row_max<false>(tS + lane_base, r, 64 * hf)) * scale2;
+        xb[hf * QT + r] = mx;
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight softmax warps
+        m_ref = fmaxf(mx, xb[(hf ^ 1) * QT + r]);
+      } else if (__any_sync(0xffffffffu, pending)) {
+        const float alpha = pending ? fast_exp2(m_ref - m_next) : 1.0f;
+        rescale_o(alpha);
+        l *= alpha;
+        if (pending) m_ref = m_next;
+        pending = false;
+      }
+      float tmax;
+      float sum = diag ? half_row_exp<true>(tS + lane_base, tP + lane_base, r, 64 * hf, scale2, m_ref, tmax)
+                       : half_row_exp<false>(tS + lane_base, tP + lane_base, r, 64 * hf, scale2, m_ref, tmax);
+      if (j > 0) {
+        xb[hf * QT + r] = tmax;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float rise = fmaxf(tmax, xb[(hf ^ 1) * QT + r]);  // of the whole row, relative to m_ref
+        const bool redo = rise > 15.0f;
+        if (__any_sync(0xffffffffu, redo)) {  // P would overflow f16: move the reference now and recompute (rare)
+          const float alpha = redo ? fast_exp2(-rise) : 1.0f;
+          rescale_o(alpha);
+          l *= alpha;
+          if (redo) m_ref += rise;
+          sum = diag ? half_row_exp<true>(tS + lane_base, tP + lane_base, r, 64 * hf, scale2, m_ref, tmax)
+                     : half_row_exp<false>(tS + lane_base, tP + lane_base, r, 64 * hf, scale2, m_ref, tmax);
+        } else if (rise > LAZY_RESCALE) {
+          pending = true;
+          m_next = m_ref + rise;
+        }
+      }
+      l += sum;
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(p_full);
+    }
+    // total row sum = the two halves' partial sums (same reference maximum)
+    float *xb = rowx + ((n_kv & 1) * 2 * QT);
+    xb[hf * QT + r] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += xb[(hf ^ 1) * QT + r];
+    if (ok && tc::mbar_wait(pv_full, 0, guard)) {
+      tc::fence_after_sync();
+      const float inv = 1.0f / l;
+      __half *dst = out + (size_t)(row_base + q0 + r) * E + h * HD + 32 * hf;
+      uint32_t pr[32];
+      tc::tmem_ld32(tO + lane_base + 32 * hf, pr);
+      tc::tmem_ld_wait();
+      if (q0 + r < T) {
+#pragma unroll
+        for (int d = 0; d < 32; d += 8) {
+          uint4 pk;
+          __half2 t0 = __floats2half2_rn(__uint_as_float(pr[d]) * inv, __uint_as_float(pr[d + 1]) * inv),
+                         t1 = __floats2half2_rn(__uint_as_float(pr[d + 2]) * inv, __uint_as_float(pr[d + 3]) * inv),
+                         t2 = __floats2half2_rn(__uint_as_float(pr[d + 4]) * inv, __uint_as_float(pr[d + 5]) * inv),
+                         t3 = __floats2half2_rn(__uint_as_float(pr[d + 6]) * inv, __uint_as_float(pr[d + 7]) * inv);
+          pk.x = *reinterpret_cast<uint32_t *>(&t0); pk.y = *reinterpret_cast<uint32_t *>(&t1);
+          pk.z = *reinterpret_cast<uint32_t *>(&t2); pk.w = *reinterpret_cast<uint32_t *>(&t3);
+          *reinterpret_cast<uint4 *>(dst + d) = pk;
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (warp == 1) tc::tmem_dealloc<ATT_TMEM_COLS>(tmem);
+}
+
 // -------------------------------------------------------------------------------------------------------------------
 // Batched single-query attention off the fp32 caches.  cache layout: [B][C][E] (time-major, heads interleaved -- the
 // reference's per-block cache, main.zig:298-299, once per sequence).  q: [B, ldq] (row b holds q at columns h*64..).
@@ -423,10 +678,16 @@ bool attn_prefill_plan(AttnPrefillPlan *p, const void *qkv_f16, void *out_f16, i
   return make_tmap_2d(&p->tm_qkv, qkv_f16, 1, (uint64_t)B * T, (uint64_t)3 * E, (uint64_t)3 * E * 2, QT, HD);
 }
 
+static bool attn_v1() {  // A/B switch: ZG_ATTN_V1=1 selects the round-1 kernel (P through shared memory, O in registers)
+  static const bool v1 = getenv("ZG_ATTN_V1") != nullptr;
+  return v1;
+}
+
 void attn_init_attrs() {
   static unsigned attr_gen = 0;  // per device: redone after every zg_init
   if (attr_gen != ctx().generation) {
     ZG_CUDA(cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    ZG_CUDA(cudaFuncSetAttribute(attn_prefill_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
     attr_gen = ctx().generation;
   }
 }
@@ -434,8 +695,12 @@ void attn_init_attrs() {
 void attn_prefill_launch(const AttnPrefillPlan &p) {
   attn_init_attrs();
   const int num_qt = (p.T + QT - 1) / QT, n_bh = p.B * p.H;
-  attn_prefill_kernel<<<num_qt * n_bh, ATT_THREADS, ATT_SMEM, ctx().stream>>>(
-      p.tm_qkv, reinterpret_cast<__half *>(p.out), p.T, p.H, p.E, n_bh, gemm_error_word());
+  if (attn_v1())
+    attn_prefill_kernel<<<num_qt * n_bh, ATT_THREADS, ATT_SMEM, ctx().stream>>>(
+        p.tm_qkv, reinterpret_cast<__half *>(p.out), p.T, p.H, p.E, n_bh, gemm_error_word());
+  else
+    attn_prefill_kernel_v2<<<num_qt * n_bh, ATT2_THREADS, ATT2_SMEM, ctx().stream>>>(
+        p.tm_qkv, reinterpret_cast<__half *>(p.out), p.T, p.H, p.E, n_bh, gemm_error_word());
   ZG_LAUNCH_CHECK();
 }
 

@@ -241,58 +241,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   // work item = (output tile, K slice); slice ks covers k-blocks [ks num_kb / ksplit, (ks + 1) num_kb / ksplit)
   const int ksplit = g.ksplit, items = tiles * ksplit;
 
-  if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer ----------------
-      uint32_t stage = 0, phase = 0;
-      bool ok = true;
-      for (int item = blockIdx.x; item < items && ok; item += gridDim.x) {
-        const int tile = item % tiles, ks = item / tiles;
-        const int m_blk = g.n_fastest ? tile / num_n : tile % num_m, n_blk = g.n_fastest ? tile % num_n : tile / num_m;
-        const int kb0 = ks * num_kb / ksplit, kb1 = (ks + 1) * num_kb / ksplit;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          if (!tc::mbar_wait(empty_bar + 8 * stage, phase ^ 1, guard)) { ok = false; break; }
-          tc::mbar_expect_tx(full_bar + 8 * stage, C::STAGE);
-          tc::tma_load_2d(sA + stage * A_STAGE, &tm_a, kb * BK, m_blk * BM, full_bar + 8 * stage);
-          tc::tma_load_2d(sB + stage * C::B_STAGE, &tm_b, kb * BK, n_blk * BN, full_bar + 8 * stage);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-        }
+  // warps 0 and 1 run their loops with all 32 lanes and warp-uniform operands; one elected lane issues (zg_tc.cuh, *_u)
+  if (warp == 0) {  // ---------------- TMA producer ----------------
+    uint32_t stage = 0, phase = 0;
+    bool ok = true;
+    for (int item = blockIdx.x; item < items && ok; item += gridDim.x) {
+      const int tile = item % tiles, ks = item / tiles;
+      const int m_blk = g.n_fastest ? tile / num_n : tile % num_m, n_blk = g.n_fastest ? tile % num_n : tile / num_m;
+      const int kb0 = ks * num_kb / ksplit, kb1 = (ks + 1) * num_kb / ksplit;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        if (!tc::mbar_wait_u(empty_bar + 8 * stage, phase ^ 1, guard)) { ok = false; break; }
+        tc::mbar_expect_tx_u(full_bar + 8 * stage, C::STAGE);
+        tc::tma_load_2d_u(sA + stage * A_STAGE, &tm_a, kb * BK, m_blk * BM, full_bar + 8 * stage);
+        tc::tma_load_2d_u(sB + stage * C::B_STAGE, &tm_b, kb * BK, n_blk * BN, full_bar + 8 * stage);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {  // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc = tc::umma_idesc(TF32 ? 2u : 0u, BM, BN, 0, 0);
-      const uint32_t ready_bar = SPLIT ? split_bar : full_bar;
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      bool ok = true;
-      for (int item = blockIdx.x; item < items && ok; item += gridDim.x) {
-        const int ks = item / tiles;
-        const int kb0 = ks * num_kb / ksplit, kb1 = (ks + 1) * num_kb / ksplit;
-        if (!tc::mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1, guard)) break;
+  } else if (warp == 1) {  // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc = tc::umma_idesc(TF32 ? 2u : 0u, BM, BN, 0, 0);
+    const uint32_t ready_bar = SPLIT ? split_bar : full_bar;
+    // descriptors differ only in the 14-bit start-address field (units of 16 bytes): built once, then an add per MMA
+    const uint64_t da0 = tc::umma_desc_sw128(sA, 16, 1024), db0 = tc::umma_desc_sw128(sB, 16, 1024);
+    const uint64_t da0_lo = tc::umma_desc_sw128(SPLIT ? sAlo : sA, 16, 1024), db0_lo = tc::umma_desc_sw128(SPLIT ? sBlo : sB, 16, 1024);
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    bool ok = true;
+    for (int item = blockIdx.x; item < items && ok; item += gridDim.x) {
+      const int ks = item / tiles;
+      const int kb0 = ks * num_kb / ksplit, kb1 = (ks + 1) * num_kb / ksplit;
+      if (!tc::mbar_wait_u(tempty_bar + 8 * acc, acc_phase ^ 1, guard)) break;
+      tc::fence_after_sync();
+      const uint32_t d = tmem + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        if (!tc::mbar_wait_u(ready_bar + 8 * stage, phase, guard)) { ok = false; break; }
         tc::fence_after_sync();
-        const uint32_t d = tmem + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          if (!tc::mbar_wait(ready_bar + 8 * stage, phase, guard)) { ok = false; break; }
-          tc::fence_after_sync();
-          const uint32_t a = sA + stage * A_STAGE, b = sB + stage * C::B_STAGE;
+        const uint64_t oa = (uint64_t)(stage * (A_STAGE >> 4)), ob = (uint64_t)(stage * (C::B_STAGE >> 4));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per swizzle row: UMMA_K = 8 (tf32) / 16 (f16)
-            const uint64_t da = tc::umma_desc_sw128(a + 32 * k, 16, 1024), db = tc::umma_desc_sw128(b + 32 * k, 16, 1024);
-            if constexpr (SPLIT) {
-              const uint64_t da_lo = tc::umma_desc_sw128(sAlo + stage * A_STAGE + 32 * k, 16, 1024);
-              const uint64_t db_lo = tc::umma_desc_sw128(sBlo + stage * C::B_STAGE + 32 * k, 16, 1024);
-              tc::umma<true>(d, da_lo, db, idesc, (uint32_t)(((kb - kb0) | k) != 0));
-              tc::umma<true>(d, da, db_lo, idesc, 1u);
-              tc::umma<true>(d, da, db, idesc, 1u);
-            } else {
-              tc::umma<TF32>(d, da, db, idesc, (uint32_t)(((kb - kb0) | k) != 0));
-            }
+        for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per swizzle row: UMMA_K = 8 (tf32) / 16 (f16)
+          const uint64_t da = da0 + oa + 2 * k, db = db0 + ob + 2 * k;
+          if constexpr (SPLIT) {
+            const uint64_t da_lo = da0_lo + oa + 2 * k, db_lo = db0_lo + ob + 2 * k;
+            tc::umma_u<true>(d, da_lo, db, idesc, (uint32_t)(((kb - kb0) | k) != 0));
+            tc::umma_u<true>(d, da, db_lo, idesc, 1u);
+            tc::umma_u<true>(d, da, db, idesc, 1u);
+          } else {
+            tc::umma_u<TF32>(d, da, db, idesc, (uint32_t)(((kb - kb0) | k) != 0));
           }
-          tc::umma_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs have read it
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        if (ok) tc::umma_commit(tfull_bar + 8 * acc);  // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        tc::umma_commit_u(empty_bar + 8 * stage);  // frees the smem slot once these MMAs have read it
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
+      if (ok) tc::umma_commit_u(tfull_bar + 8 * acc);  // accumulator complete -> epilogue
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (SPLIT && warp >= 6) {  // ---------------- operand splitters (3xTF32) ----------------
     const int t = threadIdx.x - 6 * 32;  // 0..127

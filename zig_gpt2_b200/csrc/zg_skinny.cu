@@ -103,67 +103,66 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
     u1 = (int)((long long)num_n * (blockIdx.x + 1) / gridDim.x) * num_kb;
   }
 
-  if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer ----------------
-      const uint64_t pol_w = tc::policy_evict_first(), pol_x = tc::policy_evict_last();
-      uint32_t stage = 0, phase = 0;
-      // The weights are written by no kernel of the step: the first ring-full of W tiles is requested BEFORE waiting for
-      // the predecessor grid (programmatic dependent launch), so the pipeline fill overlaps the predecessor's tail.
-      const int npre = min(u1 - u0, C::STAGES);
-      for (int i = 0; i < npre; ++i) {
-        const int u = u0 + i, nt = u / num_kb, kb = u - nt * num_kb;
-        tc::mbar_expect_tx(full_bar + 8 * i, W_STAGE + C::X_STAGE);
-        tc::tma_load_2d_hint(sW + i * W_STAGE, &tm_w, kb * BK, nt * WM, full_bar + 8 * i, pol_w);
+  // warps 0 and 1 run their loops with all 32 lanes and warp-uniform operands; one elected lane issues (zg_tc.cuh, *_u)
+  if (warp == 0) {  // ---------------- TMA producer ----------------
+    const uint64_t pol_w = tc::policy_evict_first(), pol_x = tc::policy_evict_last();
+    uint32_t stage = 0, phase = 0;
+    // The weights are written by no kernel of the step: the first ring-full of W tiles is requested BEFORE waiting for
+    // the predecessor grid (programmatic dependent launch), so the pipeline fill overlaps the predecessor's tail.
+    const int npre = min(u1 - u0, C::STAGES);
+    for (int i = 0; i < npre; ++i) {
+      const int u = u0 + i, nt = u / num_kb, kb = u - nt * num_kb;
+      tc::mbar_expect_tx_u(full_bar + 8 * i, W_STAGE + C::X_STAGE);
+      tc::tma_load_2d_hint_u(sW + i * W_STAGE, &tm_w, kb * BK, nt * WM, full_bar + 8 * i, pol_w);
+    }
+    pdl_wait();  // X is the predecessor's output
+    for (int u = u0; u < u1; ++u) {
+      const int nt = u / num_kb, kb = u - nt * num_kb;
+      if (u - u0 >= npre) {
+        if (!tc::mbar_wait_u(empty_bar + 8 * stage, phase ^ 1, guard)) break;
+        tc::mbar_expect_tx_u(full_bar + 8 * stage, W_STAGE + C::X_STAGE);
+        tc::tma_load_2d_hint_u(sW + stage * W_STAGE, &tm_w, kb * BK, nt * WM, full_bar + 8 * stage, pol_w);
       }
-      pdl_wait();  // X is the predecessor's output
-      for (int u = u0; u < u1; ++u) {
-        const int nt = u / num_kb, kb = u - nt * num_kb;
-        if (u - u0 >= npre) {
-          if (!tc::mbar_wait(empty_bar + 8 * stage, phase ^ 1, guard)) break;
-          tc::mbar_expect_tx(full_bar + 8 * stage, W_STAGE + C::X_STAGE);
-          tc::tma_load_2d_hint(sW + stage * W_STAGE, &tm_w, kb * BK, nt * WM, full_bar + 8 * stage, pol_w);
+      tc::tma_load_2d_hint_u(sX + stage * C::X_STAGE, &tm_x, kb * BK, 0, full_bar + 8 * stage, pol_x);
+      if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {  // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc = tc::umma_idesc(F16 ? 0u : 2u, WM, MB, 0, 0);
+    const uint32_t ready_bar = XF ? xf_bar : full_bar;
+    // descriptors differ only in the 14-bit start-address field (units of 16 bytes): built once, then an add per MMA
+    const uint64_t da0 = tc::umma_desc_sw128(sW, 16, 1024), db0 = tc::umma_desc_sw128(sX, 16, 1024);
+    const uint64_t da0_lo = tc::umma_desc_sw128(SPLIT ? sWlo : sW, 16, 1024), db0_lo = tc::umma_desc_sw128(SPLIT ? sXlo : sX, 16, 1024);
+    uint32_t stage = 0, phase = 0, tphase = 0;
+    bool ok = true;
+    int u = u0;
+    while (u < u1 && ok) {
+      const int nt = u / num_kb;
+      const int seg_end = min(u1, (nt + 1) * num_kb);
+      if (!tc::mbar_wait_u(tempty_bar, tphase ^ 1, guard)) break;  // the previous segment's accumulator has been read
+      tc::fence_after_sync();
+      for (int uu = u; uu < seg_end; ++uu) {
+        if (!tc::mbar_wait_u(ready_bar + 8 * stage, phase, guard)) { ok = false; break; }
+        tc::fence_after_sync();
+        const uint64_t oa = (uint64_t)(stage * (W_STAGE >> 4)), ob = (uint64_t)(stage * (C::X_STAGE >> 4));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per swizzle row: UMMA_K = 8 (tf32)
+          const uint64_t da = da0 + oa + 2 * k, db = db0 + ob + 2 * k;
+          const uint32_t acc = (uint32_t)((uu != u) | (k != 0));
+          if constexpr (SPLIT) {
+            const uint64_t da_lo = da0_lo + oa + 2 * k, db_lo = db0_lo + ob + 2 * k;
+            tc::umma_u<true>(tmem, da_lo, db, idesc, acc);
+            tc::umma_u<true>(tmem, da, db_lo, idesc, 1u);
+            tc::umma_u<true>(tmem, da, db, idesc, 1u);
+          } else {
+            tc::umma_u<!F16>(tmem, da, db, idesc, acc);
+          }
         }
-        tc::tma_load_2d_hint(sX + stage * C::X_STAGE, &tm_x, kb * BK, 0, full_bar + 8 * stage, pol_x);
+        tc::umma_commit_u(empty_bar + 8 * stage);
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {  // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc = tc::umma_idesc(F16 ? 0u : 2u, WM, MB, 0, 0);
-      const uint32_t ready_bar = XF ? xf_bar : full_bar;
-      uint32_t stage = 0, phase = 0, tphase = 0;
-      bool ok = true;
-      int u = u0;
-      while (u < u1 && ok) {
-        const int nt = u / num_kb;
-        const int seg_end = min(u1, (nt + 1) * num_kb);
-        if (!tc::mbar_wait(tempty_bar, tphase ^ 1, guard)) break;  // the previous segment's accumulator has been read
-        tc::fence_after_sync();
-        for (int uu = u; uu < seg_end; ++uu) {
-          if (!tc::mbar_wait(ready_bar + 8 * stage, phase, guard)) { ok = false; break; }
-          tc::fence_after_sync();
-          const uint32_t a = sW + stage * W_STAGE, b = sX + stage * C::X_STAGE;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per swizzle row: UMMA_K = 8 (tf32)
-            const uint64_t da = tc::umma_desc_sw128(a + 32 * k, 16, 1024), db = tc::umma_desc_sw128(b + 32 * k, 16, 1024);
-            const uint32_t acc = (uint32_t)((uu != u) | (k != 0));
-            if constexpr (SPLIT) {
-              const uint64_t da_lo = tc::umma_desc_sw128(sWlo + stage * W_STAGE + 32 * k, 16, 1024);
-              const uint64_t db_lo = tc::umma_desc_sw128(sXlo + stage * C::X_STAGE + 32 * k, 16, 1024);
-              tc::umma<true>(tmem, da_lo, db, idesc, acc);
-              tc::umma<true>(tmem, da, db_lo, idesc, 1u);
-              tc::umma<true>(tmem, da, db, idesc, 1u);
-            } else {
-              tc::umma<!F16>(tmem, da, db, idesc, acc);
-            }
-          }
-          tc::umma_commit(empty_bar + 8 * stage);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-        }
-        if (ok) tc::umma_commit(tfull_bar);
-        tphase ^= 1;
-        u = seg_end;
-      }
+      if (ok) tc::umma_commit_u(tfull_bar);
+      tphase ^= 1;
+      u = seg_end;
     }
   } else {  // ---------------- warps 2..5: tile transform, then the segment's epilogue ----------------
     const int t = threadIdx.x - 64;  // 0..127

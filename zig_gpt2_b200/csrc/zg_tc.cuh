@@ -76,6 +76,10 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, Guard g
   if (mbar_try(bar, parity)) return true;
   return mbar_wait_slow(bar, parity, g);
 }
+// all 32 lanes wait; the verdict is made warp-uniform so that the *_u issue forms below stay convergent
+__device__ __forceinline__ bool mbar_wait_u(uint32_t bar, uint32_t parity, Guard g) {
+  return __all_sync(0xffffffffu, mbar_wait(bar, parity, g));
+}
 
 // ---- TMA ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *m) {
@@ -150,6 +154,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM: thread i of the warp writes lane (base_lane + i), columns [col, col + N)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- UMMA descriptors ---------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, 128-byte swizzle (the layout TMA writes with CU_TENSOR_MAP_SWIZZLE_128B into a
@@ -186,9 +211,73 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
         : "memory");
   }
 }
+// D[tmem] (+)= A[TMEM] . B[smem], kind::f16: the A operand (M = 128 rows = TMEM lanes, K-major, two f16 per 32-bit column)
+// is read from tensor memory -- the P matrix of flash attention never touches shared memory
+__device__ __forceinline__ void umma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrive once every tcgen05.mma issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// ---- warp-uniform issue ------------------------------------------------------------------------------------------
+// The single-thread instructions (tcgen05.mma, tcgen05.commit, TMA, arrive.expect_tx) take their operands from UNIFORM
+// registers.  Issued under `if (lane == 0)` the compiler sees divergent control flow, cannot keep descriptors in uniform
+// registers and wraps every such instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall: ~90 cycles per MMA
+// (measured: 755 cycles to issue the eight P V MMAs of one attention tile -- the tensor pipe starved by its own issuer).
+// The *_u forms below are called by ALL 32 lanes of the role's warp with warp-uniform arguments; the election and the
+// predication happen inside the asm block, so the surrounding address arithmetic stays on the uniform datapath.
+template <bool TF32>
+__device__ __forceinline__ void umma_u(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_ts_f16_u(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_u(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_u(uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_u(uint32_t dst, const CUtensorMap *m, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n\t}"
+      ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint_u(uint32_t dst, const CUtensorMap *m, int c0, int c1, uint32_t bar, uint64_t pol) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;\n\t}"
+      ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(bar), "l"(pol)
+      : "memory");
 }
 
 __device__ __forceinline__ bool elect_one() {
