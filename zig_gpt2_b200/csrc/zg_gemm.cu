@@ -316,7 +316,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                            l1 = __float_as_uint(__uint_as_float(x1) - __uint_as_float(h1)),
                            l2 = __float_as_uint(__uint_as_float(x2) - __uint_as_float(h2)),
                            l3 = __float_as_uint(__uint_as_float(x3) - __uint_as_float(h3));
+#if ZG_SPLIT_STORE_HI
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi[w] + 16 * i), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+#endif
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo[w] + 16 * i), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
           }
         }

@@ -189,7 +189,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
             if constexpr (SPLIT) {
               const float4 h = make_float4(__uint_as_float(__float_as_uint(x.x) & 0xffffe000u), __uint_as_float(__float_as_uint(x.y) & 0xffffe000u),
                                            __uint_as_float(__float_as_uint(x.z) & 0xffffe000u), __uint_as_float(__float_as_uint(x.w) & 0xffffe000u));
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(xs + 16 * i), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+              if (ZG_SPLIT_STORE_HI || g.xform == SK_XFORM_GELU)  // (the unmasked GELU value would do as well: same store)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(xs + 16 * i), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
               asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sXlo + stage * C::X_STAGE + 16 * i), "f"(x.x - h.x), "f"(x.y - h.y),
                            "f"(x.z - h.z), "f"(x.w - h.w) : "memory");
             } else {
@@ -206,7 +207,9 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
                              l1 = __float_as_uint(__uint_as_float(x1) - __uint_as_float(h1)),
                              l2 = __float_as_uint(__uint_as_float(x2) - __uint_as_float(h2)),
                              l3 = __float_as_uint(__uint_as_float(x3) - __uint_as_float(h3));
+#if ZG_SPLIT_STORE_HI
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ws + 16 * i), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+#endif
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sWlo + stage * W_STAGE + 16 * i), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
             }
           }
