@@ -30,12 +30,17 @@ enum { MODE_F16 = 0, MODE_TF32 = 1, MODE_TF32X3 = 2 };
 
 template <int MODE, int BN>
 struct Cfg {
-  static constexpr bool SPLIT = MODE == MODE_TF32X3;  // hi/lo operand copies: every stage holds two A and two B tiles
+  // 3xTF32: every stage holds the W tile twice in shared memory (as landed, and its lo part); the A tile's hi and lo
+  // parts live in TMEM (A_COLS columns per stage behind the two accumulators), so the MMAs read only W from shared memory
+  static constexpr bool SPLIT = MODE == MODE_TF32X3;
+  static_assert(!SPLIT || BN <= 128, "3xTF32: two accumulators + the A ring must fit 512 TMEM columns");
   static constexpr int B_STAGE = BN * ROW_BYTES;
-  static constexpr int STAGE = A_STAGE + B_STAGE;
-  static constexpr int STAGE_ALL = SPLIT ? 2 * STAGE : STAGE;
-  static constexpr int STAGES = (SMEM_BUDGET / STAGE_ALL) > 10 ? 10 : (SMEM_BUDGET / STAGE_ALL);
-  static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;  // two accumulator stages
+  static constexpr int STAGE = A_STAGE + B_STAGE;  // what TMA writes per stage
+  static constexpr int STAGE_ALL = SPLIT ? STAGE + B_STAGE : STAGE;
+  static constexpr int A_COLS = 64;  // SPLIT: A_hi in columns 0..31, A_lo in 32..63 (one 32-bit column per K element)
+  static constexpr int MAX_STAGES = SPLIT ? (512 - 2 * BN) / A_COLS : 10;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_ALL) > MAX_STAGES ? MAX_STAGES : (SMEM_BUDGET / STAGE_ALL);
+  static constexpr int TMEM_COLS = SPLIT ? 512 : ((2 * BN) < 32 ? 32 : 2 * BN);  // two accumulator stages (+ the A ring)
   // epilogue warps e and e+4 split the columns; in the 3xTF32 mode warps 6..9 split operands instead
   static constexpr int HALVES = (SPLIT || BN < 64) ? 1 : 2;
   static constexpr int COLS_PER_HALF = BN / HALVES;
@@ -188,9 +193,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs &g, float (&v)[32]
 
 // MODE_F16: fp16 operands, kind::f16.  MODE_TF32: fp32 operands read in place as kind::tf32 (the tensor core drops the
 // low 13 mantissa bits).  MODE_TF32X3: error-compensated fp32 -- warps 6..9 split every landed tile into
-// hi = x & 0xffffe000 (exactly representable in tf32) and lo = x - hi (exact in fp32), and the MMA warp accumulates
-// A_lo B_hi + A_hi B_lo + A_hi B_hi, which restores fp32-class accuracy (~2^-20 relative per product) on the tensor
-// cores.  Used by the batched decode step, which is HBM-bound, so the 3x MMA count is free.
+// hi = x & 0xffffe000 (what kind::tf32 reads out of the raw word anyway) and lo = x - hi (exact in fp32), and the MMA
+// warp accumulates A_lo B_hi + A_hi B_lo + A_hi B_hi, which restores fp32-class accuracy (~2^-20 relative per product)
+// on the tensor cores.  Twelve MMAs per k-block re-read their operands from shared memory, which made the mode
+// shared-memory-bound (ncu: tensor pipe 30 % busy); the A tile therefore goes to TMEM (tcgen05.st by the splitter
+// warps, raw words + lo parts) and the MMAs take A from there: half the operand reads, no A_lo copy in shared memory.
 template <int MODE, int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -204,7 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const uint32_t raw = tc::smem_addr(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t sA = base, sB = base + C::STAGES * A_STAGE;
-  const uint32_t sAlo = base + C::STAGES * C::STAGE, sBlo = sAlo + C::STAGES * A_STAGE;  // SPLIT only
+  const uint32_t sBlo = base + C::STAGES * C::STAGE;  // SPLIT only
   const uint32_t staging = base + C::STAGES * C::STAGE_ALL;  // 1024-byte aligned: every stage size is a multiple of 1024
   const uint32_t bars = staging + STAGING;
   const uint32_t full_bar = bars, empty_bar = bars + 8 * C::STAGES, split_bar = bars + 16 * C::STAGES;
@@ -262,7 +269,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const uint32_t ready_bar = SPLIT ? split_bar : full_bar;
     // descriptors differ only in the 14-bit start-address field (units of 16 bytes): built once, then an add per MMA
     const uint64_t da0 = tc::umma_desc_sw128(sA, 16, 1024), db0 = tc::umma_desc_sw128(sB, 16, 1024);
-    const uint64_t da0_lo = tc::umma_desc_sw128(SPLIT ? sAlo : sA, 16, 1024), db0_lo = tc::umma_desc_sw128(SPLIT ? sBlo : sB, 16, 1024);
+    const uint64_t db0_lo = tc::umma_desc_sw128(SPLIT ? sBlo : sB, 16, 1024);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     bool ok = true;
     for (int item = blockIdx.x; item < items && ok; item += gridDim.x) {
@@ -279,10 +286,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per swizzle row: UMMA_K = 8 (tf32) / 16 (f16)
           const uint64_t da = da0 + oa + 2 * k, db = db0 + ob + 2 * k;
           if constexpr (SPLIT) {
-            const uint64_t da_lo = da0_lo + oa + 2 * k, db_lo = db0_lo + ob + 2 * k;
-            tc::umma_u<true>(d, da_lo, db, idesc, (uint32_t)(((kb - kb0) | k) != 0));
-            tc::umma_u<true>(d, da, db_lo, idesc, 1u);
-            tc::umma_u<true>(d, da, db, idesc, 1u);
+            const uint64_t db_lo = db0_lo + ob + 2 * k;
+            const uint32_t ta = tmem + 2 * BN + stage * C::A_COLS + 8 * k;  // 8 K elements per MMA = 8 columns
+            tc::umma_ts_u<true>(d, ta + 32, db, idesc, (uint32_t)(((kb - kb0) | k) != 0));  // A_lo W_hi
+            tc::umma_ts_u<true>(d, ta, db_lo, idesc, 1u);                                   // A_hi W_lo
+            tc::umma_ts_u<true>(d, ta, db, idesc, 1u);                                      // A_hi W_hi
           } else {
             tc::umma_u<TF32>(d, da, db, idesc, (uint32_t)(((kb - kb0) | k) != 0));
           }
@@ -295,6 +303,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
   } else if (SPLIT && warp >= 6) {  // ---------------- operand splitters (3xTF32) ----------------
     const int t = threadIdx.x - 6 * 32;  // 0..127
+    const int a_row = (warp & 3) * 32 + lane;  // tcgen05.st: warp w may touch TMEM lanes 32 (w % 4) ..
+    const uint32_t a_lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t stage = 0, phase = 0;
     bool ok = true;
     for (int item = blockIdx.x; item < items && ok; item += gridDim.x) {
@@ -302,26 +312,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int kb0 = ks * num_kb / ksplit, kb1 = (ks + 1) * num_kb / ksplit;
       for (int kb = kb0; kb < kb1; ++kb) {
         if (!tc::mbar_wait(full_bar + 8 * stage, phase, guard)) { ok = false; break; }
-        const uint32_t hi[2] = {sA + stage * A_STAGE, sB + stage * C::B_STAGE};
-        const uint32_t lo[2] = {sAlo + stage * A_STAGE, sBlo + stage * C::B_STAGE};
-        const int chunks[2] = {A_STAGE / 16, C::B_STAGE / 16};
+        {  // A: this thread's tile row (TMEM lane) -> 32 raw words + 32 lo parts.  The row's 16-byte chunk c sits at
+           // c ^ (row % 8) (SWIZZLE_128B), so the eight rows of a quarter-warp hit eight different bank groups.
+          const uint32_t arow = sA + stage * A_STAGE + (uint32_t)a_row * 128u;
+          uint32_t x[32], lo[32];
 #pragma unroll
-        for (int w = 0; w < 2; ++w) {
+          for (int c = 0; c < 8; ++c)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x[4 * c]), "=r"(x[4 * c + 1]), "=r"(x[4 * c + 2]), "=r"(x[4 * c + 3])
+                         : "r"(arow + ((uint32_t)(c ^ (a_row & 7)) << 4)));
+#pragma unroll
+          for (int i = 0; i < 32; ++i) lo[i] = __float_as_uint(__uint_as_float(x[i]) - __uint_as_float(x[i] & 0xffffe000u));
+          const uint32_t ta = tmem + 2 * BN + a_lane_base + stage * C::A_COLS;
+          tc::tmem_st32(ta, x);
+          tc::tmem_st32(ta + 32, lo);
+        }
+        {  // W: lo part next to the landed tile (elementwise, so the swizzled placement is irrelevant)
+          const uint32_t hi = sB + stage * C::B_STAGE, lo = sBlo + stage * C::B_STAGE;
 #pragma unroll 4
-          for (int i = t; i < chunks[w]; i += 128) {  // elementwise, so the swizzled placement is irrelevant
+          for (int i = t; i < C::B_STAGE / 16; i += 128) {
             uint32_t x0, x1, x2, x3;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(hi[w] + 16 * i));
-            const uint32_t h0 = x0 & 0xffffe000u, h1 = x1 & 0xffffe000u, h2 = x2 & 0xffffe000u, h3 = x3 & 0xffffe000u;
-            const uint32_t l0 = __float_as_uint(__uint_as_float(x0) - __uint_as_float(h0)),
-                           l1 = __float_as_uint(__uint_as_float(x1) - __uint_as_float(h1)),
-                           l2 = __float_as_uint(__uint_as_float(x2) - __uint_as_float(h2)),
-                           l3 = __float_as_uint(__uint_as_float(x3) - __uint_as_float(h3));
-#if ZG_SPLIT_STORE_HI
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi[w] + 16 * i), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
-#endif
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo[w] + 16 * i), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(hi + 16 * i));
+            const uint32_t l0 = __float_as_uint(__uint_as_float(x0) - __uint_as_float(x0 & 0xffffe000u)),
+                           l1 = __float_as_uint(__uint_as_float(x1) - __uint_as_float(x1 & 0xffffe000u)),
+                           l2 = __float_as_uint(__uint_as_float(x2) - __uint_as_float(x2 & 0xffffe000u)),
+                           l3 = __float_as_uint(__uint_as_float(x3) - __uint_as_float(x3 & 0xffffe000u));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo + 16 * i), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
           }
         }
+        tc::tmem_st_wait();
+        tc::fence_before_sync();
         tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(split_bar + 8 * stage);
@@ -403,7 +422,11 @@ void launch_one(const GemmPlan &p) {
 template <int MODE>
 void launch_mode(const GemmPlan &p) {
   switch (p.bn) {
-    case 256: launch_one<MODE, 256>(p); break;
+    case 256:
+      if constexpr (MODE != MODE_TF32X3) {  // (gemm_plan never picks 256 columns for 3xTF32: no TMEM left for the A ring)
+        launch_one<MODE, 256>(p);
+        break;
+      }
     case 128: launch_one<MODE, 128>(p); break;
     case 64: launch_one<MODE, 64>(p); break;
     default: launch_one<MODE, 32>(p); break;
@@ -411,7 +434,8 @@ void launch_mode(const GemmPlan &p) {
 }
 template <int MODE>
 void set_attr_mode() {
-  set_attr<MODE, 256>(); set_attr<MODE, 128>(); set_attr<MODE, 64>(); set_attr<MODE, 32>();
+  if constexpr (MODE != MODE_TF32X3) set_attr<MODE, 256>();
+  set_attr<MODE, 128>(); set_attr<MODE, 64>(); set_attr<MODE, 32>();
 }
 
 unsigned *g_err_word = nullptr;
@@ -500,6 +524,7 @@ bool gemm_plan(GemmPlan *p, int mode, const void *A, size_t lda, const void *W, 
       // of 32 columns (two waves) lose to 75 tiles of 64.
       long best = -1;
       for (int cand : {256, 128, 64, 32}) {
+        if (cand > 128 && mode == MODE_TF32X3) continue;
         const int t = (args.N + cand - 1) / cand;
         const long cost = (long)((t + sms - 1) / sms) * (BM + cand);
         if (best < 0 || cost < best) { best = cost; bn = cand; }
@@ -509,6 +534,7 @@ bool gemm_plan(GemmPlan *p, int mode, const void *A, size_t lda, const void *W, 
       // accept a tile count a little under the SM count (144 tiles of 128 beat 288 of 64)
       const int need = mode == MODE_TF32X3 ? (sms * 9) / 10 : sms;
       for (int cand : {256, 128, 64}) {
+        if (cand > 128 && mode == MODE_TF32X3) continue;
         if (num_m * ((args.N + cand - 1) / cand) >= need) { bn = cand; break; }
       }
     }
@@ -523,6 +549,7 @@ bool gemm_plan(GemmPlan *p, int mode, const void *A, size_t lda, const void *W, 
       }
     }
   }
+  if (mode == MODE_TF32X3 && bn > 128) bn = 128;  // an explicit request for 256 columns: the 3xTF32 kernel has no such tile
   p->bn = bn;
   p->mode = mode;
   p->args = args;
