@@ -239,7 +239,7 @@ zg_batch *zg_batch_create(const zg_gpt *gpt, size_t n_seqs, size_t cache_rows, s
 void zg_batch_destroy(zg_batch *e);
 /* GPT.forward(seq_len, tokens[b], compute_logits) for every sequence b (tokens: HOST, n_seqs entries).  compute_logits:
  * 0 = none, 1 = logits (zg_batch_logits) and their argmax (zg_batch_read_tokens), 2 = argmax only -- fused into the
- * lm_head GEMM's epilogue when zg_batch_fused_argmax() is 1, so no logits are written (what generate / run_steps use). */
+ * lm_head GEMM's epilogue (zg_batch_fused_argmax() == 1), so no logits are written (what generate / run_steps use). */
 void zg_batch_forward(zg_batch *e, size_t seq_len, const size_t *tokens, int compute_logits);
 const float *zg_batch_logits(const zg_batch *e);      /* device, [n_seqs, pitch] */
 size_t zg_batch_logits_pitch(const zg_batch *e);      /* floats per row (vocab_size rounded up to 4) */
@@ -256,7 +256,7 @@ int zg_batch_generate_sample(zg_batch *e, const size_t *prompts, size_t n_inputs
 void zg_batch_set_position(zg_batch *e, size_t pos); /* next step attends to cache rows [0, pos] (timing at a given context) */
 void zg_batch_run_steps(zg_batch *e, size_t n_steps); /* n greedy steps from the current position, device resident, async */
 int zg_batch_storage_bits(const zg_batch *e); /* 32 (the reference's fp32 weights and caches) or 16 */
-int zg_batch_fused_argmax(const zg_batch *e); /* 1 when the decode step runs the stream-K GEMMs (n_seqs <= 128) and fuses the argmax */
+int zg_batch_fused_argmax(const zg_batch *e); /* 1: greedy steps carry the argmax in the lm_head epilogue (both GEMM kernels) */
 int zg_batch_read_tokens(zg_batch *e, size_t *out_tokens); /* argmax token of every sequence's last step (HOST, n_seqs ids); synchronises */
 const float *zg_batch_k_cache(const zg_batch *e, size_t layer); /* device, [n_seqs, cache_rows, n_embed] */
 const float *zg_batch_v_cache(const zg_batch *e, size_t layer);

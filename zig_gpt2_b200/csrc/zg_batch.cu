@@ -302,7 +302,7 @@ struct zg_batch {
   __half *h16 = nullptr, *att16 = nullptr, *h4_16 = nullptr;
   void *k_cache16 = nullptr, *v_cache16 = nullptr;
   SkinnyPlan sk_head_logits;  // lm_head into a zeroed logits buffer (compute_logits = 1)
-  GemmPlan dec_head, pre_head;
+  GemmPlan dec_head, dec_head_best, pre_head;
   std::vector<AttnPrefillPlan> pre_attn;
   int pre_T = -1;
   cudaGraphExec_t graph_sample = nullptr, graph_prompt = nullptr;
@@ -356,7 +356,9 @@ bool build_decode_plans(zg_batch *e) {
     if (!gemm_plan(&p.proj2, e->dec_mode, e->h4, 4 * E, w.proj2_w, a, 0)) return false;
   }
   GemmArgs a = base_args(B, V, E, nullptr, e->logits, e->Vp, 0);
-  return gemm_plan(&e->dec_head, e->dec_mode, e->h, E, e->wte, a, 0);
+  if (!gemm_plan(&e->dec_head, e->dec_mode, e->h, E, e->wte, a, 0)) return false;
+  a.best = e->best;  // greedy steps: the argmax rides in the lm_head's epilogue, no logits are written
+  return gemm_plan(&e->dec_head_best, e->dec_mode, e->h, E, e->wte, a, 0);
 }
 
 // Decode step with <= 128 sequences: every layer GEMM through the stream-K kernel.  c_attn reduces into a zeroed qkv
@@ -542,6 +544,10 @@ void enqueue_step(zg_batch *e, bool from_prompt, int n_inputs, int head) {
   } else if (head == 2 && e->skinny) {
     launch_ln_zero_rows<false>(e->x, e->h, e->lnf_g, e->lnf_b, E, B, reinterpret_cast<float *>(e->best), 4, s);  // main.zig:189; best := 0
     skinny_launch(e->sk_head);                                         // tied lm_head + argmax (main.zig:192-194)
+    skinny_finish_argmax(e->best, e->tok, e->hist, B, e->pos);
+  } else if (head == 2) {
+    launch_ln_zero_rows<false>(e->x, e->h, e->lnf_g, e->lnf_b, E, B, reinterpret_cast<float *>(e->best), 4, s);  // main.zig:189; best := 0
+    gemm_launch(e->dec_head_best);                                     // tied lm_head + argmax (main.zig:192-194)
     skinny_finish_argmax(e->best, e->tok, e->hist, B, e->pos);
   } else if (head) {
     launch_ln_rows<false>(e->x, E, e->h, e->lnf_g, e->lnf_b, E, B, s);  // main.zig:189
@@ -907,7 +913,7 @@ void zg_batch_run_steps(zg_batch *e, size_t n_steps) {
     }
   }
 }
-int zg_batch_fused_argmax(const zg_batch *e) { return e->skinny ? 1 : 0; }
+int zg_batch_fused_argmax(const zg_batch *e) { (void)e; return 1; }
 int zg_batch_storage_bits(const zg_batch *e) { return e->store16 ? 16 : 32; }
 // Set the common position (and so the attended length) directly: timing a step at T = 1024 needs no 1023 real steps.
 void zg_batch_set_position(zg_batch *e, size_t pos) {

@@ -360,6 +360,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         tc::fence_after_sync();
         const int row = m_blk * BM + quad * 32 + lane;
         et.row0 = m_blk * BM + quad * 32;
+        unsigned long long row_best = 0ull;  // fused argmax: this row's best over the tile's columns
 #pragma unroll 1
         for (int c = 0; c < C::COLS_PER_HALF; c += 32) {
           const int col_in_tile = half * C::COLS_PER_HALF + c;
@@ -367,13 +368,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           uint32_t r[32];
           tc::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + acc * BN + col_in_tile, r);
           tc::tmem_ld_wait();
-          if (col0 < g.N) {
+          if (col0 < g.N && g.best) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              if (col < g.N) {
+                const unsigned bits = __float_as_uint(__uint_as_float(r[j]) + (g.bias ? __ldg(g.bias + col) : 0.0f));
+                const unsigned key = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);  // order-preserving float -> uint
+                const unsigned long long cand = ((unsigned long long)key << 32) | (0xffffffffu - (unsigned)col);
+                row_best = cand > row_best ? cand : row_best;
+              }
+            }
+          } else if (col0 < g.N) {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             epilogue_chunk(g, v, row, col0, pos_now, et, lane, ks == 0);
           }
         }
+        if (g.best && row < g.M) atomicMax(g.best + 2 * row, row_best);
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(tempty_bar + 8 * acc);
@@ -512,7 +525,7 @@ bool gemm_plan(GemmPlan *p, int mode, const void *A, size_t lda, const void *W, 
   const int num_m = (args.M + BM - 1) / BM, num_kb = (args.K + bk - 1) / bk;
   // An in-place residual (x += Linear(h), main.zig:136-145) goes out as TMA reduce-adds, so its K range may be split
   // across work items: pick the widest tile whose (tiles x K slices) still occupy ~every SM with >= 6 k-blocks each.
-  const bool can_split = !g_disable_tma_out && !g_disable_split_k && bn == 0 && args.epi == TC_EPI_RESIDUAL &&
+  const bool can_split = !args.best && !g_disable_tma_out && !g_disable_split_k && bn == 0 && args.epi == TC_EPI_RESIDUAL &&
                          args.resid == args.out && args.ldr == args.ldo && !args.out_f16 &&
                          ((uintptr_t)args.out & 15) == 0 && ((size_t)args.ldo * 4) % 16 == 0;
   int ksplit = 1;
@@ -569,7 +582,7 @@ bool gemm_plan(GemmPlan *p, int mode, const void *A, size_t lda, const void *W, 
   const bool resid_inplace = g.epi == TC_EPI_RESIDUAL && g.resid == g.out && g.ldr == g.ldo && !g.out_f16;
   g.tma_out = g.tma_reduce = g.tma_kv = 0;
   p->tm_out = p->tm_a; p->tm_k = p->tm_a; p->tm_v = p->tm_a;  // valid placeholders
-  if (!g_disable_tma_out && ((uintptr_t)g.out & 15) == 0 && ((size_t)g.ldo * oes) % 16 == 0 &&
+  if (!g.best && !g_disable_tma_out && ((uintptr_t)g.out & 15) == 0 && ((size_t)g.ldo * oes) % 16 == 0 &&
       (g.epi != TC_EPI_RESIDUAL || resid_inplace)) {
     if (!make_tmap_2d(&p->tm_out, g.out, g.out_f16 ? 1 : 0, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldo * oes, 32, 32,
                       g.out_f16 ? 64 : 128))

@@ -35,6 +35,10 @@ struct GemmArgs {
   // work items; every slice reduce-adds its partial tile into `out` (which already holds the residual), slice 0 adds
   // the bias.  Lets a skinny GEMM (few output tiles, long K) occupy every SM with wide tiles.
   int ksplit = 1;
+  // fused greedy head (main.zig:192-194 + the caller's argmax): no output leaves the kernel; every tile raises its best
+  // (order-preserving logit bits << 32 | ~column) per row into best[2 * row] with one atomicMax.  The caller zeroes
+  // `best` before the launch and decodes it with skinny_finish_argmax.  First maximum wins ties, as in the reference.
+  unsigned long long *best = nullptr;
 };
 
 // A prepared launch: tensor maps are encoded once (start-up for the engines, per call for the op-level API).

@@ -42,8 +42,14 @@ __device__ __forceinline__ float gelu_sfu(float x) {
 template <bool SPLIT, int MB>
 struct SkCfg {
   static constexpr int X_STAGE = MB * ROW_BYTES;
-  static constexpr int STAGE = (W_STAGE + X_STAGE) * (SPLIT ? 2 : 1);
-  static constexpr int STAGES = (SK_SMEM_BUDGET / STAGE) > 10 ? 10 : (SK_SMEM_BUDGET / STAGE);
+  // 3xTF32: X twice in shared memory (as landed / GELU'd, and its lo part); the weight tile's raw words and lo parts go
+  // to TMEM (W_COLS columns per stage behind the accumulator) and are the MMAs' A operand from there, so shared memory
+  // carries each weight byte twice (TMA in, one read by the splitter) instead of five times
+  static constexpr int STAGE = W_STAGE + X_STAGE * (SPLIT ? 2 : 1);
+  static constexpr int W_COLS = 64;  // SPLIT: W_hi in columns 0..31, W_lo in 32..63 (one 32-bit column per K element)
+  static constexpr int MAX_STAGES = SPLIT ? (512 - MB) / W_COLS : 10;
+  static constexpr int STAGES = (SK_SMEM_BUDGET / STAGE) > MAX_STAGES ? MAX_STAGES : (SK_SMEM_BUDGET / STAGE);
+  static constexpr int TMEM_COLS = SPLIT ? 512 : MB;
   static constexpr int STAGING = 4 * 4096;  // one 32 x 32 fp32 epilogue chunk per transform/epilogue warp
   static constexpr int SMEM = STAGES * STAGE + STAGING + 1024 /*alignment slack*/ + 512 /*barriers*/;
 };
@@ -63,7 +69,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
   const uint32_t raw = tc::smem_addr(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t sW = base, sX = base + C::STAGES * W_STAGE;
-  const uint32_t sWlo = sX + C::STAGES * C::X_STAGE, sXlo = sWlo + C::STAGES * W_STAGE;  // SPLIT only
+  const uint32_t sXlo = sX + C::STAGES * C::X_STAGE;  // SPLIT only
   const uint32_t staging = base + C::STAGES * C::STAGE;
   const uint32_t bars = staging + C::STAGING;
   const uint32_t full_bar = bars, empty_bar = bars + 8 * C::STAGES, xf_bar = bars + 16 * C::STAGES;
@@ -87,7 +93,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
     tc::prefetch_tmap(&tm_x);
     if (g.tma_out) tc::prefetch_tmap(&tm_out);
   }
-  if (warp == 1) tc::tmem_alloc<MB>(slot);
+  if (warp == 1) tc::tmem_alloc<C::TMEM_COLS>(slot);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -131,7 +137,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
     const uint32_t ready_bar = XF ? xf_bar : full_bar;
     // descriptors differ only in the 14-bit start-address field (units of 16 bytes): built once, then an add per MMA
     const uint64_t da0 = tc::umma_desc_sw128(sW, 16, 1024), db0 = tc::umma_desc_sw128(sX, 16, 1024);
-    const uint64_t da0_lo = tc::umma_desc_sw128(SPLIT ? sWlo : sW, 16, 1024), db0_lo = tc::umma_desc_sw128(SPLIT ? sXlo : sX, 16, 1024);
+    const uint64_t db0_lo = tc::umma_desc_sw128(SPLIT ? sXlo : sX, 16, 1024);
     uint32_t stage = 0, phase = 0, tphase = 0;
     bool ok = true;
     int u = u0;
@@ -149,10 +155,11 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
           const uint64_t da = da0 + oa + 2 * k, db = db0 + ob + 2 * k;
           const uint32_t acc = (uint32_t)((uu != u) | (k != 0));
           if constexpr (SPLIT) {
-            const uint64_t da_lo = da0_lo + oa + 2 * k, db_lo = db0_lo + ob + 2 * k;
-            tc::umma_u<true>(tmem, da_lo, db, idesc, acc);
-            tc::umma_u<true>(tmem, da, db_lo, idesc, 1u);
-            tc::umma_u<true>(tmem, da, db, idesc, 1u);
+            const uint64_t db_lo = db0_lo + ob + 2 * k;
+            const uint32_t tw = tmem + MB + stage * C::W_COLS + 8 * k;  // 8 K elements per MMA = 8 columns
+            tc::umma_ts_u<true>(tmem, tw + 32, db, idesc, acc);  // W_lo X_hi
+            tc::umma_ts_u<true>(tmem, tw, db_lo, idesc, 1u);     // W_hi X_lo
+            tc::umma_ts_u<true>(tmem, tw, db, idesc, 1u);        // W_hi X_hi
           } else {
             tc::umma_u<!F16>(tmem, da, db, idesc, acc);
           }
@@ -189,7 +196,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
             if constexpr (SPLIT) {
               const float4 h = make_float4(__uint_as_float(__float_as_uint(x.x) & 0xffffe000u), __uint_as_float(__float_as_uint(x.y) & 0xffffe000u),
                                            __uint_as_float(__float_as_uint(x.z) & 0xffffe000u), __uint_as_float(__float_as_uint(x.w) & 0xffffe000u));
-              if (ZG_SPLIT_STORE_HI || g.xform == SK_XFORM_GELU)  // (the unmasked GELU value would do as well: same store)
+              if (g.xform == SK_XFORM_GELU)  // otherwise the landed word already is the hi operand (zg_tc.cuh)
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(xs + 16 * i), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
               asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sXlo + stage * C::X_STAGE + 16 * i), "f"(x.x - h.x), "f"(x.y - h.y),
                            "f"(x.z - h.z), "f"(x.w - h.w) : "memory");
@@ -198,20 +205,22 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
             }
           }
           if constexpr (SPLIT) {
-#pragma unroll 4
-            for (int i = t; i < W_STAGE / 16; i += 128) {
-              uint32_t x0, x1, x2, x3;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(ws + 16 * i));
-              const uint32_t h0 = x0 & 0xffffe000u, h1 = x1 & 0xffffe000u, h2 = x2 & 0xffffe000u, h3 = x3 & 0xffffe000u;
-              const uint32_t l0 = __float_as_uint(__uint_as_float(x0) - __uint_as_float(h0)),
-                             l1 = __float_as_uint(__uint_as_float(x1) - __uint_as_float(h1)),
-                             l2 = __float_as_uint(__uint_as_float(x2) - __uint_as_float(h2)),
-                             l3 = __float_as_uint(__uint_as_float(x3) - __uint_as_float(h3));
-#if ZG_SPLIT_STORE_HI
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ws + 16 * i), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
-#endif
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sWlo + stage * W_STAGE + 16 * i), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
-            }
+            // W: this thread's tile row (TMEM lane) -> 32 raw words + 32 lo parts.  The row's 16-byte chunk c sits at
+            // c ^ (row % 8) (SWIZZLE_128B), so the eight rows of a quarter-warp hit eight different bank groups.
+            const int w_row = quad * 32 + lane;
+            const uint32_t wrow = ws + (uint32_t)w_row * 128u;
+            uint32_t x[32], lo[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x[4 * c]), "=r"(x[4 * c + 1]), "=r"(x[4 * c + 2]), "=r"(x[4 * c + 3])
+                           : "r"(wrow + ((uint32_t)(c ^ (w_row & 7)) << 4)));
+#pragma unroll
+            for (int i = 0; i < 32; ++i) lo[i] = __float_as_uint(__uint_as_float(x[i]) - __uint_as_float(x[i] & 0xffffe000u));
+            const uint32_t tw = tmem + MB + ((uint32_t)(quad * 32) << 16) + stage * C::W_COLS;
+            tc::tmem_st32(tw, x);
+            tc::tmem_st32(tw + 32, lo);
+            tc::tmem_st_wait();
+            tc::fence_before_sync();
           }
           tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
           __syncwarp();
@@ -278,7 +287,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  if (warp == 1) tc::tmem_dealloc<MB>(tmem);
+  if (warp == 1) tc::tmem_dealloc<C::TMEM_COLS>(tmem);
 }
 
 template <bool SPLIT, int MB, bool XF, bool F16 = false>

@@ -225,12 +225,9 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// 3xTF32 operand split, x = hi + lo with hi = x & 0xffffe000.  kind::tf32 reads the fp32 word and ignores its low 13
-// mantissa bits, so the raw word already IS the hi operand: only lo is written (ZG_SPLIT_STORE_HI=1 stores the masked
-// word as well; tests/test_gpu_ops.py pins the 3xTF32 error bound either way).
-#ifndef ZG_SPLIT_STORE_HI
-#define ZG_SPLIT_STORE_HI 0
-#endif
+// 3xTF32 operand split, x = hi + lo with hi = x & 0xffffe000: kind::tf32 reads the fp32 word and ignores its low 13
+// mantissa bits, so the raw word already IS the hi operand and only lo = x - hi is ever written (measured: the GEMM
+// errors are bit-identical with and without storing the masked word; tests/test_gpu_batch.py pins the 3xTF32 bound).
 
 // ---- warp-uniform issue ------------------------------------------------------------------------------------------
 // The single-thread instructions (tcgen05.mma, tcgen05.commit, TMA, arrive.expect_tx) take their operands from UNIFORM
