@@ -242,9 +242,10 @@ def measure_cfg5(L, lib, rank: int, world: int, dist, trials: int = 3, small: bo
         L.zg_sync()
 
     out = {}
-    modes = ((True, "cfg5"), (False, "cfg5_reference_prompt_loop")) if both_prompt_modes else ((True, "cfg5"),)
-    for use_prefill, key in modes:
-        eng = BatchEngine(model, Bl, cache_rows=n_total, max_prompt=n_in)
+    modes = (((True, "cfg5", False), (False, "cfg5_reference_prompt_loop", False), (True, "cfg5_tf32", True))
+             if both_prompt_modes else ((True, "cfg5", False),))
+    for use_prefill, key, tf32 in modes:
+        eng = BatchEngine(model, Bl, cache_rows=n_total, max_prompt=n_in, tf32_single_pass=tf32)
         eng.generate_greedy(prompts, n_in + 8, use_prefill=use_prefill)  # warm-up (graph capture, clocks)
         sampler = ClockSampler(device_index)
         sampler.start()
@@ -270,7 +271,8 @@ def measure_cfg5(L, lib, rank: int, world: int, dist, trials: int = 3, small: bo
         out[key] = {
             "metric": "decode_tokens_per_sec", "value": S * n_new / sec, "unit": "tok/s", "n_gpus": world, "steps": n_new,
             "ms_per_step": sec * 1e3 / n_new, "higher_is_better": True, "scaling": "strong",
-            "dtype": "f32 storage, 3xTF32 tensor-core GEMMs" + (" (f16 prompt prefill)" if use_prefill else ""), "data": "synthetic",
+            "dtype": ("f32 storage, single-pass TF32 tensor-core GEMMs (tolerance class 2e-2, not token-exact)" if tf32 else
+                      "f32 storage, 3xTF32 tensor-core GEMMs") + (" (f16 prompt prefill)" if use_prefill else ""), "data": "synthetic",
             "config": {"workload": f"GPT-2 {size}, {S} independent synthetic sequences sharded over the GPUs, {n_in}-token prompts, "
                                    f"{n_new} greedy tokens each (BASELINE configs[4]); prompt "
                                    f"{'batched prefill' if use_prefill else 'token at a time (reference loop)'}",
