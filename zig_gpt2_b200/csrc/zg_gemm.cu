@@ -10,6 +10,7 @@
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).  The epilogue of tile i
 // overlaps the main loop of tile i+1.  kind::tf32 reads the fp32 tensors as they are; kind::f16 reads f16 copies.
 #include <initializer_list>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "zg_gemm.cuh"
@@ -401,6 +402,158 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (warp == 1) tc::tmem_dealloc<C::TMEM_COLS>(tmem);
 }
 
+// -------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) of the plain f16 / tf32 GEMM for wide problems: a cluster of two CTAs owns a
+// 256 x 256 output tile.  Each CTA loads its 128 rows of A and its 128 of the tile's 256 W rows (32 KB per stage instead
+// of 48: six stages), the leader's MMA warp issues one 256 x 256 x K-step MMA for the pair, and each CTA's epilogue
+// drains its own 128 accumulator rows exactly like the single-CTA kernel.  Barriers: `full` lives in the leader (one
+// arrive.expect_tx per producer, transaction bytes of both CTAs' TMA loads); `empty` and `tfull` are multicast commits
+// (every CTA waits on its own copy); `tempty` lives in the leader and collects both CTAs' epilogue warps.
+// -------------------------------------------------------------------------------------------------------------------
+constexpr int PAIR_BN = 256;
+constexpr int PAIR_B_STAGE = (PAIR_BN / 2) * ROW_BYTES;  // this CTA's half of the W tile
+constexpr int PAIR_STAGE = A_STAGE + PAIR_B_STAGE;
+constexpr int PAIR_STAGES = SMEM_BUDGET / PAIR_STAGE;
+constexpr int PAIR_SMEM = PAIR_STAGES * PAIR_STAGE + STAGING + 1024 + 384;
+
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_k,
+                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ GemmArgs g) {
+  static_assert(MODE != MODE_TF32X3, "the pair kernel has no operand splitters");
+  constexpr bool TF32 = MODE != MODE_F16;
+  constexpr int BN = PAIR_BN, BK = TF32 ? 32 : 64, HALVES = 2, COLS_PER_HALF = BN / HALVES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = tc::smem_addr(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sA = base, sB = base + PAIR_STAGES * A_STAGE;
+  const uint32_t staging = base + PAIR_STAGES * PAIR_STAGE;
+  const uint32_t bars = staging + STAGING;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * PAIR_STAGES;
+  const uint32_t tfull_bar = bars + 16 * PAIR_STAGES, tempty_bar = tfull_bar + 16;
+  const uint32_t slot = tempty_bar + 16, abort_flag = slot + 4;
+  uint32_t *slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (slot - raw));
+  const tc::Guard guard{g.err, abort_flag};
+  const uint32_t cr = tc::cluster_ctarank();  // 0 = leader
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PAIR_STAGES; ++s) {
+      tc::mbar_init(full_bar + 8 * s, 2);   // leader's copy is the one in use: one arrive.expect_tx per CTA
+      tc::mbar_init(empty_bar + 8 * s, 1);  // multicast commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      tc::mbar_init(tfull_bar + 8 * a, 1);                // multicast commit
+      tc::mbar_init(tempty_bar + 8 * a, 2 * 4 * HALVES);  // leader's copy: the epilogue warps of both CTAs
+    }
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(abort_flag), "r"(0u));
+    tc::fence_mbar_init();
+    tc::prefetch_tmap(&tm_a);
+    tc::prefetch_tmap(&tm_b);
+    if (g.tma_out) tc::prefetch_tmap(&tm_out);
+  }
+  if (warp == 1) tc::tmem_alloc2<512>(slot);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::cluster_sync();  // the peer's barriers are initialised before anything arrives on them
+  tc::fence_after_sync();
+  const uint32_t tmem = *slot_ptr;
+
+  const int num_m = (g.M + 2 * BM - 1) / (2 * BM), num_n = (g.N + BN - 1) / BN, tiles = num_m * num_n;
+  const int num_kb = (g.K + BK - 1) / BK;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const uint32_t lead_full = tc::mapa(full_bar, 0), lead_tempty = tc::mapa(tempty_bar, 0);
+
+  if (warp == 0) {  // ---------------- TMA producer (both CTAs) ----------------
+    uint32_t stage = 0, phase = 0;
+    bool ok = true;
+    for (int tile = pair; tile < tiles && ok; tile += npairs) {
+      const int m_blk = g.n_fastest ? tile / num_n : tile % num_m, n_blk = g.n_fastest ? tile % num_n : tile / num_m;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if (!tc::mbar_wait_u(empty_bar + 8 * stage, phase ^ 1, guard)) { ok = false; break; }
+        tc::mbar_expect_tx_cluster_u(lead_full + 8 * stage, PAIR_STAGE);
+        tc::tma_load_2d_pair_u(sA + stage * A_STAGE, &tm_a, kb * BK, m_blk * 2 * BM + (int)cr * BM, lead_full + 8 * stage);
+        tc::tma_load_2d_pair_u(sB + stage * PAIR_B_STAGE, &tm_b, kb * BK, n_blk * BN + (int)cr * (BN / 2), lead_full + 8 * stage);
+        if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {  // ---------------- MMA issuer (leader only) ----------------
+    if (cr == 0) {
+      constexpr uint32_t idesc = tc::umma_idesc(TF32 ? 2u : 0u, 2 * BM, BN, 0, 0);
+      const uint64_t da0 = tc::umma_desc_sw128(sA, 16, 1024), db0 = tc::umma_desc_sw128(sB, 16, 1024);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      bool ok = true;
+      for (int tile = pair; tile < tiles && ok; tile += npairs) {
+        if (!tc::mbar_wait_u(tempty_bar + 8 * acc, acc_phase ^ 1, guard)) break;
+        tc::fence_after_sync();
+        const uint32_t d = tmem + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (!tc::mbar_wait_u(full_bar + 8 * stage, phase, guard)) { ok = false; break; }
+          tc::fence_after_sync();
+          const uint64_t oa = (uint64_t)(stage * (A_STAGE >> 4)), ob = (uint64_t)(stage * (PAIR_B_STAGE >> 4));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc::umma2_u<TF32>(d, da0 + oa + 2 * k, db0 + ob + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+          tc::umma2_commit_both_u(empty_bar + 8 * stage);
+          if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (ok) tc::umma2_commit_both_u(tfull_bar + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {  // ---------------- epilogue warps (both CTAs): this CTA's 128 accumulator rows ----------------
+    const int e = warp - 2, quad = warp & 3, half = e >> 2;
+    uint32_t acc = 0, acc_phase = 0;
+    const int pos_now = g.pos_base + (g.pos_dev ? *g.pos_dev : 0);
+    EpiTma et{&tm_out, &tm_k, &tm_v, staging + (uint32_t)e * 4096u, 0};
+    for (int tile = pair; tile < tiles; tile += npairs) {
+      const int m_blk = g.n_fastest ? tile / num_n : tile % num_m, n_blk = g.n_fastest ? tile % num_n : tile / num_m;
+      if (!tc::mbar_wait(tfull_bar + 8 * acc, acc_phase, guard)) break;
+      tc::fence_after_sync();
+      const int row = m_blk * 2 * BM + (int)cr * BM + quad * 32 + lane;
+      et.row0 = m_blk * 2 * BM + (int)cr * BM + quad * 32;
+      unsigned long long row_best = 0ull;
+#pragma unroll 1
+      for (int c = 0; c < COLS_PER_HALF; c += 32) {
+        const int col_in_tile = half * COLS_PER_HALF + c;
+        const int col0 = n_blk * BN + col_in_tile;
+        uint32_t r[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + acc * BN + col_in_tile, r);
+        tc::tmem_ld_wait();
+        if (col0 < g.N && g.best) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col < g.N) {
+              const unsigned bits = __float_as_uint(__uint_as_float(r[j]) + (g.bias ? __ldg(g.bias + col) : 0.0f));
+              const unsigned key = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+              const unsigned long long cand = ((unsigned long long)key << 32) | (0xffffffffu - (unsigned)col);
+              row_best = cand > row_best ? cand : row_best;
+            }
+          }
+        } else if (col0 < g.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_chunk(g, v, row, col0, pos_now, et, lane, true);
+        }
+      }
+      if (g.best && row < g.M) atomicMax(g.best + 2 * row, row_best);
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_cluster(lead_tempty + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (g.tma_out && lane == 0) tc::tma_wait_all0();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::cluster_sync();  // nobody leaves (or frees TMEM) while the peer may still signal this CTA's barriers
+  tc::fence_after_sync();
+  if (warp == 1) tc::tmem_dealloc2<512>(tmem);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -433,7 +586,70 @@ void launch_one(const GemmPlan &p) {
 }
 
 template <int MODE>
+void set_attr_pair() {
+  static unsigned attr_gen = 0;
+  if (attr_gen != ctx().generation) {
+    ZG_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+    attr_gen = ctx().generation;
+  }
+}
+// how many CTA pairs the device runs at once (a persistent grid must not exceed it, or the excess pairs run as a second wave)
+template <int MODE>
+int max_pairs() {
+  static unsigned gen = 0;
+  static int n = 0;
+  if (gen != ctx().generation) {
+    set_attr_pair<MODE>();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (ctx().sm_count > 0 ? ctx().sm_count : 148));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = PAIR_SMEM;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, gemm_pair_kernel<MODE>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      clusters = 0;
+    }
+    n = clusters;
+    gen = ctx().generation;
+    if (getenv("ZG_DEBUG_PAIR")) fprintf(stderr, "zg: max active CTA pairs (mode %d) = %d\n", MODE, n);
+  }
+  return n;
+}
+
+template <int MODE>
+void launch_pair(const GemmPlan &p) {
+  set_attr_pair<MODE>();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = PAIR_SMEM;
+  cfg.stream = ctx().stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ZG_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<MODE>, p.tm_a, p.tm_b, p.tm_out, p.tm_k, p.tm_v, p.args));
+  ZG_LAUNCH_CHECK();
+}
+
+template <int MODE>
 void launch_mode(const GemmPlan &p) {
+  if constexpr (MODE != MODE_TF32X3) {
+    if (p.pair) {
+      launch_pair<MODE>(p);
+      return;
+    }
+  }
   switch (p.bn) {
     case 256:
       if constexpr (MODE != MODE_TF32X3) {  // (gemm_plan never picks 256 columns for 3xTF32: no TMEM left for the A ring)
@@ -447,7 +663,10 @@ void launch_mode(const GemmPlan &p) {
 }
 template <int MODE>
 void set_attr_mode() {
-  if constexpr (MODE != MODE_TF32X3) set_attr<MODE, 256>();
+  if constexpr (MODE != MODE_TF32X3) {
+    set_attr<MODE, 256>();
+    set_attr_pair<MODE>();
+  }
   set_attr<MODE, 128>(); set_attr<MODE, 64>(); set_attr<MODE, 32>();
 }
 
@@ -522,6 +741,7 @@ bool gemm_plan(GemmPlan *p, int mode, const void *A, size_t lda, const void *W, 
   static const bool env_no_split = getenv("ZG_NO_SPLIT_K") != nullptr;
   if (env_no_split) g_disable_split_k = true;
   const int sms = ctx().sm_count > 0 ? ctx().sm_count : 148;
+  const bool explicit_bn = bn != 0;
   const int num_m = (args.M + BM - 1) / BM, num_kb = (args.K + bk - 1) / bk;
   // An in-place residual (x += Linear(h), main.zig:136-145) goes out as TMA reduce-adds, so its K range may be split
   // across work items: pick the widest tile whose (tiles x K slices) still occupy ~every SM with >= 6 k-blocks each.
@@ -563,6 +783,10 @@ bool gemm_plan(GemmPlan *p, int mode, const void *A, size_t lda, const void *W, 
     }
   }
   if (mode == MODE_TF32X3 && bn > 128) bn = 128;  // an explicit request for 256 columns: the 3xTF32 kernel has no such tile
+  // wide problems: CTA pairs on 256 x 256 tiles (gemm_pair_kernel) when that still gives every pair a tile
+  static const bool env_no_pair = getenv("ZG_NO_PAIR") != nullptr;
+  const int pair_tiles = ((args.M + 2 * BM - 1) / (2 * BM)) * ((args.N + PAIR_BN - 1) / PAIR_BN);
+  p->pair = (!env_no_pair && !explicit_bn && mode != MODE_TF32X3 && bn == 256 && ksplit == 1 && pair_tiles >= sms / 2) ? 1 : 0;
   p->bn = bn;
   p->mode = mode;
   p->args = args;
@@ -570,8 +794,13 @@ bool gemm_plan(GemmPlan *p, int mode, const void *A, size_t lda, const void *W, 
   if (!p->args.err) p->args.err = gemm_error_word();
   const int tiles = ((args.M + BM - 1) / BM) * ((args.N + bn - 1) / bn) * ksplit;
   p->grid = tiles < sms ? tiles : sms;
+  if (p->pair) {
+    const int mp = mode == MODE_F16 ? max_pairs<MODE_F16>() : max_pairs<MODE_TF32>();
+    if (mp <= 0) p->pair = 0;
+    else p->grid = 2 * (pair_tiles < mp ? pair_tiles : mp);
+  }
   if (!make_tmap_2d(&p->tm_a, A, tf32 ? 0 : 1, (uint64_t)args.M, (uint64_t)args.K, lda * es, BM, bk)) return false;
-  if (!make_tmap_2d(&p->tm_b, W, tf32 ? 0 : 1, (uint64_t)args.N, (uint64_t)args.K, (uint64_t)args.K * es, bn, bk)) return false;
+  if (!make_tmap_2d(&p->tm_b, W, tf32 ? 0 : 1, (uint64_t)args.N, (uint64_t)args.K, (uint64_t)args.K * es, p->pair ? bn / 2 : bn, bk)) return false;
   // Epilogue through TMA stores when the output is addressable by a tensor map; a residual that aliases the output
   // (x += ..., main.zig:136-145) becomes a TMA reduce-add so the kernel never reads it.
   GemmArgs &g = p->args;

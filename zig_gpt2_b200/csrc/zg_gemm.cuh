@@ -48,6 +48,7 @@ struct GemmPlan {
   int bn = 256;
   int mode = 1;  // 0 = fp16 operands, 1 = fp32 operands as tf32, 2 = fp32 operands, 3xTF32 error-compensated
   int grid = 0;
+  int pair = 0;  // 1: CTA pairs on 256 x 256 tiles (cta_group::2), grid = 2 x pairs launched as clusters of two
 };
 
 // A: [M, K] row-major with pitch lda elements; W: [N, K] row-major (the reference's Linear.weight layout, ops.zig:9).
