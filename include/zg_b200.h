@@ -105,6 +105,7 @@ void zg_linear_argmax_skinny(const zg_linear *self, const float *inputs, size_t 
                              unsigned long long *best_scratch, size_t *tokens_dev);
 void zg_to_f16(const float *src, void *dst_f16, size_t n); /* fp32 -> f16 round-to-nearest-even copy (start-up) */
 void zg_tc_set_direct_epilogue(int on); /* test hook: 1 = per-row direct stores instead of the staged TMA-store epilogue */
+unsigned long long zg_tc_pair_launch_count(void); /* launches of the CTA-pair (cta_group::2) GEMM so far: tests assert the path they cover */
 int zg_tc_error(void); /* watchdog word of the tensor-core kernels (0 = clean); synchronises */
 
 typedef struct { size_t emb_dim; const float *weight; } zg_embedding; /* ops.zig:49-57 */

@@ -65,6 +65,46 @@ def test_linear_tensor_core_matches_oracle(L, M, N, K, precision, tol):
     assert e <= tol, f"precision {precision}: {e:.3e} > {tol}"
 
 
+@pytest.mark.parametrize("precision", [1, 0])
+@pytest.mark.parametrize("M,N,K,epi", [(2000, 2500, 200, 0), (2048, 2560, 1024, 1), (2304, 2304, 136, 2), (16384, 1024, 256, 2)])
+def test_linear_cta_pair_kernel_exact_on_representable_operands(L, M, N, K, epi, precision):
+    """Wide problems run on CTA pairs (cta_group::2: 256 x 256 tiles, each CTA holds half of the W tile).  Operands that
+    are exactly representable in the tensor-core input format (f16 / tf32) make the products exact, so the result must
+    match float64 numpy to fp32 accumulation error -- for ragged M, N and K (TMA zero fill, clipped stores), the GELU and
+    the in-place residual (TMA reduce-add) epilogues.  The launch counter proves the pair kernel is what ran."""
+    from zig_gpt2_b200 import lib
+    from zig_gpt2_b200.lib import DeviceBuffer, ZgLinear
+
+    rs = np.random.RandomState(M + N + K + epi)
+    x = rs.randn(M, K).astype(np.float32)
+    w = (rs.randn(N, K) * 0.05).astype(np.float32)
+    b, r = rs.randn(N).astype(np.float32), rs.randn(M, N).astype(np.float32)
+    if precision == 1:
+        x, w = x.astype(np.float16).astype(np.float32), w.astype(np.float16).astype(np.float32)
+    else:
+        x, w = ((a.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32) for a in (x, w))
+    want = x.astype(np.float64) @ w.astype(np.float64).T + b
+    if epi == 1:
+        want = 0.5 * want * (1.0 + np.tanh(want * 0.7978845608028654 * (1.0 + 0.044715 * want * want)))
+    if epi == 2:
+        want = want + r
+    dx, dw, db = DeviceBuffer.from_numpy(x), DeviceBuffer.from_numpy(w), DeviceBuffer.from_numpy(b)
+    out = DeviceBuffer.from_numpy(r) if epi == 2 else DeviceBuffer(M * N)
+    lin = ZgLinear(K, N, dw.ptr, db.ptr)
+    xin, lowp = dx.ptr, None
+    if precision == 1:
+        x16, w16 = DeviceBuffer(M * K, np.uint16), DeviceBuffer(N * K, np.uint16)
+        L.zg_to_f16(dx.ptr, x16.ptr, M * K)
+        L.zg_to_f16(dw.ptr, w16.ptr, N * K)
+        xin, lowp = x16.ptr, w16.ptr
+    n0 = L.zg_tc_pair_launch_count()
+    L.zg_linear_forward_tc(C.byref(lin), xin, M * K, out.ptr, precision, lowp, epi, out.ptr if epi == 2 else None, 0)
+    lib.check()
+    assert L.zg_tc_error() == 0
+    assert L.zg_tc_pair_launch_count() == n0 + 1, "the CTA-pair kernel did not run"
+    assert rel(out.download().reshape(M, N), want) <= 2e-5
+
+
 def test_linear_forward_routes_large_m_to_tensor_cores(L):
     """The reference's own Linear test shape (tests.zig:22-78: x[3,768], W[3072,768]) scaled to M = 48, through the
     reference-facing zg_linear_forward (ops.Linear.forward)."""

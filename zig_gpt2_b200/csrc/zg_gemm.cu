@@ -410,6 +410,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 // arrive.expect_tx per producer, transaction bytes of both CTAs' TMA loads); `empty` and `tfull` are multicast commits
 // (every CTA waits on its own copy); `tempty` lives in the leader and collects both CTAs' epilogue warps.
 // -------------------------------------------------------------------------------------------------------------------
+unsigned long long g_pair_launches = 0;  // launches of the CTA-pair kernel (tests assert the path they mean to cover)
 constexpr int PAIR_BN = 256;
 constexpr int PAIR_B_STAGE = (PAIR_BN / 2) * ROW_BYTES;  // this CTA's half of the W tile
 constexpr int PAIR_STAGE = A_STAGE + PAIR_B_STAGE;
@@ -640,6 +641,7 @@ void launch_pair(const GemmPlan &p) {
   cfg.numAttrs = 1;
   ZG_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<MODE>, p.tm_a, p.tm_b, p.tm_out, p.tm_k, p.tm_v, p.args));
   ZG_LAUNCH_CHECK();
+  g_pair_launches++;
 }
 
 template <int MODE>
@@ -895,6 +897,7 @@ void zg_to_f16(const float *src, void *dst_f16, size_t n) {
   ZG_LAUNCH_CHECK();
 }
 
+unsigned long long zg_tc_pair_launch_count(void) { return g_pair_launches; }
 void zg_tc_set_direct_epilogue(int on) { g_disable_tma_out = on != 0; }  // test hook (per-op parity of both epilogues)
 
 int zg_tc_error(void) {  // watchdog word of the tensor-core kernels; 0 when clean (synchronises)

@@ -70,7 +70,7 @@ SIGNATURES = {
     "zg_linear_forward_tc": (V, [C.POINTER(ZgLinear), P, Z, P, I, P, I, P, I]),
     "zg_linear_forward_skinny": (V, [C.POINTER(ZgLinear), P, Z, P, I, I, P]),
     "zg_linear_argmax_skinny": (V, [C.POINTER(ZgLinear), P, Z, I, P, P]),
-    "zg_to_f16": (V, [P, P, Z]), "zg_tc_error": (I, []), "zg_tc_set_direct_epilogue": (V, [I]),
+    "zg_to_f16": (V, [P, P, Z]), "zg_tc_error": (I, []), "zg_tc_pair_launch_count": (C.c_ulonglong, []), "zg_tc_set_direct_epilogue": (V, [I]),
     "zg_embedding_forward": (V, [C.POINTER(ZgEmbedding), c_size_p, Z, P]),
     "zg_layer_norm_forward": (V, [C.POINTER(ZgLayerNorm), P, Z]),
     "zg_attention_forward": (V, [C.POINTER(ZgAttention), Z] + [P] * 9),
