@@ -446,7 +446,7 @@ attn_prefill_kernel_v2(const __grid_constant__ CUtensorMap tm_qkv, __half *__res
       if (j == 0) {
         float mx = (diag ? half_row_max<true>(tS + lane_base, r, 64 * hf) : half_row_max<false>(tS + lane_base, r, 64 * hf)) * scale2;
         xb[hf * QT + r] = mx;
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight softmax warps
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");  // the two warps that share these 32 rows
         m_ref = fmaxf(mx, xb[(hf ^ 1) * QT + r]);
       } else if (__any_sync(0xffffffffu, pending)) {
         const float alpha = pending ? fast_exp2(m_ref - m_next) : 1.0f;
@@ -460,7 +460,7 @@ attn_prefill_kernel_v2(const __grid_constant__ CUtensorMap tm_qkv, __half *__res
                        : half_row_exp<false>(tS + lane_base, tP + lane_base, r, 64 * hf, scale2, m_ref, tmax);
       if (j > 0) {
         xb[hf * QT + r] = tmax;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
         const float rise = fmaxf(tmax, xb[(hf ^ 1) * QT + r]);  // of the whole row, relative to m_ref
         const bool redo = rise > 15.0f;
         if (__any_sync(0xffffffffu, redo)) {  // P would overflow f16: move the reference now and recompute (rare)
@@ -483,7 +483,7 @@ attn_prefill_kernel_v2(const __grid_constant__ CUtensorMap tm_qkv, __half *__res
     // total row sum = the two halves' partial sums (same reference maximum)
     float *xb = rowx + ((n_kv & 1) * 2 * QT);
     xb[hf * QT + r] = l;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
     l += xb[(hf ^ 1) * QT + r];
     if (ok && tc::mbar_wait(pv_full, 0, guard)) {
       tc::fence_after_sync();
