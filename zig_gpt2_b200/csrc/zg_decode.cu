@@ -37,6 +37,7 @@
 //   * the layer table lives in __constant__ memory, so no phase starts with a dependent global load;
 //   * the token loop of generate() runs inside the kernel; each token is written to device memory and to a
 //     pinned host ring, so the host only waits once per call.
+#include <chrono>
 #include <cooperative_groups.h>
 #include <stdlib.h>
 #include <string.h>
@@ -98,6 +99,8 @@ struct DecodeParams {
   u64 *tokens;                 // device [C]: token forwarded/sampled at every step
   volatile u64 *tokens_host;   // pinned host ring [C]
   u64 *last_token;             // device: argmax of the last logits computed
+  volatile u64 *result_host;   // pinned host {token, sequence number}: GPT.sample's answer without a copy + synchronise
+  u64 result_seq;
   int first_step, n_steps;
   int force_logits;  // compute logits + argmax on every step (GPT.forward(compute_logits=true) on a prompt step)
   int store_logits;  // also write the logits vector to global memory
@@ -1120,7 +1123,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_persistent_kernel(const De
         }
         consumer_sync();
         const u64 amax = (u64)__float_as_uint(sm.red[RED_TOK]);
-        if (cta == 0 && tid == 0) *p.last_token = amax;
+        if (cta == 0 && tid == 0) {
+          *p.last_token = amax;
+          if (p.result_host && step == last_step) {  // the host spins on the sequence number (zg_engine_sample_greedy)
+            p.result_host[0] = amax;
+            __threadfence_system();
+            p.result_host[1] = p.result_seq;
+          }
+        }
         if (step >= p.n_prompt) out_tok = amax;  // generate(): main.zig:335-338
         consumer_sync();
       }
@@ -1220,6 +1230,8 @@ struct zg_engine {
   u64 *tokens_host;  // pinned, mapped
   u64 *tokens_host_devptr;
   u64 *last_token_dev;
+  u64 result_seq;   // sequence number of the last zg_engine_sample_greedy answer (pinned slot tokens_host[C .. C+1])
+  int sample_slot;  // zg_engine_forward is being called by zg_engine_sample_greedy
   u64 *prof_dev;
   unsigned *err_dev;
   void *samp_dev;  // {temp, seed, sequence} of the sampling generate loop (zg_engine_generate_sample)
@@ -1332,14 +1344,14 @@ zg_engine *zg_engine_create(const zg_gpt *gpt, const zg_state *state) {
   e->prof_dev = (u64 *)zg_alloc((2 * PROF_MAX + 4) * 8);
   e->err_dev = (unsigned *)zg_alloc(256);
   e->samp_dev = zg_alloc(64);
-  ZG_CUDA(cudaHostAlloc(&e->tokens_host, C * 8, cudaHostAllocMapped));
+  ZG_CUDA(cudaHostAlloc(&e->tokens_host, (C + 2) * 8, cudaHostAllocMapped));  // + {token, sequence number} of GPT.sample
   note_alloc();
   ZG_CUDA(cudaHostGetDevicePointer((void **)&e->tokens_host_devptr, e->tokens_host, 0));
   if (zg_last_error()) {
     free(e);
     return nullptr;
   }
-  memset(e->tokens_host, 0xff, C * 8);
+  memset(e->tokens_host, 0xff, (C + 2) * 8);
   zg_memset(e->exchange_dev, 0, n_exchange * 8);  // epoch 0 everywhere; the first phase of the first launch is epoch 1
   zg_memset(e->err_dev, 0, 256);
   zg_memset(e->tokens_dev, 0, C * 8);
@@ -1442,18 +1454,36 @@ void zg_engine_forward(zg_engine *e, size_t seq_len, size_t token, int compute_l
   p.force_logits = compute_logits ? 1 : 0;
   p.store_logits = compute_logits ? 1 : 0;
   p.write_xout = 1;
+  if (e->sample_slot) {
+    p.result_host = e->tokens_host_devptr + e->cfg.context_size;
+    p.result_seq = e->result_seq;
+  }
   engine_launch(e, p);
 }
 
+// GPT.sample with temp -> 0 (main.zig:198-207): host token in, host token out.  The kernel writes {token, sequence number}
+// into pinned host memory and the host spins on the sequence number: no copy, no stream synchronise on the per-token
+// path (~10 us of a 150 us step).  If the answer does not show up the slow path synchronises and reads the watchdog.
 size_t zg_engine_sample_greedy(zg_engine *e, size_t seq_len, size_t token) {
   if (!require_ready("zg_engine_sample_greedy")) return (size_t)-1;
   Context &c = ctx();
+  const size_t C = e->cfg.context_size;
+  volatile u64 *slot = e->tokens_host + C;
+  e->result_seq = (e->result_seq + 1) & 0x7fffffffffffffffull;  // never the 0xff.. fill pattern
+  e->sample_slot = 1;
   zg_engine_forward(e, seq_len, token, 1);
+  e->sample_slot = 0;
   if (zg_last_error()) return (size_t)-1;
-  ZG_CUDA(cudaMemcpyAsync(c.token_slot_host, e->last_token_dev, 8, cudaMemcpyDeviceToHost, c.stream));
-  ZG_CUDA(cudaStreamSynchronize(c.stream));
-  if (engine_check_watchdog(e)) return (size_t)-1;
-  return (size_t)c.token_slot_host[0];
+  const auto t0 = std::chrono::steady_clock::now();
+  for (unsigned spins = 0; slot[1] != e->result_seq; ++spins) {
+    __builtin_ia32_pause();
+    if ((spins & 0xffffu) == 0xffffu && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(3)) break;
+  }
+  if (slot[1] != e->result_seq) {  // slow path: the launch failed or the watchdog fired
+    ZG_CUDA(cudaStreamSynchronize(c.stream));
+    if (engine_check_watchdog(e) || slot[1] != e->result_seq) return (size_t)-1;
+  }
+  return (size_t)slot[0];
 }
 
 size_t zg_engine_sample(zg_engine *e, size_t seq_len, float temp, size_t token, double u) {
