@@ -11,6 +11,8 @@ layers; stated per test); TF32 / fp16 tensor-core paths <= 2e-2 on logits; greed
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 import pytest
 
@@ -359,6 +361,53 @@ def test_batch_prefill_matches_oracle(small_model):
     agree = float((got == toks).mean())
     assert agree >= 0.8, agree  # fp16 prompt pass: tokens may legitimately flip where the top-2 margin is < 2e-2
     eng.close()
+
+
+_PAIR_PREFILL = r'''
+import numpy as np, sys
+sys.path.insert(0, ".")
+from zig_gpt2_b200 import gpt, lib
+from zig_gpt2_b200.batch import BatchEngine
+from zig_gpt2_b200.config import GPTConfig
+from zig_gpt2_b200.weights import synth_weights
+L = lib.init(0)
+cfg = GPTConfig(vocab_size=4099, context_size=1024, n_layer=2, n_heads=12, n_embed=768)
+model = gpt.gpt_from_numpy(cfg, synth_weights(cfg, seed=5))
+B, T = 8, 1024
+prompts = np.random.RandomState(3).randint(0, cfg.vocab_size, (B, T))
+eng = BatchEngine(model, B, cache_rows=T, max_prompt=T)
+n0 = L.zg_tc_pair_launch_count()
+eng.prefill(prompts, True)
+lib.check()
+k, v = eng.kv(cfg.n_layer - 1, T)
+np.savez(sys.argv[1], logits=eng.logits(), k=k, v=v, pair_launches=int(L.zg_tc_pair_launch_count() - n0))
+print("prefill ok")
+'''
+
+
+def test_prefill_cta_pair_gemms_equal_single_cta_gemms():
+    """The f16 prefill at 8 x 1024 rows runs its GEMMs on CTA pairs (c_attn with the fused K/V cache append, c_fc + GELU,
+    the two in-place residual projections); ZG_NO_PAIR=1 runs the same plans on the single-CTA kernel.  Both accumulate
+    every output element over K in the same order, so the last layer's caches and the logits must agree to fp32 rounding
+    of the reduce-add epilogue (<= 1e-5), and the launch counter says which kernel ran."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for tag, env in (("pair", {}), ("single", {"ZG_NO_PAIR": "1"})):
+        out = os.path.join(root, "gpurun_out", f"_prefill_{tag}.npz")
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        r = subprocess.run([sys.executable, "-c", _PAIR_PREFILL, out], cwd=root, capture_output=True, text=True, timeout=600,
+                           env={**os.environ, **env})
+        assert r.returncode == 0 and "prefill ok" in r.stdout, r.stderr[-1500:]
+        outs.append(dict(np.load(out)))
+        os.remove(out)
+    a, b = outs
+    assert int(a["pair_launches"]) >= 8 and int(b["pair_launches"]) == 0
+    assert np.isfinite(a["logits"]).all()
+    for key in ("logits", "k", "v"):
+        assert rel(a[key], b[key]) <= 1e-5, key
 
 
 def test_batch_engine_124m_64_greedy_tokens_identical(weights_124m):
