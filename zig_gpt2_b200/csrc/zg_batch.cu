@@ -183,6 +183,20 @@ void launch_ln_zero_rows(const float *in, void *out, const float *g, const float
   ZG_LAUNCH_CHECK();
 }
 
+// pre := gelu(pre) in place (main.zig:80), exact tanhf GELU (ops.zig:225): the stream-K decode step applies it here, once
+// per element, instead of in mlp c_proj's operand load -- there every weight tile re-applies it to the X chunk it
+// multiplies (12.5x redundant at 1.5B), and the single-pass TF32 kernel needs its transform warps only for that.
+// cfg 4: 8.39 -> 8.18 ms (TF32), 8.94 -> 8.78 ms (3xTF32).
+__global__ void __launch_bounds__(256) gelu_inplace_kernel(float *__restrict__ pre, size_t n4) {
+  pdl_trigger();
+  pdl_wait();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<float4 *>(pre)[i];
+    v.x = gelu_ref(v.x); v.y = gelu_ref(v.y); v.z = gelu_ref(v.z); v.w = gelu_ref(v.w);
+    reinterpret_cast<float4 *>(pre)[i] = v;
+  }
+}
+
 // h16 = f16(gelu(pre)): the GELU between c_fc and mlp c_proj (main.zig:80) of the 16-bit decode step, where c_proj's f16
 // operand cannot be produced by c_fc's epilogue (stream-K partial sums).  Exact tanhf GELU (ops.zig:225).
 __global__ void __launch_bounds__(256) gelu_to_f16_kernel(const float *__restrict__ pre, __half *__restrict__ out, size_t n4) {
@@ -391,6 +405,12 @@ bool build_skinny_plans16(zg_batch *e) {
   return skinny_plan(&e->sk_head_logits, 0, e->h16, E, e->wte16, a);
 }
 
+static bool gelu_separate(const zg_batch *e) {  // ZG_GELU_FUSED=1: A/B switch back to the operand-load GELU
+  static const bool fused = getenv("ZG_GELU_FUSED") != nullptr;
+  (void)e;
+  return !fused;
+}
+
 bool build_skinny_plans(zg_batch *e) {
   if (e->store16) return build_skinny_plans16(e);
   const int B = e->B, E = (int)e->cfg.n_embed;
@@ -408,7 +428,8 @@ bool build_skinny_plans(zg_batch *e) {
     a.M = B; a.N = 4 * E; a.K = E; a.bias = w.fc_b; a.out = e->h4; a.ldo = 4 * E;
     if (!skinny_plan(&p.fc, e->dec_mode, e->h, E, w.fc_w, a)) return false;
     a = SkinnyArgs();
-    a.M = B; a.N = E; a.K = 4 * E; a.bias = w.proj2_b; a.out = e->x; a.ldo = E; a.xform = SK_XFORM_GELU;
+    // the GELU is a separate in-place pass over h4 (gelu_inplace_kernel); SK_XFORM_GELU in the operand load is the A/B form
+    a.M = B; a.N = E; a.K = 4 * E; a.bias = w.proj2_b; a.out = e->x; a.ldo = E; a.xform = gelu_separate(e) ? 0 : SK_XFORM_GELU;
     if (!skinny_plan(&p.proj2, e->dec_mode, e->h4, 4 * E, w.proj2_w, a)) return false;
   }
   SkinnyArgs a;
@@ -521,6 +542,10 @@ void enqueue_step(zg_batch *e, bool from_prompt, int n_inputs, int head) {
     skinny_launch(p.proj);                                                       // x += c_proj(att) (ops.zig:172, main.zig:136-139)
     launch_ln_zero_rows<false>(e->x, e->h, w.ln2_g, w.ln2_b, E, B, e->h4, 4 * E, s);    // main.zig:140; h4 := 0
     skinny_launch(p.fc);                                                         // c_fc pre-activation (main.zig:79)
+    if (gelu_separate(e)) {
+      ZG_CUDA(launch_pdl(PDL_LN_DEP, gelu_inplace_kernel, dim3(2 * ctx().sm_count), dim3(256), 0, s, e->h4, (size_t)B * E));  // B * 4E / 4
+      ZG_LAUNCH_CHECK();
+    }
     skinny_launch(p.proj2);                                                      // x += c_proj(gelu(.)) (main.zig:80-81,142-145)
   }
   for (size_t l = 0; !e->skinny && l < e->layers.size(); ++l) {
