@@ -552,7 +552,7 @@ __device__ __forceinline__ void st_out(__half *p, float v) { *p = __float2half_r
 // CT: cache element type; OT: output element type (f16 when the c_proj GEMM that follows reads f16 operands)
 template <typename CT, typename OT>
 __global__ void __launch_bounds__(DEC_WARPS * 32)
-attn_decode_batch_kernel(const float *__restrict__ q, int ldq, const CT *k_cache, const CT *v_cache, long long seq_stride, int E, OT *__restrict__ out, int ldo,
+attn_decode_batch_kernel(const float *q, int ldq, const CT *k_cache, const CT *v_cache, long long seq_stride, int E, OT *out, int ldo,
                          const int *pos_dev, int pos_base, const float *knew, const float *vnew, int trigger,
                          int rows_per_seq) {
   __shared__ float s_m[DEC_WARPS], s_l[DEC_WARPS];

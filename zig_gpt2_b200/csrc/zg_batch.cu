@@ -118,16 +118,18 @@ void launch_ln_rows(const float *in, size_t in_stride, void *out, const float *g
 // warp ~2,000 dependent instructions (the one-warp-per-row kernel took 11-12 us per call at E = 1600).
 constexpr int LNZ_THREADS = 128;
 template <int LN_MAXV, bool OUT_F16>  // float4 per thread: n_embed <= 4 * LNZ_THREADS * LN_MAXV
-__global__ void __launch_bounds__(LNZ_THREADS) ln_zero_rows_kernel(const float *__restrict__ in, void *__restrict__ out,
+// (`in` is NOT __restrict__: see the PDL note in zg_common.cuh -- a const __restrict__ load may be hoisted above pdl_wait)
+__global__ void __launch_bounds__(LNZ_THREADS) ln_zero_rows_kernel(const float *in, void *__restrict__ out,
                                                                    const float *__restrict__ g, const float *__restrict__ b,
                                                                    int E, float eps, float *__restrict__ zero, int zero_n,
                                                                    int trigger) {
   __shared__ float red[2][LNZ_THREADS / 32];
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (trigger) pdl_trigger();
+  const int nv = E >> 2;
+  const float4 *g4 = reinterpret_cast<const float4 *>(g), *b4 = reinterpret_cast<const float4 *>(b);
   pdl_wait();  // x is the previous GEMM's output; the buffer zeroed below may still be read by it
   const float4 *src = reinterpret_cast<const float4 *>(in + (size_t)row * E);
-  const int nv = E >> 2;
   float4 v[LN_MAXV];
   float s = 0.0f, ss = 0.0f;
 #pragma unroll
@@ -151,7 +153,6 @@ __global__ void __launch_bounds__(LNZ_THREADS) ln_zero_rows_kernel(const float *
   ss = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
   const float n = (float)E, mean = s / n;
   const float std_ = sqrtf(ss / n - mean * mean + eps);
-  const float4 *g4 = reinterpret_cast<const float4 *>(g), *b4 = reinterpret_cast<const float4 *>(b);
 #pragma unroll
   for (int i = 0; i < LN_MAXV; ++i) {
     const int c = i * LNZ_THREADS + tid;
@@ -187,7 +188,7 @@ void launch_ln_zero_rows(const float *in, void *out, const float *g, const float
 // per element, instead of in mlp c_proj's operand load -- there every weight tile re-applies it to the X chunk it
 // multiplies (12.5x redundant at 1.5B), and the single-pass TF32 kernel needs its transform warps only for that.
 // cfg 4: 8.39 -> 8.18 ms (TF32), 8.94 -> 8.78 ms (3xTF32).
-__global__ void __launch_bounds__(256) gelu_inplace_kernel(float *__restrict__ pre, size_t n4) {
+__global__ void __launch_bounds__(256) gelu_inplace_kernel(float *pre, size_t n4) {
   pdl_trigger();
   pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(256) gelu_inplace_kernel(float *__restrict__ p
 
 // h16 = f16(gelu(pre)): the GELU between c_fc and mlp c_proj (main.zig:80) of the 16-bit decode step, where c_proj's f16
 // operand cannot be produced by c_fc's epilogue (stream-K partial sums).  Exact tanhf GELU (ops.zig:225).
-__global__ void __launch_bounds__(256) gelu_to_f16_kernel(const float *__restrict__ pre, __half *__restrict__ out, size_t n4) {
+__global__ void __launch_bounds__(256) gelu_to_f16_kernel(const float *pre, __half *out, size_t n4) {  // (no __restrict__: PDL note)
   pdl_trigger();
   pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {

@@ -60,6 +60,11 @@ inline void note_alloc() { ctx().alloc_calls++; }
 // pdl_wait() returns once every prerequisite grid has completed and its writes are visible, and must precede the first
 // access to anything an earlier kernel produces and the first global write.  pdl_trigger() lets the NEXT kernel start
 // launching.  Both are no-ops in a kernel launched the ordinary way.
+// PITFALL (found the hard way): data the predecessor writes must NOT be read through a `const T *__restrict__` parameter in
+// a dependent kernel.  Such loads become LDG.CONSTANT (ld.global.nc) of memory the compiler may assume is never written
+// during the kernel, so it is free to hoist them ABOVE the wait despite the "memory" clobber -- the LayerNorm kernel read
+// x while the GEMM before it was still reduce-adding into it (SASS: the first LDG of x sat two instructions before
+// ACQBULK).  Predecessor-produced operands are plain pointers; __restrict__ / __ldg only for data no kernel of the step writes.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
