@@ -36,7 +36,7 @@ def L():
     return lib.init(0)
 
 
-@pytest.mark.parametrize("M,N,K", [(16, 3072, 768), (64, 2304, 768), (192, 768, 3072), (300, 1000, 200), (1024, 50257, 768)])
+@pytest.mark.parametrize("M,N,K", [(16, 3072, 768), (64, 2304, 768), (192, 768, 3072), (300, 1000, 200), (1024, 3072, 768), (1024, 50257, 768)])
 @pytest.mark.parametrize("precision,tol", [(2, FP32_RTOL), (0, TC_RTOL), (1, TC_RTOL)])
 def test_linear_tensor_core_matches_oracle(L, M, N, K, precision, tol):
     import zg_oracle as zo

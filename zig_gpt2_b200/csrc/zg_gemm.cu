@@ -34,12 +34,15 @@ struct Cfg {
   // 3xTF32: every stage holds the W tile twice in shared memory (as landed, and its lo part); the A tile's hi and lo
   // parts live in TMEM (A_COLS columns per stage behind the two accumulators), so the MMAs read only W from shared memory
   static constexpr bool SPLIT = MODE == MODE_TF32X3;
-  static_assert(!SPLIT || BN <= 128, "3xTF32: two accumulators + the A ring must fit 512 TMEM columns");
+  static_assert(!SPLIT || BN <= 192, "3xTF32: the accumulator(s) + the A ring must fit 512 TMEM columns");
+  // accumulator stages: two (the epilogue of a tile overlaps the next tile's main loop); the 192-column 3xTF32 tile has TMEM
+  // for one only and is used where a CTA gets a single tile anyway (gemm_plan)
+  static constexpr int ACC = (SPLIT && BN > 128) ? 1 : 2;
   static constexpr int B_STAGE = BN * ROW_BYTES;
   static constexpr int STAGE = A_STAGE + B_STAGE;  // what TMA writes per stage
   static constexpr int STAGE_ALL = SPLIT ? STAGE + B_STAGE : STAGE;
   static constexpr int A_COLS = 64;  // SPLIT: A_hi in columns 0..31, A_lo in 32..63 (one 32-bit column per K element)
-  static constexpr int MAX_STAGES = SPLIT ? (512 - 2 * BN) / A_COLS : 10;
+  static constexpr int MAX_STAGES = SPLIT ? (512 - ACC * BN) / A_COLS : 10;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_ALL) > MAX_STAGES ? MAX_STAGES : (SMEM_BUDGET / STAGE_ALL);
   static constexpr int TMEM_COLS = SPLIT ? 512 : ((2 * BN) < 32 ? 32 : 2 * BN);  // two accumulator stages (+ the A ring)
   // epilogue warps e and e+4 split the columns; in the 3xTF32 mode warps 6..9 split operands instead
@@ -288,7 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           const uint64_t da = da0 + oa + 2 * k, db = db0 + ob + 2 * k;
           if constexpr (SPLIT) {
             const uint64_t db_lo = db0_lo + ob + 2 * k;
-            const uint32_t ta = tmem + 2 * BN + stage * C::A_COLS + 8 * k;  // 8 K elements per MMA = 8 columns
+            const uint32_t ta = tmem + C::ACC * BN + stage * C::A_COLS + 8 * k;  // 8 K elements per MMA = 8 columns
             tc::umma_ts_u<true>(d, ta + 32, db, idesc, (uint32_t)(((kb - kb0) | k) != 0));  // A_lo W_hi
             tc::umma_ts_u<true>(d, ta, db_lo, idesc, 1u);                                   // A_hi W_lo
             tc::umma_ts_u<true>(d, ta, db, idesc, 1u);                                      // A_hi W_hi
@@ -300,7 +303,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
       if (ok) tc::umma_commit_u(tfull_bar + 8 * acc);  // accumulator complete -> epilogue
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == C::ACC) { acc = 0; acc_phase ^= 1; }
     }
   } else if (SPLIT && warp >= 6) {  // ---------------- operand splitters (3xTF32) ----------------
     const int t = threadIdx.x - 6 * 32;  // 0..127
@@ -323,7 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                          : "r"(arow + ((uint32_t)(c ^ (a_row & 7)) << 4)));
 #pragma unroll
           for (int i = 0; i < 32; ++i) lo[i] = __float_as_uint(__uint_as_float(x[i]) - __uint_as_float(x[i] & 0xffffe000u));
-          const uint32_t ta = tmem + 2 * BN + a_lane_base + stage * C::A_COLS;
+          const uint32_t ta = tmem + C::ACC * BN + a_lane_base + stage * C::A_COLS;
           tc::tmem_st32(ta, x);
           tc::tmem_st32(ta + 32, lo);
         }
@@ -391,7 +394,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(tempty_bar + 8 * acc);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == C::ACC) { acc = 0; acc_phase ^= 1; }
       }
       if (g.tma_out && lane == 0) tc::tma_wait_all0();  // staged chunks fully written before the CTA retires
     }
@@ -658,6 +661,11 @@ void launch_mode(const GemmPlan &p) {
         launch_one<MODE, 256>(p);
         break;
       }
+    case 192:
+      if constexpr (MODE == MODE_TF32X3) {
+        launch_one<MODE, 192>(p);
+        break;
+      }
     case 128: launch_one<MODE, 128>(p); break;
     case 64: launch_one<MODE, 64>(p); break;
     default: launch_one<MODE, 32>(p); break;
@@ -669,6 +677,7 @@ void set_attr_mode() {
     set_attr<MODE, 256>();
     set_attr_pair<MODE>();
   }
+  if constexpr (MODE == MODE_TF32X3) set_attr<MODE, 192>();
   set_attr<MODE, 128>(); set_attr<MODE, 64>(); set_attr<MODE, 32>();
 }
 
@@ -772,6 +781,14 @@ bool gemm_plan(GemmPlan *p, int mode, const void *A, size_t lda, const void *W, 
         if (cand > 128 && mode == MODE_TF32X3) continue;
         if (num_m * ((args.N + cand - 1) / cand) >= need) { bn = cand; break; }
       }
+      if (mode == MODE_TF32X3) {
+        // rounds x shared-memory bytes per k-block (A in and out once, W in, read for the split, lo written, read by three
+        // MMAs): a 192-column tile (one accumulator stage) wins where it turns two rounds of 128 into one -- c_fc of the
+        // 124M decode step at 1024 rows: 192 tiles of 128 on 148 SMs vs 128 tiles of 192
+        const long t128 = (long)num_m * ((args.N + 127) / 128), t192 = (long)num_m * ((args.N + 191) / 192);
+        const long c_now = ((num_m * ((args.N + bn - 1) / bn) + sms - 1) / sms) * (32 + 5 * bn / 8);
+        if (t192 <= sms && t128 > sms && (32 + 5 * 192 / 8) < c_now && args.epi != TC_EPI_RESIDUAL) bn = 192;
+      }
     }
     if (can_split && bn < 128) {
       for (int cand : {128, 64, 32}) {
@@ -784,7 +801,7 @@ bool gemm_plan(GemmPlan *p, int mode, const void *A, size_t lda, const void *W, 
       }
     }
   }
-  if (mode == MODE_TF32X3 && bn > 128) bn = 128;  // an explicit request for 256 columns: the 3xTF32 kernel has no such tile
+  if (mode == MODE_TF32X3 && bn > 192) bn = 128;  // an explicit request for 256 columns: the 3xTF32 kernel has no such tile
   // wide problems: CTA pairs on 256 x 256 tiles (gemm_pair_kernel) when that still gives every pair a tile
   static const bool env_no_pair = getenv("ZG_NO_PAIR") != nullptr;
   const int pair_tiles = ((args.M + 2 * BM - 1) / (2 * BM)) * ((args.N + PAIR_BN - 1) / PAIR_BN);
