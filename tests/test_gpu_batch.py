@@ -320,6 +320,38 @@ def test_batch_forward_argmax_only_equals_logits_argmax(small_model):
     b.close()
 
 
+@pytest.mark.parametrize("tf32", [False, True])
+def test_batch_argmax_head_full_vocabulary(tf32):
+    """The greedy head at the real vocabulary size (50257 rows, not a multiple of any tile): 3xTF32 runs it on the general
+    kernel's 128-column tiles, single-pass TF32 on CTA pairs (256 x 256 tiles whose rows past the batch are TMA zero fill),
+    both with the argmax in the epilogue.  The ids must be the argmax of the logits the same engine writes."""
+    from zig_gpt2_b200 import gpt, lib
+    from zig_gpt2_b200.batch import BatchEngine
+    from zig_gpt2_b200.weights import synth_weights
+
+    cfg = GPTConfig(SIZES["124M"].vocab_size, 64, 2, 12, 768)
+    model = gpt.gpt_from_numpy(cfg, synth_weights(cfg, seed=9))
+    B = 5
+    L = lib.load()
+    toks = np.random.RandomState(8).randint(0, cfg.vocab_size, (4, B))
+    a = BatchEngine(model, B, cache_rows=16, tf32_single_pass=tf32)
+    b = BatchEngine(model, B, cache_rows=16, tf32_single_pass=tf32)
+    n0 = L.zg_tc_pair_launch_count()
+    for s in range(4):
+        a.forward(s + 1, toks[s], 1)
+        b.forward(s + 1, toks[s], 2)
+        lg = a.logits()
+        want = lg.argmax(axis=1)
+        got = b.read_tokens()
+        top2 = np.sort(lg, axis=1)[:, -2:]
+        clear = (top2[:, 1] - top2[:, 0]) > 1e-3 * np.abs(lg).max()  # the two engines' stream-K layer sums differ in the last bits
+        assert np.array_equal(got[clear], want[clear]) and clear.sum() >= B - 1
+    assert (L.zg_tc_pair_launch_count() > n0) == tf32
+    a.close()
+    b.close()
+    model.close()
+
+
 def test_batch_above_128_sequences_uses_the_general_kernel(small_model):
     from zig_gpt2_b200.batch import BatchEngine
 
